@@ -1,0 +1,216 @@
+/*
+ * jfx.h — C ABI of the B200-native tensor-product spectral transform engine.
+ *
+ * This is the drop-in boundary for ONE path of spectralDNS/jaxfun: the
+ * OrthogonalSpace / TensorProductSpace forward, backward, scalar_product and
+ * backward_primitive transforms plus the pseudo-spectral nonlinear-term
+ * evaluation the integrators call every stage.  The reference has no FFI of its
+ * own (it is 100 % Python on JAX); each entry point below names the reference
+ * Python interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, POD structs; no C++/torch/XLA types.
+ *  - every function returns 0 (JFX_OK) or a negative jfx_status; the message of
+ *    the last failure on the calling thread is available via jfx_last_error().
+ *  - arrays are dense, row-major (C order); complex = interleaved (re, im).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - jfx_execute* never allocates, never synchronises the device and is safe to
+ *    capture into a CUDA graph.  Plans are immutable after creation and may be
+ *    executed concurrently from several host threads with distinct workspaces.
+ *  - there is no CPU fallback: without a CUDA device every compute entry point
+ *    fails with JFX_ERR_CUDA.
+ */
+#ifndef JFX_H_
+#define JFX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JFX_ABI_VERSION 1
+#define JFX_MAX_DIMS 4      /* up to 3 transformed axes + 1 leading batch axis */
+#define JFX_MAX_LEAVES 8    /* backward_primitive leaves of one nonlinear term  */
+#define JFX_MAX_PROGRAM 128 /* pointwise bytecode length                        */
+
+typedef enum {
+  JFX_OK = 0,
+  JFX_ERR_INVALID = -1,     /* bad descriptor / argument                        */
+  JFX_ERR_UNSUPPORTED = -2, /* valid request the engine cannot run              */
+  JFX_ERR_CUDA = -3,        /* CUDA runtime / driver error (incl. no device)    */
+  JFX_ERR_NOMEM = -4,
+  JFX_ERR_COMM = -5         /* slab exchange failure                            */
+} jfx_status;
+
+typedef enum { JFX_F32 = 0, JFX_F64 = 1, JFX_C64 = 2, JFX_C128 = 3 } jfx_dtype;
+
+/* Which reference method the plan reproduces. */
+typedef enum {
+  JFX_OP_FORWARD = 0,            /* OrthogonalSpace.forward       galerkin/orthogonal.py:256-262;
+                                    TensorProductSpace.forward     galerkin/tensorproductspace.py:395-417 */
+  JFX_OP_SCALAR_PRODUCT = 1,     /* OrthogonalSpace.scalar_product orthogonal.py:264-277;
+                                    TensorProductSpace.scalar_product tensorproductspace.py:367-393       */
+  JFX_OP_BACKWARD = 2,           /* OrthogonalSpace.backward      orthogonal.py:214-227;
+                                    TensorProductSpace.backward    tensorproductspace.py:330-365          */
+  JFX_OP_BACKWARD_PRIMITIVE = 3, /* backward_primitive            orthogonal.py:229-246;
+                                    tensorproductspace.py:419-460                                         */
+  JFX_OP_NONLINEAR = 4,          /* BaseIntegrator.nonlinear_rhs / nonlinear_rhs_scalar_product
+                                    integrators/base.py:230-248 + integrators/nonlinear.py:89-217         */
+  JFX_OP_APPLY = 5               /* generic per-axis table apply (to_orthogonal / evaluate_mesh(uniform) /
+                                    eigenvector solves: tensorproductspace.py:462-504, orthogonal.py:180-199) */
+} jfx_op;
+
+/* 1-D basis family of one tensor axis. */
+typedef enum {
+  JFX_BASIS_NONE = 0,       /* axis is not transformed (batch axis)                                */
+  JFX_BASIS_TABLE = 1,      /* dense real table supplied by the host: Legendre / Jacobi /
+                               Ultraspherical Vandermonde contraction (orthogonal.py:277,
+                               Jacobi.py:65-110), or any basis at a size with no fast kernel      */
+  JFX_BASIS_CTABLE = 2,     /* dense complex table (Fourier at lengths without an FFT kernel)      */
+  JFX_BASIS_CHEBYSHEV = 3,  /* DCT-II / DCT-III fast path     galerkin/Chebyshev.py:225-279        */
+  JFX_BASIS_FOURIER = 4     /* c2c FFT fast path              galerkin/Fourier.py:126-180          */
+} jfx_basis;
+
+typedef struct {
+  int32_t basis;         /* jfx_basis                                                            */
+  int32_t n_modes;       /* N: number of spectral coefficients kept along this axis              */
+  int32_t n_quad;        /* n: number of quadrature points (>= n_modes; > means padding)         */
+  int32_t deriv;         /* derivative order k of backward_primitive along this axis (else 0)    */
+  double domain_factor;  /* df = reference length / true length (orthogonal.py:343-354)          */
+  /* JFX_BASIS_TABLE / CTABLE: host pointer to the row-major table [n_out, n_in] that maps the
+     axis (n_in -> n_out).  All weights / norms / derivative factors are already folded in by the
+     host (it is the constant the reference rebuilds inside every jitted call).  The engine copies
+     it to the device at plan creation; the caller may free it afterwards.  NULL for fast bases.  */
+  const void* table;
+  int32_t table_rows;    /* n_out */
+  int32_t table_cols;    /* n_in  */
+} jfx_axis_desc;
+
+/* Pointwise bytecode of a nonlinear term (integrators/nonlinear.py:135-217).  A tiny stack
+   machine evaluated per quadrature point over the leaf values.                                 */
+typedef enum {
+  JFX_PW_LEAF = 0,   /* push leaf[arg]                       */
+  JFX_PW_CONST = 1,  /* push consts[arg] (complex constant)  */
+  JFX_PW_ADD = 2,
+  JFX_PW_MUL = 3,
+  JFX_PW_POWI = 4,   /* top <- top ** arg (integer, may be negative) */
+  JFX_PW_ABS = 5,    /* |top| (real result)                  */
+  JFX_PW_NEG = 6,
+  JFX_PW_FUNC = 7,   /* top <- func[arg](top): see jfx_pw_func */
+  JFX_PW_POWR = 8,   /* top <- top ** consts[arg].re         */
+  JFX_PW_CONJ = 9,
+  JFX_PW_STATIC = 10 /* push statics[arg][point] (mesh-sampled coefficient, nonlinear.py:219-242) */
+} jfx_pw_opcode;
+
+typedef enum {
+  JFX_FN_EXP = 0, JFX_FN_LOG, JFX_FN_SIN, JFX_FN_COS, JFX_FN_TAN, JFX_FN_SINH, JFX_FN_COSH,
+  JFX_FN_TANH, JFX_FN_SQRT, JFX_FN_SIGN, JFX_FN_HEAVISIDE, JFX_FN_ASIN, JFX_FN_ACOS, JFX_FN_ATAN,
+  JFX_FN_ASINH, JFX_FN_ACOSH, JFX_FN_ATANH, JFX_FN_RE, JFX_FN_IM
+} jfx_pw_func;
+
+typedef struct { int32_t op; int32_t arg; } jfx_pw_instr;
+
+typedef struct {
+  int32_t abi_version;            /* JFX_ABI_VERSION                                             */
+  int32_t op;                     /* jfx_op                                                      */
+  int32_t dtype;                  /* jfx_dtype of input and output arrays                        */
+  int32_t ndim;                   /* number of array axes, 1..JFX_MAX_DIMS                       */
+  int64_t shape_in[JFX_MAX_DIMS]; /* input array shape                                           */
+  jfx_axis_desc axis[JFX_MAX_DIMS];
+  /* --- slab decomposition (sharding.py:43-105); size 1 = single device ------------------- */
+  int32_t slab_rank;
+  int32_t slab_size;
+  int32_t reserved[14];
+} jfx_plan_desc;
+
+/* Nonlinear term  F(uh) = T( E( leaf_0(uh), leaf_1(uh), ... ) )  (integrators/base.py:230-248):
+   every leaf is a BACKWARD / BACKWARD_PRIMITIVE plan on the same coefficient array, E the pointwise
+   program over the leaves, T a FORWARD or SCALAR_PRODUCT plan on the physical array. */
+typedef struct {
+  int32_t abi_version;
+  int32_t n_leaves;
+  const jfx_plan_desc* leaves[JFX_MAX_LEAVES];
+  const jfx_plan_desc* final_transform;
+  int32_t n_program;
+  jfx_pw_instr program[JFX_MAX_PROGRAM];
+  int32_t n_consts;
+  double consts[32][2];
+  int32_t n_statics;               /* mesh-sampled static coefficients (device pointers, physical shape) */
+  const void* statics[JFX_MAX_LEAVES];
+  int32_t reserved[8];
+} jfx_nonlinear_desc;
+
+typedef struct jfx_plan jfx_plan;
+typedef struct jfx_nonlinear jfx_nonlinear;
+
+/* Library / device ------------------------------------------------------------------------ */
+int jfx_abi_version(void);
+const char* jfx_last_error(void);
+/* Number of visible CUDA devices (0 on a CPU-only host; never fails). */
+int jfx_device_count(void);
+/* 1 when `basis` has a fast (FFT / DCT) kernel at transform length n for `dtype`, else 0. */
+int jfx_fast_path_available(int basis, int n, int dtype);
+
+/* Plans ------------------------------------------------------------------------------------ */
+int jfx_plan_create(const jfx_plan_desc* desc, jfx_plan** out);
+void jfx_plan_destroy(jfx_plan* plan);
+int jfx_plan_ndim(const jfx_plan* plan);
+int jfx_plan_shape_out(const jfx_plan* plan, int64_t* shape_out /* [JFX_MAX_DIMS] */);
+int jfx_plan_workspace_bytes(const jfx_plan* plan, size_t* bytes);
+/* Algorithmic work of one execution: flops of dense contractions and the compulsory
+   bytes (input read once + output written once). */
+int jfx_plan_work(const jfx_plan* plan, double* flops, double* bytes);
+/* Number of kernel launches one jfx_execute enqueues. */
+int jfx_plan_launches(const jfx_plan* plan);
+
+/* Execution: device pointers, enqueued on `stream`, no host synchronisation.
+   `workspace` must hold jfx_plan_workspace_bytes() bytes (may be NULL when that is 0).
+   `in` is never written; `out` must not alias `in` or `workspace`. */
+int jfx_execute(const jfx_plan* plan, void* stream, const void* in, void* out, void* workspace);
+
+/* Convenience for host callers (the reference-facing e2e path): copies `in` (host) to the
+   device, runs the plan and copies the result back into `out` (host); synchronises `stream`.
+   Device buffers are owned and cached by the plan (first call allocates). */
+int jfx_execute_host(jfx_plan* plan, void* stream, const void* in_host, void* out_host);
+
+/* Pinned host buffers for the host-pointer path (cudaHostAlloc / cudaFreeHost). */
+int jfx_host_alloc(void** ptr, size_t bytes);
+int jfx_host_free(void* ptr);
+
+/* Nonlinear-term evaluation: uh (coefficients, device) -> out (coefficients, device). */
+int jfx_nonlinear_create(const jfx_nonlinear_desc* desc, jfx_nonlinear** out);
+void jfx_nonlinear_destroy(jfx_nonlinear* nl);
+int jfx_nonlinear_workspace_bytes(const jfx_nonlinear* nl, size_t* bytes);
+int jfx_nonlinear_shape_out(const jfx_nonlinear* nl, int64_t* shape_out, int* ndim);
+int jfx_nonlinear_launches(const jfx_nonlinear* nl);
+int jfx_nonlinear_execute(const jfx_nonlinear* nl, void* stream, const void* uh, void* out,
+                          void* workspace);
+
+/* Standalone pointwise evaluation of a program over n points (leaves/statics: device arrays). */
+int jfx_pointwise(void* stream, const jfx_pw_instr* program, int n_program, const double (*consts)[2],
+                  int n_consts, const void* const* leaves, int n_leaves, const void* const* statics,
+                  void* out, int64_t n, int dtype);
+
+/* Slab exchange (sharding.py:83-89): local pack / unpack kernels around the all-to-all.
+   block p of the send buffer = x[.., split slice p, ..] so that an all-to-all of equal blocks
+   followed by concatenation along `concat_axis` reproduces lax.all_to_all(tiled=True). */
+int jfx_slab_pack(void* stream, const void* in, void* out, const int64_t* shape, int ndim,
+                  int split_axis, int parts, int dtype);
+int jfx_slab_unpack(void* stream, const void* in, void* out, const int64_t* shape_out, int ndim,
+                    int concat_axis, int parts, int dtype);
+
+/* Stage arithmetic of the integrators (etdrk4.py:152-166, rk4.py:14-20): out = sum_i c_i * x_i with
+   per-element diagonal coefficients c_i (or NULL = 1) scaled by alpha_i.  Complex or real. */
+int jfx_axpby_diag(void* stream, int n_terms, const void* const* coeff, const double* alpha,
+                   const void* const* x, void* out, int64_t n, int dtype, int coeff_is_complex);
+
+/* Calibration helpers used by bench.py (not on the product path). */
+int jfx_calibrate_dmma(void* stream, int iters, double* tflops);
+int jfx_calibrate_dfma(void* stream, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JFX_H_ */

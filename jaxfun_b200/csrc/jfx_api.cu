@@ -1,0 +1,458 @@
+// C ABI of the jfx engine: plan construction, execution, nonlinear-term composition.
+// See include/jfx.h for the contract of every entry point.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <memory>
+#include <mutex>
+
+#include "jfx_common.h"
+
+namespace jfx {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+struct Pass {
+  int axis = 0;
+  AxisGeom geom{};
+  bool fast = false;
+  void* d_table = nullptr;  // owned
+  bool table_complex = false;
+  bool dmma = false;
+  FastParams fp{};
+  FastTables* ft = nullptr;  // owned
+};
+
+}  // namespace jfx
+
+struct jfx_plan {
+  jfx_plan_desc desc{};
+  int ndim = 0;
+  int64_t shape_in[JFX_MAX_DIMS]{};
+  int64_t shape_out[JFX_MAX_DIMS]{};
+  std::vector<jfx::Pass> passes;
+  size_t buf_bytes = 0;  // one ping-pong buffer
+  size_t ws_bytes = 0;
+  double flops = 0, bytes = 0;
+  // host-pointer path (lazy, guarded)
+  std::mutex host_mu;
+  void* h_in = nullptr;
+  void* h_out = nullptr;
+  void* h_ws = nullptr;
+  ~jfx_plan() {
+    for (auto& p : passes) {
+      if (p.d_table) cudaFree(p.d_table);
+      if (p.ft) jfx::fast_tables_destroy(p.ft);
+    }
+    if (h_in) cudaFree(h_in);
+    if (h_out) cudaFree(h_out);
+    if (h_ws) cudaFree(h_ws);
+  }
+};
+
+namespace jfx {
+
+static int64_t prod(const int64_t* s, int a, int b) {
+  int64_t p = 1;
+  for (int i = a; i < b; ++i) p *= s[i];
+  return p;
+}
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
+  JFX_REQUIRE(d->abi_version == JFX_ABI_VERSION, JFX_ERR_INVALID, "ABI version %d != %d", d->abi_version,
+              JFX_ABI_VERSION);
+  JFX_REQUIRE(d->ndim >= 1 && d->ndim <= JFX_MAX_DIMS, JFX_ERR_INVALID, "ndim %d out of range", d->ndim);
+  JFX_REQUIRE(d->dtype >= JFX_F32 && d->dtype <= JFX_C128, JFX_ERR_INVALID, "bad dtype %d", d->dtype);
+  JFX_REQUIRE(d->op >= JFX_OP_FORWARD && d->op <= JFX_OP_APPLY && d->op != JFX_OP_NONLINEAR, JFX_ERR_INVALID,
+              "bad op %d (nonlinear terms use jfx_nonlinear_create)", d->op);
+  JFX_REQUIRE(d->slab_size <= 1, JFX_ERR_UNSUPPORTED,
+              "slab plans are composed by the host from two local plans + jfx_slab_pack/unpack");
+  pl->desc = *d;
+  pl->ndim = d->ndim;
+  const bool to_physical = (d->op == JFX_OP_BACKWARD || d->op == JFX_OP_BACKWARD_PRIMITIVE);
+  int64_t cur[JFX_MAX_DIMS];
+  for (int i = 0; i < d->ndim; ++i) {
+    JFX_REQUIRE(d->shape_in[i] >= 0, JFX_ERR_INVALID, "negative extent");
+    cur[i] = pl->shape_in[i] = d->shape_in[i];
+  }
+  const size_t es = dtype_size(d->dtype);
+  size_t max_inter = 0;
+  pl->flops = 0;
+  const int64_t in_elems = prod(cur, 0, d->ndim);
+
+  for (int ax = 0; ax < d->ndim; ++ax) {
+    const jfx_axis_desc& a = d->axis[ax];
+    if (a.basis == JFX_BASIS_NONE) continue;
+    Pass p;
+    p.axis = ax;
+    int n_in = (int)cur[ax], n_out;
+    if (a.basis == JFX_BASIS_TABLE || a.basis == JFX_BASIS_CTABLE) {
+      JFX_REQUIRE(a.table != nullptr, JFX_ERR_INVALID, "axis %d: table basis without a table", ax);
+      JFX_REQUIRE(a.table_cols == n_in, JFX_ERR_INVALID, "axis %d: table has %d columns, array extent is %d", ax,
+                  a.table_cols, n_in);
+      JFX_REQUIRE(a.table_rows >= 0, JFX_ERR_INVALID, "axis %d: negative table rows", ax);
+      n_out = a.table_rows;
+      p.table_complex = (a.basis == JFX_BASIS_CTABLE);
+      JFX_REQUIRE(!(p.table_complex && !dtype_is_complex(d->dtype)), JFX_ERR_INVALID,
+                  "axis %d: complex table needs a complex array dtype", ax);
+      const size_t tes = (dtype_is_double(d->dtype) ? 8 : 4) * (p.table_complex ? 2 : 1);
+      const size_t tbytes = (size_t)n_out * n_in * tes;
+      if (tbytes) {
+        JFX_CUDA_OK(cudaMalloc(&p.d_table, tbytes));
+        // the host table is always double precision; narrow for f32 plans
+        if (dtype_is_double(d->dtype)) {
+          JFX_CUDA_OK(cudaMemcpy(p.d_table, a.table, tbytes, cudaMemcpyHostToDevice));
+        } else {
+          const size_t cnt = (size_t)n_out * n_in * (p.table_complex ? 2 : 1);
+          std::vector<float> tmp(cnt);
+          const double* src = (const double*)a.table;
+          for (size_t i = 0; i < cnt; ++i) tmp[i] = (float)src[i];
+          JFX_CUDA_OK(cudaMemcpy(p.d_table, tmp.data(), tbytes, cudaMemcpyHostToDevice));
+        }
+      }
+    } else if (a.basis == JFX_BASIS_CHEBYSHEV || a.basis == JFX_BASIS_FOURIER) {
+      JFX_REQUIRE(d->op != JFX_OP_APPLY, JFX_ERR_INVALID, "axis %d: APPLY plans take table bases only", ax);
+      JFX_REQUIRE(a.n_quad >= a.n_modes && a.n_modes >= 1, JFX_ERR_INVALID, "axis %d: need n_quad >= n_modes >= 1", ax);
+      JFX_REQUIRE(!(a.basis == JFX_BASIS_FOURIER && !dtype_is_complex(d->dtype)), JFX_ERR_INVALID,
+                  "axis %d: Fourier axes need a complex array dtype", ax);
+      JFX_REQUIRE(fast_available(a.basis, a.n_quad, d->dtype), JFX_ERR_UNSUPPORTED,
+                  "axis %d: no fast kernel for basis %d at n=%d; supply a dense table instead", ax, a.basis, a.n_quad);
+      p.fast = true;
+      const bool cheb = a.basis == JFX_BASIS_CHEBYSHEV;
+      if (to_physical) {
+        JFX_REQUIRE(n_in <= a.n_modes, JFX_ERR_INVALID, "axis %d: %d coefficients > n_modes %d", ax, n_in, a.n_modes);
+        n_out = a.n_quad;
+        p.fp.kind = cheb ? FAST_CHEB_BACKWARD : FAST_FOURIER_BACKWARD;
+        p.fp.n_modes = n_in;
+      } else {
+        JFX_REQUIRE(n_in == a.n_quad, JFX_ERR_INVALID, "axis %d: physical extent %d != n_quad %d", ax, n_in, a.n_quad);
+        n_out = a.n_modes;
+        const bool sp = d->op == JFX_OP_SCALAR_PRODUCT;
+        p.fp.kind = cheb ? (sp ? FAST_CHEB_SCALAR : FAST_CHEB_FORWARD) : (sp ? FAST_FOURIER_SCALAR : FAST_FOURIER_FORWARD);
+        p.fp.n_modes = a.n_modes;
+      }
+      p.fp.n_quad = a.n_quad;
+      p.fp.deriv = (d->op == JFX_OP_BACKWARD_PRIMITIVE) ? a.deriv : 0;
+      p.fp.domain_factor = a.domain_factor;
+      int rc = fast_tables_create(p.fp, d->dtype, &p.ft);
+      if (rc != JFX_OK) return rc;
+    } else {
+      set_error("axis %d: unknown basis %d", ax, a.basis);
+      return JFX_ERR_INVALID;
+    }
+    p.geom.outer = prod(cur, 0, ax);
+    p.geom.inner = prod(cur, ax + 1, d->ndim);
+    p.geom.n_in = n_in;
+    p.geom.n_out = n_out;
+    if (!p.fast) {
+      p.dmma = table_apply_uses_dmma(p.geom, d->dtype, p.table_complex);
+      const double cm = dtype_is_complex(d->dtype) ? (p.table_complex ? 4.0 : 2.0) : 1.0;
+      pl->flops += 2.0 * cm * (double)p.geom.outer * p.geom.inner * (double)n_in * n_out;
+    }
+    cur[ax] = n_out;
+    max_inter = std::max(max_inter, (size_t)prod(cur, 0, d->ndim) * es);
+    pl->passes.push_back(p);
+  }
+  for (int i = 0; i < d->ndim; ++i) pl->shape_out[i] = cur[i];
+  const int64_t out_elems = prod(cur, 0, d->ndim);
+  pl->bytes = (double)es * ((double)in_elems + (double)out_elems);
+  pl->buf_bytes = pl->passes.size() > 1 ? align_up(max_inter, 256) : 0;
+  pl->ws_bytes = pl->passes.size() > 2 ? 2 * pl->buf_bytes : pl->buf_bytes;
+  return JFX_OK;
+}
+
+static int run_pass(cudaStream_t s, const Pass& p, int dtype, const void* src, void* dst) {
+  if (p.fast) return launch_fast_axis(s, p.geom, dtype, p.fp, p.ft, src, dst);
+  return launch_table_apply(s, p.geom, dtype, p.d_table, p.table_complex, src, dst, nullptr);
+}
+
+static int execute_plan(const jfx_plan* pl, cudaStream_t s, const void* in, void* out, void* ws) {
+  const size_t np = pl->passes.size();
+  const size_t es = dtype_size(pl->desc.dtype);
+  if (np == 0) {
+    const size_t bytes = (size_t)prod(pl->shape_in, 0, pl->ndim) * es;
+    if (bytes) JFX_CUDA_OK(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, s));
+    return JFX_OK;
+  }
+  JFX_REQUIRE(pl->ws_bytes == 0 || ws != nullptr, JFX_ERR_INVALID, "plan needs a %zu byte workspace", pl->ws_bytes);
+  char* w0 = (char*)ws;
+  char* w1 = w0 + pl->buf_bytes;
+  const void* src = in;
+  for (size_t i = 0; i < np; ++i) {
+    void* dst = (i + 1 == np) ? out : (void*)((i & 1) ? w1 : w0);
+    int rc = run_pass(s, pl->passes[i], pl->desc.dtype, src, dst);
+    if (rc != JFX_OK) return rc;
+    src = dst;
+  }
+  return JFX_OK;
+}
+
+}  // namespace jfx
+
+// =================================================================================================
+struct jfx_nonlinear {
+  std::vector<jfx_plan*> leaves;
+  jfx_plan* final_plan = nullptr;
+  jfx::PointwiseProgram prog{};
+  const void* statics[JFX_MAX_LEAVES]{};
+  int dtype = JFX_F64;
+  int64_t phys_elems = 0;
+  size_t field_bytes = 0;  // one physical field, aligned
+  size_t sub_ws = 0;       // max workspace of the sub-plans
+  size_t ws_bytes = 0;
+  ~jfx_nonlinear() {
+    for (auto* p : leaves) delete p;
+    delete final_plan;
+  }
+};
+
+extern "C" {
+
+int jfx_abi_version(void) { return JFX_ABI_VERSION; }
+const char* jfx_last_error(void) { return jfx::get_error(); }
+
+int jfx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int jfx_fast_path_available(int basis, int n, int dtype) { return jfx::fast_available(basis, n, dtype) ? 1 : 0; }
+
+int jfx_plan_create(const jfx_plan_desc* desc, jfx_plan** out) {
+  using namespace jfx;
+  JFX_REQUIRE(desc && out, JFX_ERR_INVALID, "null argument");
+  *out = nullptr;
+  JFX_REQUIRE(jfx_device_count() > 0, JFX_ERR_CUDA, "no CUDA device: the jfx engine has no CPU fallback");
+  std::unique_ptr<jfx_plan> pl(new (std::nothrow) jfx_plan);
+  JFX_REQUIRE(pl, JFX_ERR_NOMEM, "out of host memory");
+  int rc = build_plan(desc, pl.get());
+  if (rc != JFX_OK) return rc;
+  // tables were copied: do not keep dangling host pointers
+  for (int i = 0; i < JFX_MAX_DIMS; ++i) pl->desc.axis[i].table = nullptr;
+  *out = pl.release();
+  return JFX_OK;
+}
+
+void jfx_plan_destroy(jfx_plan* plan) { delete plan; }
+
+int jfx_plan_ndim(const jfx_plan* plan) { return plan ? plan->ndim : JFX_ERR_INVALID; }
+
+int jfx_plan_shape_out(const jfx_plan* plan, int64_t* shape_out) {
+  using namespace jfx;
+  JFX_REQUIRE(plan && shape_out, JFX_ERR_INVALID, "null argument");
+  for (int i = 0; i < JFX_MAX_DIMS; ++i) shape_out[i] = i < plan->ndim ? plan->shape_out[i] : 1;
+  return JFX_OK;
+}
+
+int jfx_plan_workspace_bytes(const jfx_plan* plan, size_t* bytes) {
+  using namespace jfx;
+  JFX_REQUIRE(plan && bytes, JFX_ERR_INVALID, "null argument");
+  *bytes = plan->ws_bytes;
+  return JFX_OK;
+}
+
+int jfx_plan_work(const jfx_plan* plan, double* flops, double* bytes) {
+  using namespace jfx;
+  JFX_REQUIRE(plan, JFX_ERR_INVALID, "null argument");
+  if (flops) *flops = plan->flops;
+  if (bytes) *bytes = plan->bytes;
+  return JFX_OK;
+}
+
+int jfx_plan_launches(const jfx_plan* plan) {
+  if (!plan) return JFX_ERR_INVALID;
+  return plan->passes.empty() ? 0 : (int)plan->passes.size();
+}
+
+int jfx_execute(const jfx_plan* plan, void* stream, const void* in, void* out, void* workspace) {
+  using namespace jfx;
+  JFX_REQUIRE(plan && in && out, JFX_ERR_INVALID, "null argument");
+  return execute_plan(plan, (cudaStream_t)stream, in, out, workspace);
+}
+
+int jfx_execute_host(jfx_plan* plan, void* stream, const void* in_host, void* out_host) {
+  using namespace jfx;
+  JFX_REQUIRE(plan && in_host && out_host, JFX_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(plan->host_mu);
+  const size_t es = dtype_size(plan->desc.dtype);
+  const size_t in_b = (size_t)prod(plan->shape_in, 0, plan->ndim) * es;
+  const size_t out_b = (size_t)prod(plan->shape_out, 0, plan->ndim) * es;
+  if (!plan->h_in && in_b) JFX_CUDA_OK(cudaMalloc(&plan->h_in, in_b));
+  if (!plan->h_out && out_b) JFX_CUDA_OK(cudaMalloc(&plan->h_out, out_b));
+  if (!plan->h_ws && plan->ws_bytes) JFX_CUDA_OK(cudaMalloc(&plan->h_ws, plan->ws_bytes));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (in_b) JFX_CUDA_OK(cudaMemcpyAsync(plan->h_in, in_host, in_b, cudaMemcpyHostToDevice, s));
+  if (in_b && out_b) {
+    int rc = execute_plan(plan, s, plan->h_in, plan->h_out, plan->h_ws);
+    if (rc != JFX_OK) return rc;
+  }
+  if (out_b) JFX_CUDA_OK(cudaMemcpyAsync(out_host, plan->h_out, out_b, cudaMemcpyDeviceToHost, s));
+  JFX_CUDA_OK(cudaStreamSynchronize(s));
+  return JFX_OK;
+}
+
+int jfx_host_alloc(void** ptr, size_t bytes) {
+  using namespace jfx;
+  JFX_REQUIRE(ptr, JFX_ERR_INVALID, "null argument");
+  JFX_CUDA_OK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return JFX_OK;
+}
+int jfx_host_free(void* ptr) {
+  using namespace jfx;
+  if (ptr) JFX_CUDA_OK(cudaFreeHost(ptr));
+  return JFX_OK;
+}
+
+// ---- nonlinear terms -----------------------------------------------------------------------
+int jfx_nonlinear_create(const jfx_nonlinear_desc* d, jfx_nonlinear** out) {
+  using namespace jfx;
+  JFX_REQUIRE(d && out, JFX_ERR_INVALID, "null argument");
+  *out = nullptr;
+  JFX_REQUIRE(d->abi_version == JFX_ABI_VERSION, JFX_ERR_INVALID, "ABI version mismatch");
+  JFX_REQUIRE(d->n_leaves >= 1 && d->n_leaves <= JFX_MAX_LEAVES, JFX_ERR_INVALID, "n_leaves must be 1..%d", JFX_MAX_LEAVES);
+  JFX_REQUIRE(d->final_transform, JFX_ERR_INVALID, "missing final transform");
+  JFX_REQUIRE(d->n_program >= 1 && d->n_program <= JFX_MAX_PROGRAM, JFX_ERR_INVALID, "bad program length");
+  JFX_REQUIRE(d->n_consts >= 0 && d->n_consts <= 32, JFX_ERR_INVALID, "bad constant count");
+  std::unique_ptr<jfx_nonlinear> nl(new (std::nothrow) jfx_nonlinear);
+  JFX_REQUIRE(nl, JFX_ERR_NOMEM, "out of host memory");
+  for (int l = 0; l < d->n_leaves; ++l) {
+    JFX_REQUIRE(d->leaves[l], JFX_ERR_INVALID, "leaf %d missing", l);
+    JFX_REQUIRE(d->leaves[l]->op == JFX_OP_BACKWARD || d->leaves[l]->op == JFX_OP_BACKWARD_PRIMITIVE,
+                JFX_ERR_INVALID, "leaf %d must be a backward transform", l);
+    jfx_plan* p = nullptr;
+    int rc = jfx_plan_create(d->leaves[l], &p);
+    if (rc != JFX_OK) return rc;
+    nl->leaves.push_back(p);
+  }
+  JFX_REQUIRE(d->final_transform->op == JFX_OP_FORWARD || d->final_transform->op == JFX_OP_SCALAR_PRODUCT,
+              JFX_ERR_INVALID, "final transform must be forward or scalar_product");
+  int rc = jfx_plan_create(d->final_transform, &nl->final_plan);
+  if (rc != JFX_OK) return rc;
+  nl->dtype = d->final_transform->dtype;
+  const jfx_plan* f = nl->final_plan;
+  nl->phys_elems = prod(f->shape_in, 0, f->ndim);
+  for (auto* p : nl->leaves) {
+    JFX_REQUIRE(p->desc.dtype == nl->dtype, JFX_ERR_INVALID, "leaf dtype differs from final transform dtype");
+    JFX_REQUIRE(p->ndim == f->ndim, JFX_ERR_INVALID, "leaf rank differs");
+    for (int i = 0; i < f->ndim; ++i)
+      JFX_REQUIRE(p->shape_out[i] == f->shape_in[i], JFX_ERR_INVALID, "leaf physical shape differs on axis %d", i);
+    for (int i = 0; i < f->ndim; ++i)
+      JFX_REQUIRE(p->shape_in[i] == nl->leaves[0]->shape_in[i], JFX_ERR_INVALID, "leaf coefficient shapes differ");
+    nl->sub_ws = std::max(nl->sub_ws, p->ws_bytes);
+  }
+  nl->sub_ws = std::max(nl->sub_ws, f->ws_bytes);
+  nl->prog.n_instr = d->n_program;
+  memcpy(nl->prog.instr, d->program, sizeof(jfx_pw_instr) * d->n_program);
+  nl->prog.n_consts = d->n_consts;
+  memcpy(nl->prog.consts, d->consts, sizeof(d->consts));
+  nl->prog.n_leaves = d->n_leaves;
+  for (int i = 0; i < JFX_MAX_LEAVES; ++i) nl->statics[i] = i < d->n_statics ? d->statics[i] : nullptr;
+  nl->field_bytes = align_up((size_t)nl->phys_elems * dtype_size(nl->dtype), 256);
+  // workspace = leaf fields + pointwise result + sub-plan workspace
+  nl->ws_bytes = (size_t)(d->n_leaves + 1) * nl->field_bytes + align_up(nl->sub_ws, 256);
+  *out = nl.release();
+  return JFX_OK;
+}
+
+void jfx_nonlinear_destroy(jfx_nonlinear* nl) { delete nl; }
+
+int jfx_nonlinear_workspace_bytes(const jfx_nonlinear* nl, size_t* bytes) {
+  using namespace jfx;
+  JFX_REQUIRE(nl && bytes, JFX_ERR_INVALID, "null argument");
+  *bytes = nl->ws_bytes;
+  return JFX_OK;
+}
+
+int jfx_nonlinear_shape_out(const jfx_nonlinear* nl, int64_t* shape_out, int* ndim) {
+  using namespace jfx;
+  JFX_REQUIRE(nl && shape_out, JFX_ERR_INVALID, "null argument");
+  if (ndim) *ndim = nl->final_plan->ndim;
+  return jfx_plan_shape_out(nl->final_plan, shape_out);
+}
+
+int jfx_nonlinear_launches(const jfx_nonlinear* nl) {
+  if (!nl) return JFX_ERR_INVALID;
+  int n = 1 + jfx_plan_launches(nl->final_plan);
+  for (auto* p : nl->leaves) n += std::max(1, jfx_plan_launches(p));
+  return n;
+}
+
+int jfx_nonlinear_execute(const jfx_nonlinear* nl, void* stream, const void* uh, void* out, void* workspace) {
+  using namespace jfx;
+  JFX_REQUIRE(nl && uh && out && workspace, JFX_ERR_INVALID, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  char* base = (char*)workspace;
+  const size_t nleaf = nl->leaves.size();
+  char* sub = base + (nleaf + 1) * nl->field_bytes;
+  const void* fields[JFX_MAX_LEAVES];
+  for (size_t l = 0; l < nleaf; ++l) {
+    void* f = base + l * nl->field_bytes;
+    int rc = execute_plan(nl->leaves[l], s, uh, f, sub);
+    if (rc != JFX_OK) return rc;
+    fields[l] = f;
+  }
+  void* e = base + nleaf * nl->field_bytes;
+  int rc = launch_pointwise(s, nl->prog, fields, nl->statics, e, nl->phys_elems, nl->dtype);
+  if (rc != JFX_OK) return rc;
+  return execute_plan(nl->final_plan, s, e, out, sub);
+}
+
+int jfx_pointwise(void* stream, const jfx_pw_instr* program, int n_program, const double (*consts)[2],
+                  int n_consts, const void* const* leaves, int n_leaves, const void* const* statics,
+                  void* out, int64_t n, int dtype) {
+  using namespace jfx;
+  JFX_REQUIRE(program && leaves && out, JFX_ERR_INVALID, "null argument");
+  JFX_REQUIRE(n_program >= 1 && n_program <= JFX_MAX_PROGRAM, JFX_ERR_INVALID, "bad program length");
+  JFX_REQUIRE(n_consts >= 0 && n_consts <= 32 && n_leaves >= 0 && n_leaves <= JFX_MAX_LEAVES, JFX_ERR_INVALID, "bad counts");
+  PointwiseProgram p{};
+  p.n_instr = n_program;
+  memcpy(p.instr, program, sizeof(jfx_pw_instr) * n_program);
+  p.n_consts = n_consts;
+  if (n_consts) memcpy(p.consts, consts, sizeof(double) * 2 * n_consts);
+  p.n_leaves = n_leaves;
+  return launch_pointwise((cudaStream_t)stream, p, leaves, statics, out, n, dtype);
+}
+
+// ---- slab / stage arithmetic / calibration ---------------------------------------------------
+int jfx_slab_pack(void* stream, const void* in, void* out, const int64_t* shape, int ndim, int split_axis,
+                  int parts, int dtype) {
+  using namespace jfx;
+  JFX_REQUIRE(in && out && shape, JFX_ERR_INVALID, "null argument");
+  return launch_slab_pack((cudaStream_t)stream, in, out, shape, ndim, split_axis, parts, dtype);
+}
+int jfx_slab_unpack(void* stream, const void* in, void* out, const int64_t* shape_out, int ndim, int concat_axis,
+                    int parts, int dtype) {
+  using namespace jfx;
+  JFX_REQUIRE(in && out && shape_out, JFX_ERR_INVALID, "null argument");
+  return launch_slab_unpack((cudaStream_t)stream, in, out, shape_out, ndim, concat_axis, parts, dtype);
+}
+int jfx_axpby_diag(void* stream, int n_terms, const void* const* coeff, const double* alpha, const void* const* x,
+                   void* out, int64_t n, int dtype, int coeff_is_complex) {
+  using namespace jfx;
+  JFX_REQUIRE(x && out, JFX_ERR_INVALID, "null argument");
+  return launch_axpby_diag((cudaStream_t)stream, n_terms, coeff, alpha, x, out, n, dtype, coeff_is_complex);
+}
+int jfx_calibrate_dmma(void* stream, int iters, double* tflops) {
+  using namespace jfx;
+  JFX_REQUIRE(tflops && iters > 0, JFX_ERR_INVALID, "bad argument");
+  return calibrate_dmma((cudaStream_t)stream, iters, tflops);
+}
+int jfx_calibrate_dfma(void* stream, int iters, double* tflops) {
+  using namespace jfx;
+  JFX_REQUIRE(tflops && iters > 0, JFX_ERR_INVALID, "bad argument");
+  return calibrate_dfma((cudaStream_t)stream, iters, tflops);
+}
+
+}  // extern "C"

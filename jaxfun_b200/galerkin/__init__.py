@@ -1,0 +1,10 @@
+from . import (  # noqa: F401
+    Chebyshev as Chebyshev,
+    ChebyshevU as ChebyshevU,
+    Fourier as Fourier,
+    Jacobi as Jacobi,
+    Legendre as Legendre,
+    Ultraspherical as Ultraspherical,
+    orthogonal as orthogonal,
+)
+from .tensorproductspace import TensorProduct as TensorProduct, TensorProductSpace as TensorProductSpace  # noqa: F401

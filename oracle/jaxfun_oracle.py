@@ -1,0 +1,819 @@
+"""CPU ORACLE — test infrastructure only, never part of the product path.
+
+A NumPy/SciPy/SymPy restatement of the reference algorithms for the transform hot path of
+spectralDNS/jaxfun.  Every function names the reference lines it follows
+(paths relative to the reference checkout, `src/jaxfun/...`).  Only `tests/`,
+`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of `bench.py` may import
+this module; nothing under `jaxfun_b200/` does.
+
+Pinning status: the reference is pure Python on JAX and jax is not installable here, so the
+reference itself cannot be executed.  The oracle is pinned by (1) the reference's own known-answer
+tests re-run against it (`tests/test_oracle_pins.py`: numpy.polynomial Vandermondes,
+analytic derivatives, round trips, nonlinear identities — SURVEY.md §8c) and (2) golden vectors
+produced by running the reference's *source files* on a minimal numpy stand-in for the `jax`
+API (`tests/golden/make_golden.py`).  Bit-level agreement with XLA's own `cos`/FFT/dot is not
+verifiable in this environment ("parity unpinned at the bit level" — see DESIGN.md).
+
+Third-party arithmetic restated here: jax.numpy.fft / jax.scipy.fft.dct (jaxlib 0.11.0) ->
+numpy.fft / scipy.fft; scipy.special.roots_jacobi (scipy 1.17.0 pinned, 1.18.1 here).
+"""
+from __future__ import annotations
+
+import functools
+import json
+import os
+
+import numpy as np
+import scipy.fft
+import sympy as sp
+from scipy.special import roots_jacobi
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "jaxfun_b200", "data")
+n_sym = sp.Symbol("n", integer=True)
+alf, bet = sp.symbols("a,b", real=True)
+delta = sp.KroneckerDelta
+
+
+# =================================================================================================
+# FastGL  (utils/fastgl.py)
+# =================================================================================================
+@functools.lru_cache(maxsize=1)
+def _gl_data():
+    tab = np.load(os.path.join(_DATA, "fastgl_tables.npz"))
+    with open(os.path.join(_DATA, "fastgl_coeffs.json")) as f:
+        co = {k: [float(s) for s in v] for k, v in json.load(f).items()}
+    return tab["theta"], tab["weight"], tab["cl"], co
+
+
+def besseljzero(k: int) -> float:
+    """utils/fastgl.py:232-271."""
+    co = _gl_data()[3]
+    if k > 20:
+        z = np.pi * (k - 0.25)
+        r = 1.0 / z
+        r2 = r * r
+        c = co["kb20"]
+        acc = c[7] + c[8] * r2
+        for i in range(6, -1, -1):
+            acc = c[i] + r2 * acc
+        return z + r * acc
+    return co["JZ"][k - 1]
+
+
+def besselj1squared(k: int) -> float:
+    """utils/fastgl.py:276-314."""
+    co = _gl_data()[3]
+    if k > 21:
+        x = 1.0 / (k - 0.25)
+        x2 = x * x
+        c = co["km21"]
+        acc = c[7] + c[8] * x2
+        for i in range(6, 0, -1):
+            acc = c[i] + x2 * acc
+        return x * (c[0] + x2 * x2 * acc)
+    return co["J1"][k - 1]
+
+
+def _poly_desc(c, x):
+    acc = c[0] * x + c[1]
+    for v in c[2:]:
+        acc = acc * x + v
+    return acc
+
+
+def GLPairS(n: int, k: int):
+    """Asymptotic (theta, weight) pair, utils/fastgl.py:335-508."""
+    co = _gl_data()[3]
+    w = 1.0 / (n + 0.5)
+    nu = besseljzero(k)
+    theta = w * nu
+    x = theta * theta
+    B = besselj1squared(k)
+    SF1T, SF2T, SF3T = (_poly_desc(co[s], x) for s in ("SF1T", "SF2T", "SF3T"))
+    WSF1T, WSF2T, WSF3T = (_poly_desc(co[s], x) for s in ("WSF1T", "WSF2T", "WSF3T"))
+    NuoSin = nu / np.sin(theta)
+    BNuoSin = B * NuoSin
+    WInvSinc = w * w * NuoSin
+    WIS2 = WInvSinc * WInvSinc
+    theta = w * (nu + theta * WInvSinc * (SF1T + WIS2 * (SF2T + WIS2 * SF3T)))
+    Deno = BNuoSin + BNuoSin * WIS2 * (WSF1T + WIS2 * (WSF2T + WIS2 * WSF3T))
+    return theta, (2.0 * w) / Deno
+
+
+def GLPairTabulated(n: int, k: int):
+    """utils/fastgl.py:512-544 (k is zero based here, as in the reference)."""
+    TH, W, CL, _ = _gl_data()
+    if n % 2 == 1:
+        n2 = (n - 1) // 2
+        if k == n2:
+            return np.pi / 2, 2.0 / (CL[n] * CL[n])
+        if k < n2:
+            return TH[n, n2 - k - 1], W[n, n2 - k - 1]
+        return np.pi - TH[n, k - n2 - 1], W[n, k - n2 - 1]
+    n2 = n // 2
+    if k < n2:
+        return TH[n, n2 - k - 1], W[n, n2 - k - 1]
+    return np.pi - TH[n, k - n2], W[n, k - n2]
+
+
+def GLPair(n: int, k: int):
+    """utils/fastgl.py:548-559."""
+    if n < 101:
+        return GLPairTabulated(n, k - 1)
+    if 2 * k - 1 > n:
+        t, w = GLPairS(n, n - k + 1)
+        return np.pi - t, w
+    return GLPairS(n, k)
+
+
+@functools.lru_cache(maxsize=64)
+def leggauss(N: int) -> np.ndarray:
+    """utils/fastgl.py:562-567 -> array (2, N): x = cos(theta) ascending, weights."""
+    pairs = [GLPair(N, N - i) for i in range(N)]
+    return np.array([[np.cos(t) for t, _ in pairs], [w for _, w in pairs]])
+
+
+# =================================================================================================
+# helpers
+# =================================================================================================
+def _along(fn, x: np.ndarray, axis: int) -> np.ndarray:
+    """Apply a function that works along axis 0 of a [n, m] array along `axis` of x."""
+    x = np.moveaxis(np.asarray(x), axis, 0)
+    shp = x.shape
+    y = fn(x.reshape(shp[0], -1))
+    return np.moveaxis(y.reshape((y.shape[0],) + shp[1:]), 0, axis)
+
+
+def _lamb(expr, N):
+    """sp.lambdify(n, expr, modules=...)(arange(N)) with scalar results broadcast (Jacobi.py:81-89)."""
+    v = sp.lambdify(n_sym, expr, modules=["scipy", "numpy"])(np.arange(N))
+    if np.ndim(v) == 0:
+        v = np.full(N, float(v))
+    return np.asarray(v, dtype=float)
+
+
+# =================================================================================================
+# 1-D spaces
+# =================================================================================================
+class OrthogonalSpace:
+    """galerkin/orthogonal.py:37-444 (transform-relevant subset)."""
+
+    def __init__(self, N, domain=None):
+        self.N = N
+        self.num_quad_points = N
+        self.domain = tuple(self.reference_domain) if domain is None else tuple(domain)
+
+    # orthogonal.py:343-354
+    @property
+    def domain_factor(self):
+        a, b = (float(v) for v in self.domain)
+        c, d = (float(v) for v in self.reference_domain)
+        L, R = b - a, d - c
+        return R / L if abs(L - R) > 1e-12 else 1
+
+    # orthogonal.py:396-426
+    def map_reference_domain(self, x):
+        if tuple(map(float, self.domain)) != tuple(map(float, self.reference_domain)):
+            return float(self.reference_domain[0]) + (x - float(self.domain[0])) * float(self.domain_factor)
+        return x
+
+    def map_true_domain(self, X):
+        if tuple(map(float, self.domain)) != tuple(map(float, self.reference_domain)):
+            return float(self.domain[0]) + (X - float(self.reference_domain[0])) / float(self.domain_factor)
+        return X
+
+    # orthogonal.py:428-444
+    def mesh(self, kind="quadrature", N=None):
+        N = self.num_quad_points if N is None else N
+        if kind == "quadrature":
+            return self.map_true_domain(self.quad_points_and_weights(N)[0])
+        a, b = self.domain
+        return np.linspace(float(a), float(b), N)
+
+    # orthogonal.py:131-141, 168-178 (jacn(k=0) == plain vmap of eval_basis_functions)
+    def vandermonde(self, X):
+        return self.eval_basis_functions(np.asarray(X, dtype=float))
+
+    # orthogonal.py:102-129: evaluate -> _evaluate
+    def evaluate(self, x, c, axis=-1):
+        X = self.map_reference_domain(np.asarray(x, dtype=float))
+        return _along(lambda cm: self._evaluate(X, cm), c, axis)
+
+    def _evaluate(self, X, c):
+        # c: [nc, m]; generic: eval_basis_functions(X)[..., :len(c)] @ c
+        return self.eval_basis_functions(X)[:, : c.shape[0]] @ c
+
+    # orthogonal.py:214-227
+    def backward(self, c, N=None, axis=-1):
+        xj = self.mesh("quadrature", N)
+        return self.evaluate(xj, c, axis)
+
+    # orthogonal.py:229-246
+    def backward_primitive(self, c, k=0, N=None, axis=-1):
+        df = float(self.domain_factor ** k)
+        return df * self.backward(self.derivative_coeffs(c, k, axis), N=N, axis=axis)
+
+    # orthogonal.py:264-277 (Cartesian metric: sg == 1)
+    def scalar_product(self, u, axis=-1):
+        def f(um):
+            N = um.shape[0]
+            xj, wj = self.quad_points_and_weights(N)
+            Pi = self.vandermonde(xj)
+            wj = wj * float(1 / self.domain_factor)
+            return ((um.T * wj) @ np.conj(Pi)).T
+        return _along(f, u, axis)
+
+    # orthogonal.py:256-262
+    def forward(self, u, axis=-1):
+        Lp = self.scalar_product(u, axis)
+        A = self.norm_squared() / float(self.domain_factor)
+        shp = [1] * Lp.ndim
+        shp[axis] = -1
+        return Lp / A.reshape(shp)
+
+    def evaluate_mesh(self, c, kind="quadrature", N=None, axis=-1):
+        if kind == "quadrature":
+            return self.backward(c, N, axis)
+        return self.evaluate(self.mesh(kind, N), c, axis)
+
+    def derivative_coeffs(self, c, k=0, axis=-1):
+        if k == 0:
+            return c
+        if k > 1:
+            return self.derivative_coeffs(self.derivative_coeffs(c, k - 1, axis), 1, axis)
+        return _along(self._derivative1, c, axis)
+
+
+class Jacobi(OrthogonalSpace):
+    """galerkin/Jacobi.py:25-447."""
+    reference_domain = (-1, 1)
+
+    def __init__(self, N, domain=None, alpha=0, beta=0):
+        self.alpha, self.beta = sp.nsimplify(alpha), sp.nsimplify(beta)
+        super().__init__(N, domain)
+
+    # Jacobi.py:344-357
+    def gn(self, n):
+        return sp.S.One
+
+    # Jacobi.py:359-374
+    def _a(self, i, j):
+        a, b = self.alpha, self.beta
+        return (
+            2 * (j + a) * (j + b) / ((2 * j + a + b + 1) * (2 * j + a + b)) * delta(i + 1, j)
+            - (a**2 - b**2) / ((2 * j + a + b + 2) * (2 * j + a + b)) * delta(i, j)
+            + 2 * (j + 1) * (j + a + b + 1) / ((2 * j + a + b + 2) * (2 * j + a + b + 1)) * delta(i - 1, j)
+        )
+
+    # Jacobi.py:421-447
+    def a(self, i, j):
+        return sp.simplify(self.gn(j) / self.gn(i) * self._a(i, j))
+
+    # Jacobi.py:376-391
+    def _b(self, i, j):
+        a, b = self.alpha, self.beta
+        d = lambda m, n: int(m == n)  # noqa: E731
+        f = (2 * (i + a + b) / ((2 * i + a + b) * (2 * i + a + b - 1))) * d(i, j + 1) - (
+            (2 * (i + a + 1) * (i + b + 1)) / ((2 * i + a + b + 3) * (2 * i + a + b + 2) * (i + a + b + 1))
+        ) * d(i, j - 1)
+        if a != b:
+            f += ((2 * (a**2 - b**2)) / ((a + b) * (2 * i + a + b + 2) * (2 * i + a + b))) * d(i, j)
+        return f
+
+    # Jacobi.py:393-419
+    def b(self, i, j):
+        return sp.simplify(self.gn(j) / self.gn(i) * self._b(i, j))
+
+    # Jacobi.py:290-342
+    def psi(self, n, k):
+        return sp.rf(n + self.alpha + self.beta + 1, k) * sp.Rational(1, 2**k)
+
+    def h(self, n, k=0):
+        assert k == 0, "only the k = 0 norm is on the transform path"
+        f = sp.rf(n + 1, alf) / sp.rf(n + bet + 1, alf) * 2 ** (alf + bet + 1) / (2 * n + alf + bet + 1)
+        f = sp.simplify(f.subs([(alf, self.alpha), (bet, self.beta)]))
+        return sp.simplify(self.gn(n) ** 2 * f)
+
+    # Jacobi.py:249-251
+    def norm_squared(self):
+        return _lamb(self.h(n_sym, 0), self.N)
+
+    @functools.lru_cache(maxsize=None)
+    def _rec(self, N):
+        am = _lamb(self.a(n_sym + 1, n_sym), N)
+        ap = _lamb(self.a(n_sym, n_sym + 1), N)
+        aa = np.zeros_like(am)
+        if self.alpha != self.beta:
+            aa = _lamb(self.a(n_sym, n_sym), N)
+        return am, ap, aa
+
+    # Jacobi.py:112-124
+    def quad_points_and_weights(self, N=None):
+        N = self.num_quad_points if N is None else N
+        x, w = roots_jacobi(N, float(self.alpha), float(self.beta))
+        return np.array(x), np.array(w)
+
+    # Jacobi.py:65-110 (vectorised over points X and columns of c)
+    def _evaluate(self, X, c):
+        N = c.shape[0]
+        am, ap, aa = self._rec(N)
+        X = np.asarray(X, dtype=float)[:, None]
+        x0 = np.ones_like(X)
+        if N == 1:
+            return c[0] * x0
+        x1 = (X - aa[0]) / am[0] * x0
+        if N == 2:
+            return c[0] * x0 + c[1] * x1
+        x1_first = x1
+        acc = np.zeros((X.shape[0], c.shape[1]), dtype=np.result_type(c.dtype, float))
+        for i in range(2, N):
+            x2 = ((X - aa[i - 1]) * x1 - ap[i - 2] * x0) / am[i - 1]
+            acc = acc + x2 * c[i]
+            x0, x1 = x1, x2
+        return acc + c[0] + c[1] * x1_first
+
+    # Jacobi.py:165-202
+    def eval_basis_functions(self, X):
+        X = np.atleast_1d(np.asarray(X, dtype=float))
+        am, ap, aa = self._rec(self.N)
+        x0 = X * 0 + 1
+        cols = [x0]
+        if self.N > 1:
+            x1 = (X - aa[0]) / am[0] * x0
+            cols.append(x1)
+            for n in range(2, self.N):
+                x2 = ((X - aa[n - 1]) * x1 - ap[n - 2] * x0) / am[n - 1]
+                cols.append(x2)
+                x0, x1 = x1, x2
+        return np.stack(cols, axis=-1)
+
+    # Jacobi.py:204-247
+    def _derivative1(self, c):
+        N = c.shape[0] - 1
+        out = np.zeros_like(c)
+        if N <= 0:
+            return out
+        bm = _lamb(self.b(n_sym + 1, n_sym), N)
+        bp = _lamb(self.b(n_sym + 1, n_sym + 2), N)
+        bb = np.zeros_like(bm)
+        if self.alpha != self.beta:
+            bb = _lamb(self.b(n_sym + 1, n_sym + 1), N)
+        x0 = np.zeros_like(c[0])
+        x1 = c[-1] / bm[-1]
+        out[N - 1] = x1
+        for n in range(N - 2, -1, -1):
+            x2 = (c[n + 1] - bb[n] * x1 - bp[n] * x0) / bm[n]
+            out[n] = x2
+            x0, x1 = x1, x2
+        return out
+
+
+class Legendre(Jacobi):
+    """galerkin/Legendre.py:42-216."""
+
+    def __init__(self, N, domain=None):
+        super().__init__(N, domain, 0, 0)
+
+    # Legendre.py:125-137
+    def quad_points_and_weights(self, N=None):
+        N = self.num_quad_points if N is None else N
+        x, w = leggauss(N)
+        return x, w
+
+    # Legendre.py:162-183
+    def eval_basis_functions(self, X):
+        X = np.atleast_1d(np.asarray(X, dtype=float))
+        x0 = X * 0 + 1
+        cols = [x0]
+        x1 = X
+        for i in range(2, self.N + 1):
+            cols.append(x1)
+            x2 = (x1 * X * (2 * i - 1) - x0 * (i - 1)) / i
+            x0, x1 = x1, x2
+        return np.stack(cols[: self.N], axis=-1)
+
+    # Legendre.py:185-216
+    def _derivative1(self, c):
+        N = c.shape[0] - 1
+        out = np.zeros_like(c)
+        if N <= 0:
+            return out
+        x0 = np.zeros_like(c[0])
+        x1 = c[-1] * (2 * N - 1)
+        out[N - 1] = x1
+        for n in range(N - 2, -1, -1):
+            x2 = (2 * n + 1) * c[n + 1] + (2 * n + 1) / (2 * n + 5) * x0
+            out[n] = x2
+            x0, x1 = x1, x2
+        return out
+
+
+class Chebyshev(Jacobi):
+    """galerkin/Chebyshev.py:44-397."""
+
+    def __init__(self, N, domain=None):
+        super().__init__(N, domain, -sp.S.Half, -sp.S.Half)
+
+    # Chebyshev.py:320-338
+    def gn(self, n):
+        return sp.S.One / sp.jacobi(n, self.alpha, self.beta, 1)
+
+    def h(self, n, k):
+        if k > 0:
+            return sp.simplify(sp.pi * n * sp.gamma(n + k) / (2 * sp.factorial(n - k)))
+        return sp.Piecewise((sp.pi, sp.Eq(n, 0)), (sp.pi / 2, True))
+
+    # Chebyshev.py:352-384
+    def a(self, i, j):
+        if (i - j) == 1:
+            return sp.Piecewise((1, sp.Eq(j, 0)), (sp.S.Half, True))
+        if (j - i) == 1:
+            return sp.S.Half
+        return 0
+
+    # Chebyshev.py:149-170
+    def quad_points_and_weights(self, N=None):
+        N = self.num_quad_points if N is None else N
+        return (np.cos(np.pi + (2 * np.arange(N) + 1) * np.pi / (2 * N)), np.ones(N) * np.pi / N)
+
+    # Chebyshev.py:199-223
+    def eval_basis_functions(self, X):
+        X = np.atleast_1d(np.asarray(X, dtype=float))
+        x0 = X * 0 + 1
+        cols = [x0]
+        x1 = X
+        for _ in range(self.N - 1):
+            cols.append(x1)
+            x0, x1 = x1, 2 * X * x1 - x0
+        return np.stack(cols, axis=-1)
+
+    # Chebyshev.py:225-241 (linear extension to complex data: SURVEY §8a note)
+    def backward(self, c, N=None, axis=-1):
+        n = self.num_quad_points if N is None else N
+
+        def f(cm):
+            if n > cm.shape[0]:
+                cm = np.concatenate([cm, np.zeros((n - cm.shape[0],) + cm.shape[1:], dtype=cm.dtype)])
+            sign = (-1) ** np.arange(n)
+            uh = cm * sign[:, None]
+            return 0.5 * uh[0] + n * _idct2(uh, n)
+        return _along(f, c, axis)
+
+    # Chebyshev.py:243-260
+    def forward(self, u, axis=-1):
+        def f(um):
+            n = um.shape[0]
+            assert n >= self.N
+            sign = (-1) ** np.arange(n)
+            uh = _dct2(um, n)
+            uh[0] = uh[0] / 2
+            uh = uh * sign[:, None] / n
+            return uh[: self.N]
+        return _along(f, u, axis)
+
+    # Chebyshev.py:262-279
+    def scalar_product(self, u, axis=-1):
+        def f(um):
+            n = um.shape[0]
+            assert n >= self.N
+            sign = (-1) ** np.arange(n)
+            uh = _dct2(um, n)
+            uh = uh * np.pi * sign[:, None] / n / 2 / self.domain_factor
+            return uh[: self.N]
+        return _along(f, u, axis)
+
+    # Chebyshev.py:281-315
+    def _derivative1(self, c):
+        N = c.shape[0] - 1
+        out = np.zeros_like(c)
+        if N <= 0:
+            return out
+        x0 = np.zeros_like(c[0])
+        x1 = c[-1] * N * 2
+        out[N - 1] = x1
+        for n in range(N - 2, -1, -1):
+            x2 = 2 * (n + 1) * c[n + 1] + x0
+            out[n] = x2
+            x0, x1 = x1, x2
+        out[0] = out[0] / 2
+        return out
+
+
+def _dct2(x, n):
+    """jax.scipy.fft.dct(x, n=n) (type 2, norm=None) along axis 0; complex input = linear extension."""
+    if np.iscomplexobj(x):
+        return scipy.fft.dct(x.real, type=2, n=n, axis=0) + 1j * scipy.fft.dct(x.imag, type=2, n=n, axis=0)
+    return scipy.fft.dct(x, type=2, n=n, axis=0)
+
+
+def _idct2(x, n):
+    if np.iscomplexobj(x):
+        return scipy.fft.idct(x.real, type=2, n=n, axis=0) + 1j * scipy.fft.idct(x.imag, type=2, n=n, axis=0)
+    return scipy.fft.idct(x, type=2, n=n, axis=0)
+
+
+def dst(x, type=2, n=None):
+    """utils/common.py:197-230 along axis 0."""
+    N = x.shape[0] if n is None else n
+    if x.shape[0] < N:
+        x = np.concatenate([x, np.zeros((N - x.shape[0],) + x.shape[1:], dtype=x.dtype)])
+    zeros = np.zeros((1,) + x.shape[1:], dtype=x.dtype)
+    if type == 1:
+        y = np.concatenate([zeros, x, zeros, -x[::-1]], axis=0)
+        Y = np.fft.fft(y, axis=0)
+        return -np.imag(Y[1 : N + 1])
+    y = np.concatenate([x, -x[::-1]], axis=0)
+    Y = np.fft.fft(y, axis=0)
+    k = np.arange(N)
+    tw = np.exp(-1j * np.pi * (k + 1) / (2 * N))
+    return -np.imag(tw[:, None] * Y[1 : N + 1])
+
+
+class ChebyshevU(Jacobi):
+    """galerkin/ChebyshevU.py:14-221."""
+
+    def __init__(self, N, domain=None):
+        super().__init__(N, domain, sp.S.Half, sp.S.Half)
+
+    def gn(self, n):
+        return (n + 1) / sp.jacobi(n, self.alpha, self.beta, 1)
+
+    def norm_squared(self):
+        return np.full(self.N, np.pi / 2)
+
+    # ChebyshevU.py:83-104
+    def quad_points_and_weights(self, N=None):
+        N = self.num_quad_points if N is None else N
+        theta = (np.arange(N) + 1) * np.pi / (N + 1)
+        points = np.cos(theta + np.pi)
+        weights = np.full(N, np.pi / (N + 1)) * (1 - points**2)
+        return points, weights
+
+    # ChebyshevU.py:133-157
+    def eval_basis_functions(self, X):
+        X = np.atleast_1d(np.asarray(X, dtype=float))
+        x0 = X * 0 + 1
+        cols = [x0]
+        x1 = 2 * X
+        for _ in range(self.N - 1):
+            cols.append(x1)
+            x0, x1 = x1, 2 * X * x1 - x0
+        return np.stack(cols, axis=-1)
+
+    # ChebyshevU.py:162-177 (real data; complex handled part-wise)
+    def backward(self, c, N=None, axis=-1):
+        n = self.num_quad_points if N is None else N
+
+        def g(cm):
+            d = dst(cm, n=n, type=1)
+            return (d / (2 * np.sin((np.arange(n) + 1) * np.pi / (n + 1)))[:, None])[::-1]
+
+        def f(cm):
+            return g(cm.real) + 1j * g(cm.imag) if np.iscomplexobj(cm) else g(cm)
+        return _along(f, c, axis)
+
+    # ChebyshevU.py:192-209
+    def scalar_product(self, u, axis=-1):
+        def g(um):
+            n = um.shape[0]
+            uh = um * np.sin(np.pi / (n + 1) * np.arange(1, n + 1))[:, None]
+            uh = dst(uh, n=n, type=1)
+            uh = uh * ((-1) ** np.arange(n) * np.pi / (2 * (n + 1) * self.domain_factor))[:, None]
+            return uh[: self.N]
+
+        def f(um):
+            return g(um.real) + 1j * g(um.imag) if np.iscomplexobj(um) else g(um)
+        return _along(f, u, axis)
+
+    # ChebyshevU.py:179-190
+    def forward(self, u, axis=-1):
+        return self.scalar_product(u, axis) * (2 * self.domain_factor / np.pi)
+
+
+class Ultraspherical(Jacobi):
+    """galerkin/Ultraspherical.py:12-101."""
+
+    def __init__(self, N, domain=None, lambda_=1):
+        lam = sp.nsimplify(lambda_)
+        super().__init__(N, domain, lam - sp.S.Half, lam - sp.S.Half)
+
+    def gn(self, n):
+        return sp.S.One / sp.jacobi(n, self.alpha, self.beta, 1)
+
+
+def fourier_wavenumbers(N, eliminate_highest_freq=False):
+    """galerkin/Fourier.py:14-20."""
+    indices = np.arange(N)
+    k = np.where(indices < (N + 1) // 2, indices, indices - N)
+    if eliminate_highest_freq and N % 2 == 0:
+        k[N // 2] = 0
+    return k
+
+
+class Fourier(OrthogonalSpace):
+    """galerkin/Fourier.py:23-235."""
+
+    @property
+    def reference_domain(self):
+        return (0, 2 * np.pi)
+
+    def __init__(self, N, domain=None):
+        assert N % 2 == 0
+        super().__init__(N, domain)
+
+    def wavenumbers(self, N=None, eliminate_highest_freq=False):
+        return fourier_wavenumbers(self.N if N is None else N, eliminate_highest_freq)
+
+    # Fourier.py:77-89
+    def quad_points_and_weights(self, N=None):
+        N = self.num_quad_points if N is None else N
+        return np.arange(N, dtype=float) * 2 * np.pi / N, np.full(N, 2 * np.pi / N)
+
+    # Fourier.py:221-235
+    def mesh(self, kind="quadrature", N=None):
+        a, b = self.domain
+        N = self.num_quad_points if N is None else N
+        return np.linspace(float(a), float(b), N, endpoint=False)
+
+    # Fourier.py:105-116
+    def eval_basis_functions(self, X):
+        X = np.atleast_1d(np.asarray(X, dtype=float))
+        return np.exp(1j * self.wavenumbers()[None, :] * X[:, None])
+
+    def norm_squared(self):
+        return np.ones(self.N) * 2 * np.pi
+
+    # Fourier.py:126-148
+    def backward(self, c, N=None, axis=-1):
+        n = self.N if N is None else N
+
+        def f(cm):
+            Lc = cm.shape[0]
+            assert n >= Lc
+            if n > Lc:
+                cm = np.concatenate([cm[: Lc // 2], np.zeros((n - Lc,) + cm.shape[1:], dtype=cm.dtype), cm[Lc // 2:]])
+            return np.fft.ifft(cm, axis=0, norm="forward")
+        return _along(f, np.asarray(c, dtype=complex), axis)
+
+    # Fourier.py:150-163
+    def scalar_product(self, u, axis=-1):
+        def f(um):
+            out = np.fft.fft(um, axis=0, norm="forward") * 2 * np.pi / float(self.domain_factor)
+            return out[self.wavenumbers()] if um.shape[0] > self.N else out
+        return _along(f, np.asarray(u, dtype=complex), axis)
+
+    # Fourier.py:165-180
+    def forward(self, u, axis=-1):
+        def f(um):
+            assert um.shape[0] >= self.N
+            out = np.fft.fft(um, axis=0, norm="forward")
+            return out[self.wavenumbers()] if um.shape[0] > self.N else out
+        return _along(f, np.asarray(u, dtype=complex), axis)
+
+    # Fourier.py:206-219
+    def derivative_coeffs(self, c, k=0, axis=-1):
+        if k == 0:
+            return c
+        m = self.wavenumbers(eliminate_highest_freq=k % 2 == 1)
+        shp = [1] * np.ndim(c)
+        shp[axis] = -1
+        return ((1j * m) ** k).reshape(shp) * c
+
+
+# =================================================================================================
+# tensor products  (galerkin/tensorproductspace.py:330-460, sharding.py:24-40)
+# =================================================================================================
+class TensorProductSpace:
+    def __init__(self, *spaces):
+        self.basespaces = list(spaces)
+
+    def __len__(self):
+        return len(self.basespaces)
+
+    def _axes(self, x):
+        d = len(self)
+        return [x.ndim - d + ax for ax in range(d)]
+
+    def backward(self, c, N=None):
+        c = np.asarray(c)
+        for ax, axis in enumerate(self._axes(c)):
+            c = self.basespaces[ax].backward(c, N=None if N is None else N[ax], axis=axis)
+        return c
+
+    def forward(self, u):
+        u = np.asarray(u)
+        for ax, axis in enumerate(self._axes(u)):
+            u = self.basespaces[ax].forward(u, axis=axis)
+        return u
+
+    def scalar_product(self, u):
+        u = np.asarray(u)
+        for ax, axis in enumerate(self._axes(u)):
+            u = self.basespaces[ax].scalar_product(u, axis=axis)
+        return u
+
+    def backward_primitive(self, c, k, N=None):
+        c = np.asarray(c)
+        for ax, axis in enumerate(self._axes(c)):
+            c = self.basespaces[ax].backward_primitive(c, k=k[ax], N=None if N is None else N[ax], axis=axis)
+        return c
+
+    def mesh(self, N=None):
+        d = len(self)
+        out = []
+        for ax, s in enumerate(self.basespaces):
+            x = np.asarray(s.mesh("quadrature", None if N is None else N[ax]))
+            shp = [1] * d
+            shp[ax] = -1
+            out.append(x.reshape(shp))
+        return tuple(out)
+
+
+# sharding.py:43-105: the slab algorithm on P simulated ranks (lists of local blocks)
+def slab_transform(fns, blocks, sharded_axis, split_axis):
+    """blocks[r]: local array of rank r, sharded along `sharded_axis`.  fns[ax] acts along axis ax.
+    Phase 1 = unsharded axes, tiled all_to_all(split_axis -> concat sharded_axis), phase 2 = sharded axis."""
+    P = len(blocks)
+    d = blocks[0].ndim
+    unsharded = [ax for ax in range(d) if ax != sharded_axis]
+    loc = list(blocks)
+    for ax in unsharded:
+        loc = [fns[ax](b) for b in loc]
+    pieces = [np.split(b, P, axis=split_axis) for b in loc]          # pieces[src][dst]
+    loc = [np.concatenate([pieces[src][dst] for src in range(P)], axis=sharded_axis) for dst in range(P)]
+    return [fns[sharded_axis](b) for b in loc]
+
+
+# =================================================================================================
+# nonlinear terms and integrators (integrators/base.py:230-260, nonlinear.py, etdrk4.py, rk4.py)
+# =================================================================================================
+def nonlinear_rhs(space, leaves, expr, uh, N=None, final="forward"):
+    """testspace.forward(E(backward_primitive(uh, k_l)...)) — base.py:230-248 with the evaluator of
+    nonlinear.py:89-176 given as a Python callable `expr(*leaf_values)`."""
+    vals = []
+    for k in leaves:
+        if isinstance(space, TensorProductSpace):
+            vals.append(space.backward_primitive(uh, k, N) if any(k) else space.backward(uh, N))
+        else:
+            vals.append(space.backward_primitive(uh, k, N) if k else space.backward(uh, N))
+    e = expr(*vals)
+    return space.forward(e) if final == "forward" else space.scalar_product(e)
+
+
+def phi1(z):
+    """etdrk4.py:21-25."""
+    z = np.asarray(z, dtype=complex)
+    small = np.abs(z) < 1e-7
+    series = 1 + z / 2 + z**2 / 6 + z**3 / 24 + z**4 / 120
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(small, series, np.expm1(z) / z)
+
+
+def phi2(z):
+    """etdrk4.py:28-32."""
+    z = np.asarray(z, dtype=complex)
+    small = np.abs(z) < 1e-6
+    series = 0.5 + z / 6 + z**2 / 24 + z**3 / 120 + z**4 / 720
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(small, series, (np.expm1(z) - z) / z**2)
+
+
+def phi3(z):
+    """etdrk4.py:35-39."""
+    z = np.asarray(z, dtype=complex)
+    small = np.abs(z) < 1e-5
+    series = 1 / 6 + z / 24 + z**2 / 120 + z**3 / 720 + z**4 / 5040
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(small, series, (np.expm1(z) - z - z**2 / 2) / z**3)
+
+
+def etdrk4_coefficients(dt, Ldiag):
+    """etdrk4.py:108-121 + :42-52."""
+    z = dt * np.asarray(Ldiag)
+    E, E2 = np.exp(z), np.exp(z / 2)
+    Q = 0.5 * phi1(z / 2)
+    p1, p2, p3 = phi1(z), phi2(z), phi3(z)
+    return E, E2, Q, p1 - 3 * p2 + 4 * p3, p2 - 2 * p3, 4 * p3 - p2
+
+
+def etdrk4_step(u_hat, dt, coeffs, Nfun):
+    """etdrk4.py:152-166 (diagonal operators: `@` is elementwise)."""
+    E, E2, Q, f1, f2, f3 = coeffs
+    dtQ = dt * Q
+    n1 = Nfun(u_hat)
+    a = E2 * u_hat + dtQ * n1
+    n2 = Nfun(a)
+    b = E2 * u_hat + dtQ * n2
+    n3 = Nfun(b)
+    c = E2 * a + dtQ * (2 * n3 - n1)
+    n4 = Nfun(c)
+    return E * u_hat + dt * ((f1 * n1) + 2 * (f2 * (n2 + n3)) + (f3 * n4))
+
+
+def rk4_step(u_hat, dt, rhs):
+    """rk4.py:14-20."""
+    k1 = rhs(u_hat)
+    k2 = rhs(u_hat + 0.5 * dt * k1)
+    k3 = rhs(u_hat + 0.5 * dt * k2)
+    k4 = rhs(u_hat + dt * k3)
+    return u_hat + (dt / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
