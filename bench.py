@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Benchmark of the tensor-product transform hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size S]
+
+N = 1 (default): BASELINE configs[1] — TensorProduct forward + backward of Legendre^3 and Chebyshev^3
+at 256^3 fp64.  One step = 4 transforms (Legendre backward, forward; Chebyshev backward, forward).
+N > 1 (under torchrun): BASELINE configs[4] — Legendre^3 512^3 slab-decomposed over N ranks with the
+NCCL all-to-all; one step = backward + forward of the global field (strong scaling).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job transforms/s with inputs resident in HBM;
+`e2e` = the same through the public API with pinned HOST buffers (H2D + D2H inside the timed region);
+`roofline` = the dominant kernel (FP64 tensor-core contraction) against the FP64 peak calibrated
+live; `cpu_baseline` = the NumPy/SciPy oracle on the host cores.
+`--impl reference` times that oracle (the reference's algorithm on CPU; jax itself is not installable
+here — see DESIGN.md) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "3D tensor-product fwd/bwd transforms/s (fp64)"
+UNIT = "transforms/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=0, help="override the cube edge (default 256 / 512)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.index, self.proc, self.path = index, None, f"/tmp/jfx_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [s.strip() for s in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU side (oracle)
+# --------------------------------------------------------------------------------------------------
+def oracle_spaces(n, dims=3):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import jaxfun_oracle as O
+    O.Jacobi.fast_backward = True  # Vandermonde matmul instead of the scan: the faster CPU form
+    return (O, O.TensorProductSpace(*[O.Legendre(n) for _ in range(dims)]),
+            O.TensorProductSpace(*[O.Chebyshev(n) for _ in range(dims)]))
+
+
+def cpu_step(TL, TC, cL, cC):
+    """One step of the workload on the host: returns #transforms."""
+    n = 0
+    if TL is not None:
+        u = TL.backward(cL); TL.forward(u); n += 2
+    if TC is not None:
+        u = TC.backward(cC); TC.forward(u); n += 2
+    return n
+
+
+def run_reference(args):
+    """--impl reference: the oracle (NumPy/SciPy restatement of the reference algorithm) on host cores."""
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    multi = args.gpus > 1
+    n = args.size or (512 if multi else 256)
+    cores = os.cpu_count() or 1
+    O, TL, TC = oracle_spaces(n)
+    if multi:
+        TC = None
+    rng = np.random.default_rng(5 if multi else 2)
+    cL = rng.standard_normal((n, n, n))
+    cC = rng.standard_normal((n, n, n)) if TC is not None else None
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(TL, TC, cL, cC)
+    t0 = time.perf_counter()
+    ntr = 0
+    for _ in range(args.steps):
+        ntr += cpu_step(TL, TC, cL, cC)
+    dt = time.perf_counter() - t0
+    val = ntr / dt
+    sample = f"full workload: {ntr // args.steps} transforms of {n}^3 fp64 per step, {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(n, args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "NumPy/SciPy oracle (matmul via the recurrence / scipy.fft), not XLA: jax is not installable here"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n, gpus):
+    if gpus > 1:
+        return {"workload": f"C5: Legendre^3 {n}^3 fp64 slab-decomposed (axis0<->axis1 all-to-all), backward+forward per step",
+                "shape": [n, n, n], "parallelism": f"slab{gpus}", "l2": "arrays (>= 134 MB per rank) larger than L2"}
+    return {"workload": f"C2: TensorProduct backward+forward, Legendre^3 and Chebyshev^3, {n}^3 fp64 (4 transforms/step)",
+            "shape": [n, n, n], "parallelism": "single", "l2": f"inputs larger than L2 ({8 * n**3 / 1e6:.0f} MB arrays, 4 buffers per transform)"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU side
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import jaxfun_b200 as jf
+    from jaxfun_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    multi = world > 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if multi:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.size or (512 if multi else 256)
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = L.load()
+    import ctypes as C
+
+    if not multi:
+        TL = jf.TensorProduct(*[jf.Legendre(n) for _ in range(3)])
+        TC = jf.TensorProduct(*[jf.Chebyshev(n) for _ in range(3)])
+        g = torch.Generator(device=dev).manual_seed(2)
+        cL = torch.randn(n, n, n, dtype=torch.float64, device=dev, generator=g)
+        cC = torch.randn(n, n, n, dtype=torch.float64, device=dev, generator=g)
+        pLb, pLf = TL._plan(L.OP_BACKWARD, cL), TL._plan(L.OP_FORWARD, cL)
+        pCb, pCf = TC._plan(L.OP_BACKWARD, cC), TC._plan(L.OP_FORWARD, cC)
+        uL, uC = torch.empty_like(cL), torch.empty_like(cC)
+        oL, oC = torch.empty_like(cL), torch.empty_like(cC)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+
+        def step(i=None):
+            if i is not None:
+                evs[i][0].record()
+            pLb.execute(cL, uL); pLf.execute(uL, oL)
+            if i is not None:
+                evs[i][1].record()
+            pCb.execute(cC, uC); pCf.execute(uC, oC)
+            if i is not None:
+                evs[i][2].record()
+            return 4
+
+        launches_per_step = pLb.launches + pLf.launches + pCb.launches + pCf.launches
+        flops_L = pLb.flops + pLf.flops
+        bytes_C = pCb.bytes + pCf.bytes
+    else:
+        from jaxfun_b200.sharding import SlabTensorProduct
+        T = jf.TensorProduct(*[jf.Legendre(n) for _ in range(3)])
+        S = SlabTensorProduct(T)
+        g = torch.Generator(device=dev).manual_seed(5 + rank)
+        c_loc = torch.randn(n // world, n, n, dtype=torch.float64, device=dev, generator=g)
+
+        def step(i=None):
+            u = S.backward(c_loc)
+            S.forward(u)
+            return 2
+
+        launches_per_step = 2 * 3 + 2  # 3 contraction passes + 1 repack per transform (+ NCCL)
+        flops_L = 2 * 6.0 * float(n) ** 4 / world
+        bytes_C = 0.0
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    ntr = 0
+    for i in range(args.steps):
+        ntr += step(i if not multi else None)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if multi:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = ntr / (ms * 1e-3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n, world), "gpu_launches": launches_per_step * args.steps,
+    }
+
+    peaks = measured_peaks()
+    # FP64 denominators: calibrated live (no FP64 figure in MEASURED_PEAKS.json)
+    dm, df = C.c_double(), C.c_double()
+    L.check(lib.jfx_calibrate_dmma(None, 4000, C.byref(dm)))
+    L.check(lib.jfx_calibrate_dfma(None, 4000, C.byref(df)))
+    a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(); torch.matmul(a, b); c1.record(); torch.cuda.synchronize()
+    cublas_tf = 2 * 8192.0**3 / (c0.elapsed_time(c1) * 1e-3) / 1e12
+    del a, b
+    fp64_peak = max(dm.value, df.value, cublas_tf)
+
+    if not multi:
+        tL = sum(evs[i][0].elapsed_time(evs[i][1]) for i in range(args.steps)) / args.steps
+        tC = sum(evs[i][1].elapsed_time(evs[i][2]) for i in range(args.steps)) / args.steps
+        n_l = pLb.launches + pLf.launches
+        ach = flops_L / (tL * 1e-3) / 1e12
+        line["roofline"] = {
+            "kernel": "dgemm_dmma (FP64 tensor-core per-axis Vandermonde contraction)", "bound": "tensor",
+            "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+            "traffic": None, "launches_per_step": n_l, "avg_launch_ms": tL / n_l,
+            "flops_per_launch": flops_L / n_l,
+            "peak_source": "live calibration: max(register-resident DMMA, DFMA, cuBLAS DGEMM 8192^3); "
+                           "MEASURED_PEAKS.json has no FP64 figure",
+            "fp64_calibration_tflops": {"dmma_regs": dm.value, "dfma_regs": df.value, "cublas_dgemm_8192": cublas_tf,
+                                        "nominal": 37.0},
+        }
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        achC = bytes_C / (tC * 1e-3) / 1e9
+        line["roofline_hbm"] = {
+            "kernel": "Chebyshev^3 DCT path (backward+forward)", "bound": "hbm", "achieved": achC, "peak": hbm,
+            "unit": "GB/s", "frac": achC / hbm, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650",
+            "algorithmic_bytes_per_step": bytes_C,
+        }
+        line["detail"] = {
+            "legendre3": {"ms_per_pair": tL, "transforms_per_s": 2e3 / tL, "tflops": ach},
+            "chebyshev3": {"ms_per_pair": tC, "transforms_per_s": 2e3 / tC, "gbs_compulsory": achC},
+        }
+    else:
+        ach = 2 * 6.0 * float(n) ** 4 / world / (ms / args.steps * 1e-3) / 1e12
+        line["roofline"] = {"kernel": "dgemm_dmma inside the slab transform (per rank, incl. exchange time)",
+                            "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": ach / fp64_peak, "traffic": None,
+                            "peak_source": "live calibration (see N=1 line)"}
+        if rank == 0:
+            # same global problem on ONE GPU, for parallel-efficiency context (not part of `value`)
+            try:
+                T1 = jf.TensorProduct(*[jf.Legendre(n) for _ in range(3)])
+                c1g = torch.randn(n, n, n, dtype=torch.float64, device=dev)
+                for _ in range(2):
+                    T1.forward(T1.backward(c1g))
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); s0.record()
+                for _ in range(3):
+                    T1.forward(T1.backward(c1g))
+                s1.record(); torch.cuda.synchronize()
+                line["single_gpu_same_size"] = {"ms_per_step": s0.elapsed_time(s1) / 3}
+            except Exception as e:  # pragma: no cover
+                line["single_gpu_same_size"] = {"error": str(e)}
+
+    if rank == 0:
+        line["clocks"] = clocks
+
+    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region ---------------
+    if not args.no_e2e and not multi:
+        hin = jf.PinnedArray((n, n, n), np.float64)
+        hmid = jf.PinnedArray((n, n, n), np.float64)
+        hout = jf.PinnedArray((n, n, n), np.float64)
+        hin.array[...] = np.random.default_rng(2).standard_normal((n, n, n))
+        k_e2e = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            for T in (TL, TC):
+                pb, pf = T._plan(L.OP_BACKWARD, cL), T._plan(L.OP_FORWARD, cL)
+                pb.execute_host(hin.array, hmid.array)
+                pf.execute_host(hmid.array, hout.array)
+            return 4
+        e2e_step()
+        t0 = time.perf_counter()
+        ntr = 0
+        for _ in range(k_e2e):
+            ntr += e2e_step()
+        dt = time.perf_counter() - t0
+        line["e2e"] = {"value": ntr / dt, "unit": UNIT, "h2d_bytes_per_step": 4 * 8 * n**3,
+                       "d2h_bytes_per_step": 4 * 8 * n**3, "steps": k_e2e, "ms_per_step": 1e3 * dt / k_e2e,
+                       "api": "Plan.execute_host via TensorProductSpace (numpy in pinned memory -> numpy)"}
+        err = float(np.abs(hout.array - hin.array).max())
+        line["e2e"]["roundtrip_max_abs_err"] = err
+    elif multi:
+        # e2e for the slab path: each rank stages its block from pinned host memory and reads it back
+        hin = torch.empty(n // world, n, n, dtype=torch.float64).pin_memory()
+        hout = torch.empty(n // world, n, n, dtype=torch.float64).pin_memory()
+        hin.normal_()
+        k_e2e = 3
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            d = hin.to(dev, non_blocking=True)
+            o = S.forward(S.backward(d))
+            hout.copy_(o, non_blocking=True)
+            torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        line["e2e"] = {"value": 2 * k_e2e / float(tt.item()), "unit": UNIT,
+                       "h2d_bytes_per_step": 8 * n**3, "d2h_bytes_per_step": 8 * n**3, "steps": k_e2e}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
+    if rank == 0 and not multi and not args.no_cpu:
+        O, OL, OC = oracle_spaces(n)
+        rng = np.random.default_rng(2)
+        hL = rng.standard_normal((n, n, n))
+        t0 = time.perf_counter()
+        ntr = cpu_step(OL, OC, hL, hL)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ntr / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"1 full step ({ntr} transforms of {n}^3 fp64), {dt:.1f} s",
+                                "note": "NumPy/SciPy oracle of the reference algorithm, not XLA (jax unavailable)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if multi:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,204 @@
+"""Slab-decomposed tensor-product transforms over the GPUs of one box.
+
+Mirror of `jaxfun.sharding` (`src/jaxfun/sharding.py:9-105`): spectral arrays are sharded along
+axis 0 (`spectral_sharding = P("k")`), physical arrays along axis 1 (`physical_sharding =
+P(None, "k")`); one transform is
+
+    phase 1: the unsharded axes, locally
+    exchange: lax.all_to_all(split_axis=unsharded[0], concat_axis=sharded[0], tiled=True)
+    phase 2: the originally sharded axis, locally
+
+One process per GPU; the exchange is `torch.distributed.all_to_all_single` (NCCL over
+NVLink/NVSwitch on the GPU box, gloo in the CPU tests).  The block layout is chosen so that only ONE
+side of each exchange needs a repack kernel:
+
+* spectral -> physical (`backward`): split axis 1 -> `jfx_slab_pack` into [P, n0/P, n1/P, ...];
+  the received blocks concatenate along axis 0, i.e. they already ARE the contiguous result.
+* physical -> spectral (`forward`, `scalar_product`): split axis 0 -> the send blocks are already
+  contiguous; the received blocks interleave along axis 1 -> `jfx_slab_unpack`.
+
+The local phases are ordinary engine plans on the local block; `SlabBackend` abstracts them so the
+orchestration can be exercised on CPU ranks (gloo) with the oracle's 1-D functions injected.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Sequence
+
+import numpy as np
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+SPECTRAL = "spectral"   # axis 0 sharded  (sharding.py:10)
+PHYSICAL = "physical"   # axis 1 sharded  (sharding.py:11)
+
+
+def get_transposed_sharding(sharding: str) -> str:
+    """sharding.py:14-21."""
+    if sharding == SPECTRAL:
+        return PHYSICAL
+    if sharding == PHYSICAL:
+        return SPECTRAL
+    raise ValueError(f"Provided {sharding} does not match spectral or physical.")
+
+
+def sharded_axis(sharding: str) -> int:
+    return 0 if sharding == SPECTRAL else 1
+
+
+class SlabBackend:
+    """What the slab algorithm needs from its local engine."""
+
+    def apply_axes(self, x, axes: Sequence[int]):
+        """Apply the per-axis transforms for `axes` (in that order) to the local block."""
+        raise NotImplementedError
+
+    def pack(self, x, split_axis: int, parts: int):
+        """[.., L, ..] -> [parts, .., L/parts, ..] contiguous."""
+        raise NotImplementedError
+
+    def unpack(self, blocks, concat_axis: int, parts: int):
+        """[parts, .., L/parts, ..] -> [.., L, ..] contiguous."""
+        raise NotImplementedError
+
+    def all_to_all(self, send):
+        """Tiled all-to-all of the leading `parts` dimension; same shape out."""
+        out = torch.empty_like(send)
+        dist.all_to_all_single(out, send)
+        return out
+
+
+def apply_separable_slab(x, sharding: str, backend: SlabBackend, world_size: int):
+    """`_apply_separable_spmd_shard_map` (sharding.py:43-105) for one rank's local block `x`.
+
+    Returns the local block of the result, which carries the transposed sharding."""
+    dim = x.ndim
+    sh = sharded_axis(sharding)
+    unsharded = [ax for ax in range(dim) if ax != sh]
+    split_axis, concat_axis = unsharded[0], sh
+    # Phase 1 — unsharded axes: fully local
+    y = backend.apply_axes(x, unsharded)
+    if y.shape[split_axis] % world_size != 0:
+        raise ValueError(  # sharding.py:59-63
+            f"split axis {split_axis} has extent {y.shape[split_axis]}, not divisible by {world_size} devices")
+    # Exchange
+    if world_size > 1:
+        if split_axis == 0:
+            send = y.reshape((world_size, y.shape[0] // world_size) + tuple(y.shape[1:]))
+        else:
+            send = backend.pack(y, split_axis, world_size)
+        recv = backend.all_to_all(send)
+        if concat_axis == 0:
+            y = recv.reshape((recv.shape[0] * recv.shape[1],) + tuple(recv.shape[2:]))
+        else:
+            y = backend.unpack(recv, concat_axis, world_size)
+    # Phase 2 — the originally sharded axis
+    return backend.apply_axes(y, [sh])
+
+
+# ---------------------------------------------------------------------------------------------------
+# engine-backed implementation
+# ---------------------------------------------------------------------------------------------------
+class EngineSlabBackend(SlabBackend):
+    """Local phases = engine plans restricted to a subset of axes; repacks = jfx_slab_pack/unpack."""
+
+    def __init__(self, space, op: int, N=None, k=None):
+        self.space, self.op, self.N, self.k = space, op, N, k
+        self._plans = {}
+
+    def apply_axes(self, x, axes):
+        from . import _lib as L
+        from .engine import Plan, jfx_dtype
+        dtype = jfx_dtype(x.dtype)
+        key = (tuple(x.shape), dtype, tuple(axes))
+        plan = self._plans.get(key)
+        if plan is None:
+            specs = [None] * x.ndim
+            for ax in axes:
+                sp = self.space.basespaces[ax]
+                specs[ax] = sp.axis_spec(self.op, x.shape[ax], dtype, None if self.N is None else self.N[ax],
+                                         0 if self.k is None else self.k[ax])
+            plan = Plan(self.op, dtype, tuple(x.shape), specs)
+            self._plans[key] = plan
+        return plan(x)
+
+    def _repack(self, fn_name: str, x, out_shape, full_shape, axis: int, parts: int):
+        from . import _lib as L
+        from .engine import current_stream_ptr, jfx_dtype
+        lib = L.load()
+        out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
+        shp = (C.c_int64 * len(full_shape))(*full_shape)
+        L.check(getattr(lib, fn_name)(C.c_void_p(current_stream_ptr()), C.c_void_p(x.data_ptr()),
+                                      C.c_void_p(out.data_ptr()), shp, len(full_shape), axis, parts,
+                                      jfx_dtype(x.dtype)))
+        return out
+
+    def pack(self, x, split_axis, parts):
+        x = x.contiguous()
+        shp = list(x.shape)
+        shp[split_axis] //= parts
+        return self._repack("jfx_slab_pack", x, [parts] + shp, list(x.shape), split_axis, parts)
+
+    def unpack(self, blocks, concat_axis, parts):
+        blocks = blocks.contiguous()
+        shp = list(blocks.shape[1:])
+        shp[concat_axis] *= parts
+        return self._repack("jfx_slab_unpack", blocks, shp, shp, concat_axis, parts)
+
+
+class SlabTensorProduct:
+    """Distributed face of a TensorProductSpace: same four transforms on local blocks.
+
+    `backward` / `backward_primitive` take the spectral block (axis 0 sharded) and return the
+    physical block (axis 1 sharded); `forward` / `scalar_product` the reverse — the sharding contract
+    pinned by the reference's `tests/galerkin/test_forward_backward_spmd.py:71-75`."""
+
+    def __init__(self, space, group=None):
+        self.space = space
+        self.group = group
+        self._backends = {}
+
+    @property
+    def world_size(self) -> int:
+        return dist.get_world_size(self.group) if dist is not None and dist.is_initialized() else 1
+
+    def _backend(self, op, N=None, k=None):
+        key = (op, N, k)
+        b = self._backends.get(key)
+        if b is None:
+            b = self._backends[key] = EngineSlabBackend(self.space, op, N, k)
+        return b
+
+    def backward(self, c_local, N=None):
+        from . import _lib as L
+        return apply_separable_slab(c_local, SPECTRAL, self._backend(L.OP_BACKWARD, N), self.world_size)
+
+    def backward_primitive(self, c_local, k, N=None):
+        from . import _lib as L
+        return apply_separable_slab(c_local, SPECTRAL, self._backend(L.OP_BACKWARD_PRIMITIVE, N, tuple(k)),
+                                    self.world_size)
+
+    def forward(self, u_local):
+        from . import _lib as L
+        return apply_separable_slab(u_local, PHYSICAL, self._backend(L.OP_FORWARD), self.world_size)
+
+    def scalar_product(self, u_local):
+        from . import _lib as L
+        return apply_separable_slab(u_local, PHYSICAL, self._backend(L.OP_SCALAR_PRODUCT), self.world_size)
+
+
+def local_block(x, sharding: str, rank: int, world_size: int):
+    """The block of a global array owned by `rank` under `sharding` (numpy or torch)."""
+    ax = sharded_axis(sharding)
+    n = x.shape[ax]
+    if n % world_size:
+        raise ValueError(f"axis {ax} of extent {n} is not divisible by {world_size} devices")
+    b = n // world_size
+    idx = [slice(None)] * x.ndim
+    idx[ax] = slice(rank * b, (rank + 1) * b)
+    return x[tuple(idx)]

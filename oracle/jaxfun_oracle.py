@@ -29,6 +29,7 @@ import sympy as sp
 from scipy.special import roots_jacobi
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "jaxfun_b200", "data")
+WORKERS = os.cpu_count() or 1  # scipy.fft threads (the CPU baseline uses every host core)
 n_sym = sp.Symbol("n", integer=True)
 alf, bet = sp.symbols("a,b", real=True)
 delta = sp.KroneckerDelta
@@ -313,8 +314,14 @@ class Jacobi(OrthogonalSpace):
         x, w = roots_jacobi(N, float(self.alpha), float(self.beta))
         return np.array(x), np.array(w)
 
+    #: bench-only switch: evaluate the series as Vandermonde @ c (the generic orthogonal.py:129 form,
+    #: BLAS-backed) instead of the reference's N-step recurrence scan; same sums, different rounding
+    fast_backward = False
+
     # Jacobi.py:65-110 (vectorised over points X and columns of c)
     def _evaluate(self, X, c):
+        if self.fast_backward:
+            return OrthogonalSpace._evaluate(self, X, c)
         N = c.shape[0]
         am, ap, aa = self._rec(N)
         X = np.asarray(X, dtype=float)[:, None]
@@ -502,14 +509,14 @@ class Chebyshev(Jacobi):
 def _dct2(x, n):
     """jax.scipy.fft.dct(x, n=n) (type 2, norm=None) along axis 0; complex input = linear extension."""
     if np.iscomplexobj(x):
-        return scipy.fft.dct(x.real, type=2, n=n, axis=0) + 1j * scipy.fft.dct(x.imag, type=2, n=n, axis=0)
-    return scipy.fft.dct(x, type=2, n=n, axis=0)
+        return scipy.fft.dct(x.real, type=2, n=n, axis=0, workers=WORKERS) + 1j * scipy.fft.dct(x.imag, type=2, n=n, axis=0, workers=WORKERS)
+    return scipy.fft.dct(x, type=2, n=n, axis=0, workers=WORKERS)
 
 
 def _idct2(x, n):
     if np.iscomplexobj(x):
-        return scipy.fft.idct(x.real, type=2, n=n, axis=0) + 1j * scipy.fft.idct(x.imag, type=2, n=n, axis=0)
-    return scipy.fft.idct(x, type=2, n=n, axis=0)
+        return scipy.fft.idct(x.real, type=2, n=n, axis=0, workers=WORKERS) + 1j * scipy.fft.idct(x.imag, type=2, n=n, axis=0, workers=WORKERS)
+    return scipy.fft.idct(x, type=2, n=n, axis=0, workers=WORKERS)
 
 
 def dst(x, type=2, n=None):
@@ -652,13 +659,13 @@ class Fourier(OrthogonalSpace):
             assert n >= Lc
             if n > Lc:
                 cm = np.concatenate([cm[: Lc // 2], np.zeros((n - Lc,) + cm.shape[1:], dtype=cm.dtype), cm[Lc // 2:]])
-            return np.fft.ifft(cm, axis=0, norm="forward")
+            return scipy.fft.ifft(cm, axis=0, norm="forward", workers=WORKERS)
         return _along(f, np.asarray(c, dtype=complex), axis)
 
     # Fourier.py:150-163
     def scalar_product(self, u, axis=-1):
         def f(um):
-            out = np.fft.fft(um, axis=0, norm="forward") * 2 * np.pi / float(self.domain_factor)
+            out = scipy.fft.fft(um, axis=0, norm="forward", workers=WORKERS) * 2 * np.pi / float(self.domain_factor)
             return out[self.wavenumbers()] if um.shape[0] > self.N else out
         return _along(f, np.asarray(u, dtype=complex), axis)
 
@@ -666,7 +673,7 @@ class Fourier(OrthogonalSpace):
     def forward(self, u, axis=-1):
         def f(um):
             assert um.shape[0] >= self.N
-            out = np.fft.fft(um, axis=0, norm="forward")
+            out = scipy.fft.fft(um, axis=0, norm="forward", workers=WORKERS)
             return out[self.wavenumbers()] if um.shape[0] > self.N else out
         return _along(f, np.asarray(u, dtype=complex), axis)
 
