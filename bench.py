@@ -256,6 +256,13 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    # nvidia-smi needs ~1 s to deliver samples: if the timed region was shorter, keep running the SAME
+    # steps (untimed) so the clock/throttle record reflects this workload under load
+    t_load = time.perf_counter()
+    while (ms * 1e-3 + time.perf_counter() - t_load) < 2.0:
+        step()
+        torch.cuda.synchronize()
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
     if multi:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)

@@ -152,6 +152,10 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
     p.geom.inner = prod(cur, ax + 1, d->ndim);
     p.geom.n_in = n_in;
     p.geom.n_out = n_out;
+    if (p.fast)
+      JFX_REQUIRE(fast_geometry_ok(p.geom, d->dtype), JFX_ERR_UNSUPPORTED,
+                  "axis %d: real data with odd inner extent %lld has no fast kernel; supply a dense table", ax,
+                  (long long)p.geom.inner);
     if (!p.fast) {
       p.dmma = table_apply_uses_dmma(p.geom, d->dtype, p.table_complex);
       const double cm = dtype_is_complex(d->dtype) ? (p.table_complex ? 4.0 : 2.0) : 1.0;

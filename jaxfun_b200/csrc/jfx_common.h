@@ -78,6 +78,7 @@ struct FastParams {
   double domain_factor;
 };
 bool fast_available(int basis, int n, int dtype);
+bool fast_geometry_ok(const AxisGeom& g, int dtype);
 // twiddle tables etc. are owned by a FastTables object created at plan time
 struct FastTables;
 int fast_tables_create(const FastParams& p, int dtype, FastTables** out);

@@ -1,22 +1,462 @@
-// Fast transform kernels (Chebyshev DCT, Fourier FFT).  Placeholder until the radix kernels land:
-// reports "no fast path" so every axis is served by the dense table kernels.
+// Fast transform kernels: Fourier c2c FFT and Chebyshev DCT-II / DCT-III along one tensor axis.
+//
+// Reference semantics (all formulas restated from the Python reference):
+//   Fourier.backward        galerkin/Fourier.py:126-148   mid-spectrum zero pad + ifft(norm="forward")
+//   Fourier.forward         galerkin/Fourier.py:165-180   fft(norm="forward") + wavenumber gather
+//   Fourier.scalar_product  galerkin/Fourier.py:150-163   ... * 2 pi / domain_factor
+//   Fourier.derivative      galerkin/Fourier.py:206-219   (i m)^k prescale (host table `pre`)
+//   Chebyshev.backward      galerkin/Chebyshev.py:225-241 0.5*uh[0] + n*idct(uh), uh = c (-1)^k
+//   Chebyshev.forward       galerkin/Chebyshev.py:243-260 dct(u), uh[0]/2, *(-1)^k/n, truncate
+//   Chebyshev.scalar_product galerkin/Chebyshev.py:262-279 dct(u) * pi (-1)^k / (2 n df), truncate
+//
+// Design: one CTA owns a tile of LPB lines of length n (n = power of two, 16..4096) in shared
+// memory.  Global traffic is one coalesced read and one coalesced write of the tile (16-byte
+// elements; for a strided axis the tile is [n, LPB] with the LPB neighbouring lines contiguous in
+// memory).  The FFT itself is a Stockham autosort with radix-4/8/16 register butterflies, twiddles
+// from a host-computed fp64 table, 2-3 passes through padded (bank-conflict-skewed) shared memory.
+// DCTs use the n-point complex FFT of TWO real sequences at once: the real and imaginary parts of a
+// complex line, or two neighbouring real lines ("real pair" mode) — so real data costs half a
+// complex transform per line.  The cosine transforms' half-sample twiddles, the (-1)^k signs, the
+// padding / truncation / wavenumber gather and all scalings are fused into the tile load / store.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <vector>
+
 #include "jfx_common.h"
 
 namespace jfx {
 
-struct FastTables { int dummy; };
+template <typename T> struct Cpx { T x, y; };
+template <typename T> __device__ __forceinline__ Cpx<T> operator+(Cpx<T> a, Cpx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T> __device__ __forceinline__ Cpx<T> operator-(Cpx<T> a, Cpx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T> __device__ __forceinline__ Cpx<T> cmul(Cpx<T> a, Cpx<T> b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T> __device__ __forceinline__ Cpx<T> conj_(Cpx<T> a) { return {a.x, -a.y}; }
 
-bool fast_available(int, int, int) { return false; }
-int fast_tables_create(const FastParams&, int, FastTables** out) {
+// cos(2 pi k/16), sin(2 pi k/16), k = 0..7
+__device__ constexpr double kCos16[8] = {1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173,
+                                         0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128673848};
+__device__ constexpr double kSin16[8] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128673848,
+                                         1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173};
+
+// In-register forward DFT of R points, natural order in and out (decimation in time).
+template <typename T, int R> struct Dft {
+  static __device__ __forceinline__ void run(Cpx<T>* v) {
+    Cpx<T> e[R / 2], o[R / 2];
+#pragma unroll
+    for (int i = 0; i < R / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    Dft<T, R / 2>::run(e);
+    Dft<T, R / 2>::run(o);
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      Cpx<T> t;
+      if (k == 0) t = o[k];
+      else if (4 * k == R) t = Cpx<T>{o[k].y, -o[k].x};   // * (-i)
+      else {
+        const T c = (T)kCos16[k * (16 / R)], s = (T)kSin16[k * (16 / R)];  // W = c - i s
+        t = Cpx<T>{o[k].x * c + o[k].y * s, o[k].y * c - o[k].x * s};
+      }
+      v[k] = e[k] + t;
+      v[k + R / 2] = e[k] - t;
+    }
+  }
+};
+template <typename T> struct Dft<T, 2> {
+  static __device__ __forceinline__ void run(Cpx<T>* v) {
+    Cpx<T> a = v[0] + v[1], b = v[0] - v[1];
+    v[0] = a; v[1] = b;
+  }
+};
+template <typename T> struct Dft<T, 1> { static __device__ __forceinline__ void run(Cpx<T>*) {} };
+
+// radix plans
+template <int N> struct Plan;
+template <> struct Plan<16>   { static constexpr int R0 = 4,  R1 = 4,  R2 = 1;  };
+template <> struct Plan<32>   { static constexpr int R0 = 8,  R1 = 4,  R2 = 1;  };
+template <> struct Plan<64>   { static constexpr int R0 = 8,  R1 = 8,  R2 = 1;  };
+template <> struct Plan<128>  { static constexpr int R0 = 16, R1 = 8,  R2 = 1;  };
+template <> struct Plan<256>  { static constexpr int R0 = 16, R1 = 16, R2 = 1;  };
+template <> struct Plan<512>  { static constexpr int R0 = 8,  R1 = 8,  R2 = 8;  };
+template <> struct Plan<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8;  };
+template <> struct Plan<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8;  };
+template <> struct Plan<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16; };
+
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
+template <int N> struct Geo {
+  static constexpr int RMAX = cmax(Plan<N>::R0, cmax(Plan<N>::R1, Plan<N>::R2));
+  static constexpr int TN = N / RMAX;                       // threads per line
+  static constexpr int LOGSK = ilog2(Plan<N>::R0);          // smem skew: i + (i >> LOGSK)
+  static constexpr int PITCH = N + (N >> LOGSK) + 1;        // odd -> conflict-free across lines
+};
+
+template <int LOGSK> __device__ __forceinline__ int sk(int i) { return i + (i >> LOGSK); }
+
+// one Stockham pass over a line held in shared memory (in place: load all, sync, store all)
+template <typename T, int N, int R, int NS>
+__device__ __forceinline__ void fft_pass(Cpx<T>* __restrict__ S, int j, const Cpx<T>* __restrict__ tw) {
+  constexpr int TN = Geo<N>::TN, LOGSK = Geo<N>::LOGSK;
+  constexpr int BPT = (N / R) / TN;
+  Cpx<T> v[BPT][R];
+#pragma unroll
+  for (int bf = 0; bf < BPT; ++bf) {
+    const int jj = j + bf * TN;
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[bf][r] = S[sk<LOGSK>(jj + r * (N / R))];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int bf = 0; bf < BPT; ++bf) {
+    const int jj = j + bf * TN;
+    const int k = jj % NS;
+    if (NS > 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[bf][r] = cmul(v[bf][r], tw[(r * k) * (N / (NS * R))]);
+    }
+    Dft<T, R>::run(v[bf]);
+    const int j0 = (jj / NS) * NS * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) S[sk<LOGSK>(j0 + r * NS)] = v[bf][r];
+  }
+  __syncthreads();
+}
+
+struct FftArgs {
+  const void* in;
+  void* out;
+  const void* tw;     // W_n^m = exp(-2 pi i m / n), m < n
+  const void* half;   // exp(-i pi k / (2n)), k < n          (Chebyshev)
+  const void* pre;    // per-coefficient complex prescale    (Fourier backward derivative), or null
+  long long lines;    // complex lines (real-pair mode: pairs of real lines)
+  long long inner;    // complex inner extent; 1 = contiguous axis
+  long long real_lines;
+  int n_in, n_out;    // axis extents of the input / output arrays
+  int n_modes;        // N
+  int kind;
+  int real_pair;
+  int lpb;
+  double scale;
+};
+
+template <typename T, int N>
+__global__ void __launch_bounds__(Geo<N>::TN >= 64 ? 512 : 256)
+fft_axis_kernel(const FftArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cpx<T>* S = reinterpret_cast<Cpx<T>*>(smem_raw);
+  constexpr int TN = Geo<N>::TN, PITCH = Geo<N>::PITCH, LOGSK = Geo<N>::LOGSK;
+  const int lpb = a.lpb;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const long long line0 = (long long)blockIdx.x * lpb;
+  const Cpx<T>* tw = reinterpret_cast<const Cpx<T>*>(a.tw);
+  const Cpx<T>* half = reinterpret_cast<const Cpx<T>*>(a.half);
+  const bool strided = a.inner > 1;
+  const int kind = a.kind;
+  const bool cheb = kind <= FAST_CHEB_SCALAR;
+  const bool to_phys = (kind == FAST_CHEB_BACKWARD || kind == FAST_FOURIER_BACKWARD);
+
+  // element (line l, axis index i) of the input / output arrays
+  auto load_in = [&](long long l, int i) -> Cpx<T> {
+    if (a.real_pair) {
+      const T* p = reinterpret_cast<const T*>(a.in);
+      const long long r0 = 2 * l, r1 = 2 * l + 1;
+      Cpx<T> v;
+      v.x = p[r0 * a.n_in + i];
+      v.y = (r1 < a.real_lines) ? p[r1 * a.n_in + i] : T(0);
+      return v;
+    }
+    const long long o = l / a.inner, b = l % a.inner;
+    return reinterpret_cast<const Cpx<T>*>(a.in)[(o * a.n_in + i) * a.inner + b];
+  };
+  auto store_out = [&](long long l, int i, Cpx<T> v) {
+    if (a.real_pair) {
+      T* p = reinterpret_cast<T*>(a.out);
+      const long long r0 = 2 * l, r1 = 2 * l + 1;
+      p[r0 * a.n_out + i] = v.x;
+      if (r1 < a.real_lines) p[r1 * a.n_out + i] = v.y;
+      return;
+    }
+    const long long o = l / a.inner, b = l % a.inner;
+    reinterpret_cast<Cpx<T>*>(a.out)[(o * a.n_out + i) * a.inner + b] = v;
+  };
+
+  // ---------------- stage in: natural-order FFT input into shared memory ----------------
+  const int total = lpb * N;
+  for (int e = tid; e < total; e += nthr) {
+    int ll, i;
+    if (strided) { ll = e % lpb; i = e / lpb; } else { ll = e / N; i = e % N; }
+    const long long l = line0 + ll;
+    Cpx<T> z{T(0), T(0)};
+    int dst = i;
+    if (l < a.lines) {
+      if (kind == FAST_FOURIER_BACKWARD) {
+        // padded spectrum position i <- coefficient p
+        const int nc = a.n_in, hlf = nc / 2;
+        int p = -1;
+        if (N == nc) p = i;
+        else if (i < hlf) p = i;
+        else if (i >= N - (nc - hlf)) p = i - (N - nc);
+        if (p >= 0) {
+          z = load_in(l, p);
+          if (a.pre) z = cmul(z, reinterpret_cast<const Cpx<T>*>(a.pre)[p]);
+        }
+        z = conj_(z);                                   // inverse DFT = conj(FFT(conj(.)))
+      } else if (kind == FAST_CHEB_BACKWARD) {
+        // z_0 = A_0 ; z_k = e^{+i pi k/(2n)}/2 * (A_k - i A_{n-k}),  A_k = c_k (-1)^k (0 beyond n_in)
+        const int k = i, nc = a.n_in;
+        Cpx<T> ak{T(0), T(0)}, am{T(0), T(0)};
+        if (k < nc) { ak = load_in(l, k); if (k & 1) { ak.x = -ak.x; ak.y = -ak.y; } }
+        if (k == 0) z = ak;
+        else {
+          const int m = N - k;
+          if (m < nc) { am = load_in(l, m); if (m & 1) { am.x = -am.x; am.y = -am.y; } }
+          Cpx<T> w{ak.x + am.y, ak.y - am.x};            // A_k - i A_{n-k}
+          Cpx<T> t = conj_(half[k]);                      // e^{+i pi k/(2n)}
+          z = cmul(t, w);
+          z.x *= T(0.5); z.y *= T(0.5);
+        }
+        z = conj_(z);
+      } else if (cheb) {
+        // DCT-II: v[m] = x[2m], v[n-1-m] = x[2m+1]
+        z = load_in(l, i);
+        dst = (i & 1) ? (N - 1 - (i >> 1)) : (i >> 1);
+      } else {
+        z = load_in(l, i);                               // Fourier forward / scalar product
+      }
+    }
+    S[ll * PITCH + sk<LOGSK>(dst)] = z;
+  }
+  __syncthreads();
+
+  // ---------------- FFT passes ----------------
+  {
+    const int ll = tid / TN, j = tid % TN;
+    Cpx<T>* Sl = S + ll * PITCH;
+    using P = Plan<N>;
+    fft_pass<T, N, P::R0, 1>(Sl, j, tw);
+    fft_pass<T, N, P::R1, P::R0>(Sl, j, tw);
+    if constexpr (P::R2 > 1) fft_pass<T, N, P::R2, P::R0 * P::R1>(Sl, j, tw);
+  }
+
+  // ---------------- stage out ----------------
+  const int nout = a.n_out;
+  const int total_out = lpb * nout;
+  const T scale = (T)a.scale;
+  for (int e = tid; e < total_out; e += nthr) {
+    int ll, q;
+    if (strided) { ll = e % lpb; q = e / lpb; } else { ll = e / nout; q = e % nout; }
+    const long long l = line0 + ll;
+    if (l >= a.lines) continue;
+    const Cpx<T>* Sl = S + ll * PITCH;
+    Cpx<T> v;
+    if (kind == FAST_FOURIER_BACKWARD) {
+      v = conj_(Sl[sk<LOGSK>(q)]);
+    } else if (kind == FAST_CHEB_BACKWARD) {
+      const int m = (q & 1) ? (N - 1 - (q >> 1)) : (q >> 1);
+      v = conj_(Sl[sk<LOGSK>(m)]);
+    } else if (cheb) {
+      // C_k = t_k W[k] + conj(t_k) W[n-k],  t_k = e^{-i pi k/(2n)}
+      const int k = q;
+      const Cpx<T> t = half[k];
+      const Cpx<T> wk = Sl[sk<LOGSK>(k)], wm = Sl[sk<LOGSK>((N - k) & (N - 1))];
+      v = cmul(t, wk) + cmul(conj_(t), wm);
+      T s = scale;
+      if (k & 1) s = -s;
+      if (k == 0 && kind == FAST_CHEB_FORWARD) s *= T(0.5);
+      v.x *= s; v.y *= s;
+    } else {
+      // Fourier forward: gather by wavenumber when truncating
+      const int nm = a.n_modes;
+      int i = q;
+      if (N > nm && q >= (nm + 1) / 2) i = N + q - nm;
+      v = Sl[sk<LOGSK>(i)];
+      v.x *= scale; v.y *= scale;
+    }
+    store_out(l, q, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct FastTables {
+  int n = 0;
+  bool dbl = true;
+  void* d_tw = nullptr;
+  void* d_half = nullptr;
+  void* d_pre = nullptr;
+  ~FastTables() {
+    if (d_tw) cudaFree(d_tw);
+    if (d_half) cudaFree(d_half);
+    if (d_pre) cudaFree(d_pre);
+  }
+};
+
+static bool supported_n(int n) {
+  switch (n) {
+    case 16: case 32: case 64: case 128: case 256: case 512: case 1024: case 2048: case 4096: return true;
+  }
+  return false;
+}
+
+bool fast_geometry_ok(const AxisGeom& g, int dtype) {
+  // real data: last axis (pairs of lines) or an even inner extent (neighbouring lines = re/im)
+  if (dtype_is_complex(dtype)) return true;
+  return g.inner == 1 || g.inner % 2 == 0;
+}
+
+bool fast_available(int basis, int n, int dtype) {
+  if (basis != JFX_BASIS_CHEBYSHEV && basis != JFX_BASIS_FOURIER) return false;
+  if (basis == JFX_BASIS_FOURIER && !dtype_is_complex(dtype)) return false;
+  return supported_n(n);
+}
+
+template <typename T>
+static int upload_complex(const std::vector<long double>& re, const std::vector<long double>& im, void** dptr) {
+  std::vector<T> h(2 * re.size());
+  for (size_t i = 0; i < re.size(); ++i) { h[2 * i] = (T)re[i]; h[2 * i + 1] = (T)im[i]; }
+  JFX_CUDA_OK(cudaMalloc(dptr, h.size() * sizeof(T)));
+  JFX_CUDA_OK(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return JFX_OK;
+}
+
+// exp(-i pi num/den) with exact octant reduction, long double
+static void expmipi(long long num, long long den, long double* c, long double* s) {
+  num %= 2 * den;
+  if (num < 0) num += 2 * den;
+  const long double PI = 3.141592653589793238462643383279502884L;
+  // reduce to [0, den/2] using symmetries about pi/2 and pi
+  long long r = num;
+  int sgn_c = 1, sgn_s = 1;
+  if (r >= den) { r -= den; sgn_c = -sgn_c; sgn_s = -sgn_s; }   // angle - pi
+  if (2 * r > den) { r = den - r; sgn_c = -sgn_c; }               // pi - angle
+  long double ang = PI * (long double)r / (long double)den;
+  long double cc, ss;
+  if (4 * r <= den) { cc = cosl(ang); ss = sinl(ang); }
+  else { long double a2 = PI * (long double)(den - 2 * r) / (long double)(2 * den); cc = sinl(a2); ss = cosl(a2); }
+  *c = sgn_c * cc;
+  *s = -sgn_s * ss;  // exp(-i theta) = cos - i sin
+}
+
+int fast_tables_create(const FastParams& p, int dtype, FastTables** out) {
   *out = nullptr;
-  set_error("no fast transform kernel for this size");
+  const int n = p.n_quad;
+  JFX_REQUIRE(supported_n(n), JFX_ERR_UNSUPPORTED, "no fast transform kernel for n=%d", n);
+  const bool cheb = p.kind <= FAST_CHEB_SCALAR;
+  JFX_REQUIRE(!(cheb && p.deriv != 0), JFX_ERR_UNSUPPORTED,
+              "Chebyshev derivative orders are folded into dense tables by the host");
+  FastTables* t = new FastTables;
+  t->n = n;
+  t->dbl = dtype_is_double(dtype);
+  std::vector<long double> re(n), im(n);
+  for (int m = 0; m < n; ++m) expmipi(2LL * m, n, &re[m], &im[m]);
+  int rc = t->dbl ? upload_complex<double>(re, im, &t->d_tw) : upload_complex<float>(re, im, &t->d_tw);
+  if (rc == JFX_OK && cheb) {
+    for (int k = 0; k < n; ++k) expmipi(k, 2LL * n, &re[k], &im[k]);
+    rc = t->dbl ? upload_complex<double>(re, im, &t->d_half) : upload_complex<float>(re, im, &t->d_half);
+  }
+  if (rc == JFX_OK && p.kind == FAST_FOURIER_BACKWARD && p.deriv > 0) {
+    // (i m)^k * df^k, Nyquist mode removed for odd k   (Fourier.py:206-219, orthogonal.py:245)
+    const int nc = p.n_modes;
+    std::vector<long double> pr(nc), pi_(nc);
+    const long double dfk = powl((long double)p.domain_factor, p.deriv);
+    for (int q = 0; q < nc; ++q) {
+      long long m = (q < (nc + 1) / 2) ? q : q - nc;
+      if ((p.deriv & 1) && (nc % 2 == 0) && q == nc / 2) m = 0;
+      long double mag = powl((long double)m, p.deriv) * dfk;   // m^k (sign kept for odd k)
+      switch (p.deriv & 3) {  // i^k
+        case 0: pr[q] = mag; pi_[q] = 0; break;
+        case 1: pr[q] = 0; pi_[q] = mag; break;
+        case 2: pr[q] = -mag; pi_[q] = 0; break;
+        default: pr[q] = 0; pi_[q] = -mag; break;
+      }
+    }
+    rc = t->dbl ? upload_complex<double>(pr, pi_, &t->d_pre) : upload_complex<float>(pr, pi_, &t->d_pre);
+  }
+  if (rc != JFX_OK) { delete t; return rc; }
+  *out = t;
+  return JFX_OK;
+}
+
+void fast_tables_destroy(FastTables* t) { delete t; }
+
+template <typename T, int N>
+static int launch_n(cudaStream_t s, const FftArgs& a_in, bool strided) {
+  FftArgs a = a_in;
+  constexpr int TN = Geo<N>::TN;
+  const int max_threads = TN >= 64 ? 512 : 256;
+  const size_t line_bytes = (size_t)Geo<N>::PITCH * sizeof(Cpx<T>);
+  int lpb = max_threads / TN;
+  if (lpb < 1) lpb = 1;
+  const size_t smem_cap = 200 * 1024;
+  while (lpb > 1 && (size_t)lpb * line_bytes > smem_cap) lpb /= 2;
+  // strided axes want >= 8 neighbouring lines (128 B rows); small problems shrink the tile
+  while (lpb > 1 && (long long)(lpb / 2) >= a.lines) lpb /= 2;
+  a.lpb = lpb;
+  const size_t smem = (size_t)lpb * line_bytes;
+  static bool attr_done = false;
+  if (!attr_done) {
+    JFX_CUDA_OK(cudaFuncSetAttribute(fft_axis_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap + 8192));
+    attr_done = true;
+  }
+  const long long blocks = (a.lines + lpb - 1) / lpb;
+  JFX_REQUIRE(blocks < (1ll << 31), JFX_ERR_UNSUPPORTED, "too many lines");
+  (void)strided;
+  fft_axis_kernel<T, N><<<(unsigned)blocks, lpb * TN, smem, s>>>(a);
+  JFX_CUDA_OK(cudaGetLastError());
+  return JFX_OK;
+}
+
+template <typename T>
+static int launch_t(cudaStream_t s, const FftArgs& a, int n, bool strided) {
+  switch (n) {
+    case 16: return launch_n<T, 16>(s, a, strided);
+    case 32: return launch_n<T, 32>(s, a, strided);
+    case 64: return launch_n<T, 64>(s, a, strided);
+    case 128: return launch_n<T, 128>(s, a, strided);
+    case 256: return launch_n<T, 256>(s, a, strided);
+    case 512: return launch_n<T, 512>(s, a, strided);
+    case 1024: return launch_n<T, 1024>(s, a, strided);
+    case 2048: return launch_n<T, 2048>(s, a, strided);
+    case 4096: return launch_n<T, 4096>(s, a, strided);
+  }
+  set_error("no fast transform kernel for n=%d", n);
   return JFX_ERR_UNSUPPORTED;
 }
-void fast_tables_destroy(FastTables* t) { delete t; }
-int launch_fast_axis(cudaStream_t, const AxisGeom&, int, const FastParams&, const FastTables*,
-                     const void*, void*) {
-  set_error("no fast transform kernel for this size");
-  return JFX_ERR_UNSUPPORTED;
+
+int launch_fast_axis(cudaStream_t s, const AxisGeom& g, int dtype, const FastParams& p, const FastTables* t,
+                     const void* in, void* out) {
+  JFX_REQUIRE(t != nullptr, JFX_ERR_INVALID, "missing fast tables");
+  const bool cplx = dtype_is_complex(dtype);
+  const bool cheb = p.kind <= FAST_CHEB_SCALAR;
+  FftArgs a{};
+  a.in = in; a.out = out;
+  a.tw = t->d_tw; a.half = t->d_half; a.pre = t->d_pre;
+  a.n_in = g.n_in; a.n_out = g.n_out; a.n_modes = p.n_modes; a.kind = p.kind;
+  const double n = (double)p.n_quad;
+  const double PI = 3.14159265358979323846;
+  switch (p.kind) {
+    case FAST_CHEB_FORWARD: a.scale = 1.0 / n; break;
+    case FAST_CHEB_SCALAR: a.scale = PI / n / 2.0 / p.domain_factor; break;
+    case FAST_FOURIER_FORWARD: a.scale = 1.0 / n; break;
+    case FAST_FOURIER_SCALAR: a.scale = (1.0 / n) * 2.0 * PI / p.domain_factor; break;
+    default: a.scale = 1.0;
+  }
+  if (g.outer * g.inner == 0) return JFX_OK;
+  if (cplx) {
+    a.inner = g.inner; a.lines = g.outer * g.inner; a.real_pair = 0;
+  } else {
+    JFX_REQUIRE(cheb, JFX_ERR_INVALID, "Fourier axes need complex data");
+    if (g.inner == 1) {
+      a.real_pair = 1; a.real_lines = g.outer; a.lines = (g.outer + 1) / 2; a.inner = 1;
+    } else if (g.inner % 2 == 0) {
+      a.real_pair = 0; a.inner = g.inner / 2; a.lines = g.outer * a.inner;  // neighbouring real lines = (re, im)
+    } else {
+      set_error("real Chebyshev axis with odd inner extent %lld has no fast path", (long long)g.inner);
+      return JFX_ERR_UNSUPPORTED;
+    }
+  }
+  return dtype_is_double(dtype) ? launch_t<double>(s, a, p.n_quad, a.inner > 1)
+                                : launch_t<float>(s, a, p.n_quad, a.inner > 1);
 }
 
 }  // namespace jfx

@@ -186,7 +186,9 @@ class OrthogonalSpace:
             if op == L.OP_FORWARD:
                 T = T / self.mass_diagonal()[:, None]
         else:
-            xj = self.quad_points_and_weights(n_quad)[0]
+            # the reference evaluates at mesh() (true domain) and maps back (orthogonal.py:226-227,
+            # 113-115); keep that round trip so the nodes carry the same rounding
+            xj = self.map_reference_domain(self.mesh("quadrature", n_quad))
             T = self.vandermonde(xj)[:, :n_coeff]          # backward: sum_k c_k psi_k(x_j)
             if deriv:
                 T = (float(self.domain_factor) ** deriv) * (T @ self.derivative_matrix(deriv, n_coeff))
@@ -194,7 +196,8 @@ class OrthogonalSpace:
         self._tables[key] = T
         return T
 
-    def axis_spec(self, op: int, n_in: int, dtype: int, N: int | None = None, k: int = 0) -> AxisSpec:
+    def axis_spec(self, op: int, n_in: int, dtype: int, N: int | None = None, k: int = 0,
+                  inner: int = 1) -> AxisSpec:
         """Engine description of this space's transform `op` along one axis of extent n_in."""
         if op in (L.OP_FORWARD, L.OP_SCALAR_PRODUCT):
             n_quad, n_coeff = n_in, self.N
@@ -204,7 +207,10 @@ class OrthogonalSpace:
             n_coeff = n_in
             assert n_coeff <= self.N, f"Coefficient length {n_coeff} exceeds N={self.N}"
             assert n_quad >= n_coeff, "backward only supports padding, not truncation"
-        if self.fast_basis != L.BASIS_NONE and fast_path_available(self.fast_basis, n_quad, dtype):
+        fast_ok = self.fast_basis != L.BASIS_NONE and fast_path_available(self.fast_basis, n_quad, dtype)
+        if self.fast_basis == L.BASIS_CHEBYSHEV and (k != 0 or (dtype in (L.F32, L.F64) and inner > 1 and inner % 2)):
+            fast_ok = False   # chebder^k is folded into a dense table; odd real inner extents have no DCT tile
+        if fast_ok:
             return AxisSpec(self.fast_basis, n_modes=(self.N if op in (L.OP_FORWARD, L.OP_SCALAR_PRODUCT) else n_coeff),
                             n_quad=n_quad, deriv=k, domain_factor=float(self.domain_factor))
         T = self._dense_table(op, n_coeff, n_quad, k)
@@ -224,7 +230,8 @@ class OrthogonalSpace:
             if table is not None:
                 spec = AxisSpec(L.BASIS_CTABLE if np.iscomplexobj(table) else L.BASIS_TABLE, table=table)
             else:
-                spec = self.axis_spec(op, x.shape[axis], dtype, N, k)
+                spec = self.axis_spec(op, x.shape[axis], dtype, N, k,
+                                      inner=int(np.prod(x.shape[axis + 1:], dtype=np.int64)))
             axes = [None] * x.ndim
             axes[axis] = spec
             plan = Plan(op, dtype, tuple(x.shape), axes)

@@ -94,7 +94,8 @@ class TensorProductSpace:
         specs = [None] * lead
         for ax, space in enumerate(self.basespaces):
             specs.append(space.axis_spec(op, shape[lead + ax], dtype,
-                                         None if N is None else N[ax], 0 if k is None else k[ax]))
+                                         None if N is None else N[ax], 0 if k is None else k[ax],
+                                         inner=int(np.prod(shape[lead + ax + 1:], dtype=np.int64))))
         return specs
 
     def _plan(self, op: int, x, N=None, k=None) -> Plan:

@@ -122,7 +122,8 @@ class EngineSlabBackend(SlabBackend):
             for ax in axes:
                 sp = self.space.basespaces[ax]
                 specs[ax] = sp.axis_spec(self.op, x.shape[ax], dtype, None if self.N is None else self.N[ax],
-                                         0 if self.k is None else self.k[ax])
+                                         0 if self.k is None else self.k[ax],
+                                         inner=int(np.prod(x.shape[ax + 1:], dtype=np.int64)))
             plan = Plan(self.op, dtype, tuple(x.shape), specs)
             self._plans[key] = plan
         return plan(x)
