@@ -94,6 +94,8 @@ template <int N> struct Geo {
 
 template <int LOGSK> __device__ __forceinline__ int sk(int i) { return i + (i >> LOGSK); }
 
+template <int TN> __device__ __forceinline__ void line_sync();
+
 // one Stockham pass over a line held in shared memory (in place: load all, sync, store all)
 template <typename T, int N, int R, int NS>
 __device__ __forceinline__ void fft_pass(Cpx<T>* __restrict__ S, int j, const Cpx<T>* __restrict__ tw) {
@@ -106,7 +108,7 @@ __device__ __forceinline__ void fft_pass(Cpx<T>* __restrict__ S, int j, const Cp
 #pragma unroll
     for (int r = 0; r < R; ++r) v[bf][r] = S[sk<LOGSK>(jj + r * (N / R))];
   }
-  __syncthreads();
+  line_sync<TN>();
 #pragma unroll
   for (int bf = 0; bf < BPT; ++bf) {
     const int jj = j + bf * TN;
@@ -120,7 +122,7 @@ __device__ __forceinline__ void fft_pass(Cpx<T>* __restrict__ S, int j, const Cp
 #pragma unroll
     for (int r = 0; r < R; ++r) S[sk<LOGSK>(j0 + r * NS)] = v[bf][r];
   }
-  __syncthreads();
+  line_sync<TN>();
 }
 
 struct FftArgs {
@@ -137,97 +139,125 @@ struct FftArgs {
   int kind;
   int real_pair;
   int lpb;
+  int log_lpb;
   double scale;
 };
+
+template <int TN> __device__ __forceinline__ void line_sync() {
+  // a line's TN threads live in one warp when TN <= 32: warp-level sync is enough
+  if (TN <= 32) __syncwarp(); else __syncthreads();
+}
 
 template <typename T, int N>
 __global__ void __launch_bounds__(Geo<N>::TN >= 64 ? 512 : 256)
 fft_axis_kernel(const FftArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cpx<T>* S = reinterpret_cast<Cpx<T>*>(smem_raw);
-  constexpr int TN = Geo<N>::TN, PITCH = Geo<N>::PITCH, LOGSK = Geo<N>::LOGSK;
-  const int lpb = a.lpb;
+  constexpr int TN = Geo<N>::TN, PITCH = Geo<N>::PITCH, LOGSK = Geo<N>::LOGSK, RMAX = Geo<N>::RMAX;
+  constexpr bool WARP_LINES = (TN <= 32);        // every line is owned by threads of a single warp
+  constexpr int LW = WARP_LINES ? 32 / TN : 1;    // lines per warp
+  const int lpb = a.lpb, log_lpb = a.log_lpb;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const long long line0 = (long long)blockIdx.x * lpb;
-  const Cpx<T>* tw = reinterpret_cast<const Cpx<T>*>(a.tw);
-  const Cpx<T>* half = reinterpret_cast<const Cpx<T>*>(a.half);
+  const Cpx<T>* __restrict__ tw = reinterpret_cast<const Cpx<T>*>(a.tw);
+  const Cpx<T>* __restrict__ half = reinterpret_cast<const Cpx<T>*>(a.half);
+  const Cpx<T>* __restrict__ pre = reinterpret_cast<const Cpx<T>*>(a.pre);
   const bool strided = a.inner > 1;
+  const bool warp_local = WARP_LINES && !strided;  // stage loops touch only the warp's own lines
   const int kind = a.kind;
   const bool cheb = kind <= FAST_CHEB_SCALAR;
-  const bool to_phys = (kind == FAST_CHEB_BACKWARD || kind == FAST_FOURIER_BACKWARD);
+  const int n_in = a.n_in, nout = a.n_out;
 
+  // tile element owned by this thread in stage iteration `it`: (local line, axis index)
+  auto tile_elem = [&](int it, int& ll, int& i) {
+    if (strided) { const int e = tid + it * nthr; ll = e & (lpb - 1); i = e >> log_lpb; }
+    else if (WARP_LINES) { const int e = it * 32 + lane; ll = warp * LW + e / N; i = e % N; }
+    else { const int e = tid + it * nthr; ll = e / N; i = e % N; }
+  };
   // element (line l, axis index i) of the input / output arrays
   auto load_in = [&](long long l, int i) -> Cpx<T> {
     if (a.real_pair) {
-      const T* p = reinterpret_cast<const T*>(a.in);
+      const T* __restrict__ p = reinterpret_cast<const T*>(a.in);
       const long long r0 = 2 * l, r1 = 2 * l + 1;
       Cpx<T> v;
-      v.x = p[r0 * a.n_in + i];
-      v.y = (r1 < a.real_lines) ? p[r1 * a.n_in + i] : T(0);
+      v.x = __ldg(p + r0 * n_in + i);
+      v.y = (r1 < a.real_lines) ? __ldg(p + r1 * n_in + i) : T(0);
       return v;
     }
     const long long o = l / a.inner, b = l % a.inner;
-    return reinterpret_cast<const Cpx<T>*>(a.in)[(o * a.n_in + i) * a.inner + b];
+    const Cpx<T>* __restrict__ p = reinterpret_cast<const Cpx<T>*>(a.in);
+    return p[(o * n_in + i) * a.inner + b];
   };
   auto store_out = [&](long long l, int i, Cpx<T> v) {
     if (a.real_pair) {
       T* p = reinterpret_cast<T*>(a.out);
       const long long r0 = 2 * l, r1 = 2 * l + 1;
-      p[r0 * a.n_out + i] = v.x;
-      if (r1 < a.real_lines) p[r1 * a.n_out + i] = v.y;
+      p[r0 * nout + i] = v.x;
+      if (r1 < a.real_lines) p[r1 * nout + i] = v.y;
       return;
     }
     const long long o = l / a.inner, b = l % a.inner;
-    reinterpret_cast<Cpx<T>*>(a.out)[(o * a.n_out + i) * a.inner + b] = v;
+    reinterpret_cast<Cpx<T>*>(a.out)[(o * nout + i) * a.inner + b] = v;
   };
 
-  // ---------------- stage in: natural-order FFT input into shared memory ----------------
-  const int total = lpb * N;
-  for (int e = tid; e < total; e += nthr) {
-    int ll, i;
-    if (strided) { ll = e % lpb; i = e / lpb; } else { ll = e / N; i = e % N; }
+  // ---------------- stage in: all global loads first (RMAX independent requests per thread) ------------
+  constexpr int CH = (RMAX < 4) ? RMAX : 4;   // loads in flight per thread per chunk (register budget)
+#pragma unroll 1
+  for (int it0 = 0; it0 < RMAX; it0 += CH) {
+  Cpx<T> z0[CH], z1[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int it = c; int ll, i;
+    tile_elem(it0 + c, ll, i);
     const long long l = line0 + ll;
-    Cpx<T> z{T(0), T(0)};
-    int dst = i;
+    z0[it] = Cpx<T>{T(0), T(0)};
+    z1[it] = Cpx<T>{T(0), T(0)};
     if (l < a.lines) {
       if (kind == FAST_FOURIER_BACKWARD) {
-        // padded spectrum position i <- coefficient p
-        const int nc = a.n_in, hlf = nc / 2;
+        const int hlf = n_in / 2;               // padded spectrum position i <- coefficient p
         int p = -1;
-        if (N == nc) p = i;
+        if (N == n_in) p = i;
         else if (i < hlf) p = i;
-        else if (i >= N - (nc - hlf)) p = i - (N - nc);
-        if (p >= 0) {
-          z = load_in(l, p);
-          if (a.pre) z = cmul(z, reinterpret_cast<const Cpx<T>*>(a.pre)[p]);
-        }
-        z = conj_(z);                                   // inverse DFT = conj(FFT(conj(.)))
+        else if (i >= N - (n_in - hlf)) p = i - (N - n_in);
+        if (p >= 0) { z0[it] = load_in(l, p); if (pre) z1[it] = pre[p]; }
       } else if (kind == FAST_CHEB_BACKWARD) {
-        // z_0 = A_0 ; z_k = e^{+i pi k/(2n)}/2 * (A_k - i A_{n-k}),  A_k = c_k (-1)^k (0 beyond n_in)
-        const int k = i, nc = a.n_in;
-        Cpx<T> ak{T(0), T(0)}, am{T(0), T(0)};
-        if (k < nc) { ak = load_in(l, k); if (k & 1) { ak.x = -ak.x; ak.y = -ak.y; } }
-        if (k == 0) z = ak;
-        else {
-          const int m = N - k;
-          if (m < nc) { am = load_in(l, m); if (m & 1) { am.x = -am.x; am.y = -am.y; } }
-          Cpx<T> w{ak.x + am.y, ak.y - am.x};            // A_k - i A_{n-k}
-          Cpx<T> t = conj_(half[k]);                      // e^{+i pi k/(2n)}
-          z = cmul(t, w);
-          z.x *= T(0.5); z.y *= T(0.5);
-        }
-        z = conj_(z);
-      } else if (cheb) {
-        // DCT-II: v[m] = x[2m], v[n-1-m] = x[2m+1]
-        z = load_in(l, i);
-        dst = (i & 1) ? (N - 1 - (i >> 1)) : (i >> 1);
+        if (i < n_in) z0[it] = load_in(l, i);
+        const int m = N - i;
+        if (i > 0 && m < n_in) z1[it] = load_in(l, m);
       } else {
-        z = load_in(l, i);                               // Fourier forward / scalar product
+        if (i < n_in) z0[it] = load_in(l, i);
       }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int it = c; int ll, i;
+    tile_elem(it0 + c, ll, i);
+    Cpx<T> z = z0[it];
+    int dst = i;
+    if (kind == FAST_FOURIER_BACKWARD) {
+      if (pre) z = cmul(z, z1[it]);
+      z = conj_(z);                                   // inverse DFT = conj(FFT(conj(.)))
+    } else if (kind == FAST_CHEB_BACKWARD) {
+      // z_0 = A_0 ; z_k = e^{+i pi k/(2n)}/2 * (A_k - i A_{n-k}),  A_k = c_k (-1)^k (0 beyond n_in)
+      Cpx<T> ak = z, am = z1[it];
+      if (i & 1) { ak.x = -ak.x; ak.y = -ak.y; }
+      if ((N - i) & 1) { am.x = -am.x; am.y = -am.y; }
+      if (i != 0) {
+        const Cpx<T> w{ak.x + am.y, ak.y - am.x};      // A_k - i A_{n-k}
+        const Cpx<T> t = conj_(half[i]);                // e^{+i pi k/(2n)}
+        z = cmul(t, w);
+        z.x *= T(0.5); z.y *= T(0.5);
+      } else z = ak;
+      z = conj_(z);
+    } else if (cheb) {
+      dst = (i & 1) ? (N - 1 - (i >> 1)) : (i >> 1);  // DCT-II: v[m] = x[2m], v[n-1-m] = x[2m+1]
     }
     S[ll * PITCH + sk<LOGSK>(dst)] = z;
   }
-  __syncthreads();
+  }
+  if (warp_local) __syncwarp(); else __syncthreads();
 
   // ---------------- FFT passes ----------------
   {
@@ -238,16 +268,16 @@ fft_axis_kernel(const FftArgs a) {
     fft_pass<T, N, P::R1, P::R0>(Sl, j, tw);
     if constexpr (P::R2 > 1) fft_pass<T, N, P::R2, P::R0 * P::R1>(Sl, j, tw);
   }
+  if (!warp_local) __syncthreads();
 
   // ---------------- stage out ----------------
-  const int nout = a.n_out;
-  const int total_out = lpb * nout;
   const T scale = (T)a.scale;
-  for (int e = tid; e < total_out; e += nthr) {
+#pragma unroll
+  for (int it = 0; it < RMAX; ++it) {
     int ll, q;
-    if (strided) { ll = e % lpb; q = e / lpb; } else { ll = e / nout; q = e % nout; }
+    tile_elem(it, ll, q);
     const long long l = line0 + ll;
-    if (l >= a.lines) continue;
+    if (l >= a.lines || q >= nout) continue;
     const Cpx<T>* Sl = S + ll * PITCH;
     Cpx<T> v;
     if (kind == FAST_FOURIER_BACKWARD) {
@@ -257,13 +287,12 @@ fft_axis_kernel(const FftArgs a) {
       v = conj_(Sl[sk<LOGSK>(m)]);
     } else if (cheb) {
       // C_k = t_k W[k] + conj(t_k) W[n-k],  t_k = e^{-i pi k/(2n)}
-      const int k = q;
-      const Cpx<T> t = half[k];
-      const Cpx<T> wk = Sl[sk<LOGSK>(k)], wm = Sl[sk<LOGSK>((N - k) & (N - 1))];
+      const Cpx<T> t = half[q];
+      const Cpx<T> wk = Sl[sk<LOGSK>(q)], wm = Sl[sk<LOGSK>((N - q) & (N - 1))];
       v = cmul(t, wk) + cmul(conj_(t), wm);
       T s = scale;
-      if (k & 1) s = -s;
-      if (k == 0 && kind == FAST_CHEB_FORWARD) s *= T(0.5);
+      if (q & 1) s = -s;
+      if (q == 0 && kind == FAST_CHEB_FORWARD) s *= T(0.5);
       v.x *= s; v.y *= s;
     } else {
       // Fourier forward: gather by wavenumber when truncating
@@ -392,6 +421,8 @@ static int launch_n(cudaStream_t s, const FftArgs& a_in, bool strided) {
   // strided axes want >= 8 neighbouring lines (128 B rows); small problems shrink the tile
   while (lpb > 1 && (long long)(lpb / 2) >= a.lines) lpb /= 2;
   a.lpb = lpb;
+  a.log_lpb = 0;
+  while ((1 << a.log_lpb) < lpb) ++a.log_lpb;
   const size_t smem = (size_t)lpb * line_bytes;
   static bool attr_done = false;
   if (!attr_done) {
