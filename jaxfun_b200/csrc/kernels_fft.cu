@@ -27,7 +27,7 @@
 
 namespace jfx {
 
-template <typename T> struct Cpx { T x, y; };
+template <typename T> struct alignas(2 * sizeof(T)) Cpx { T x, y; };
 template <typename T> __device__ __forceinline__ Cpx<T> operator+(Cpx<T> a, Cpx<T> b) { return {a.x + b.x, a.y + b.y}; }
 template <typename T> __device__ __forceinline__ Cpx<T> operator-(Cpx<T> a, Cpx<T> b) { return {a.x - b.x, a.y - b.y}; }
 template <typename T> __device__ __forceinline__ Cpx<T> cmul(Cpx<T> a, Cpx<T> b) {
@@ -74,9 +74,9 @@ template <typename T> struct Dft<T, 1> { static __device__ __forceinline__ void 
 // radix plans
 template <int N> struct Plan;
 template <> struct Plan<16>   { static constexpr int R0 = 4,  R1 = 4,  R2 = 1;  };
-template <> struct Plan<32>   { static constexpr int R0 = 8,  R1 = 4,  R2 = 1;  };
+template <> struct Plan<32>   { static constexpr int R0 = 4,  R1 = 8,  R2 = 1;  };
 template <> struct Plan<64>   { static constexpr int R0 = 8,  R1 = 8,  R2 = 1;  };
-template <> struct Plan<128>  { static constexpr int R0 = 16, R1 = 8,  R2 = 1;  };
+template <> struct Plan<128>  { static constexpr int R0 = 8,  R1 = 16, R2 = 1;  };
 template <> struct Plan<256>  { static constexpr int R0 = 16, R1 = 16, R2 = 1;  };
 template <> struct Plan<512>  { static constexpr int R0 = 8,  R1 = 8,  R2 = 8;  };
 template <> struct Plan<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8;  };
@@ -99,14 +99,20 @@ template <int TN> __device__ __forceinline__ void line_sync();
 // one Stockham pass over a line held in shared memory (in place: load all, sync, store all)
 template <typename T, int N, int R, int NS>
 __device__ __forceinline__ void fft_pass(Cpx<T>* __restrict__ S, int j, const Cpx<T>* __restrict__ tw) {
-  constexpr int TN = Geo<N>::TN, LOGSK = Geo<N>::LOGSK;
+  constexpr int TN = Geo<N>::TN, LOGSK = Geo<N>::LOGSK, G = 1 << LOGSK;
   constexpr int BPT = (N / R) / TN;
+  constexpr int STR = N / R;                          // input stride between a butterfly's points
+  static_assert(STR % G == 0, "input stride must be a multiple of the skew granule");
+  static_assert(NS == 1 ? (R <= G) : (NS % G == 0), "output stride must keep the skew affine");
+  constexpr int IN_OFF = STR + (STR >> LOGSK);        // sk(jj + r*STR) = sk(jj) + r*IN_OFF
+  constexpr int OUT_OFF = NS == 1 ? 1 : NS + (NS >> LOGSK);  // sk(j0 + r*NS) = sk(j0) + r*OUT_OFF
+  constexpr int TS = N / (NS * R);                    // twiddle table stride
   Cpx<T> v[BPT][R];
 #pragma unroll
   for (int bf = 0; bf < BPT; ++bf) {
-    const int jj = j + bf * TN;
+    const Cpx<T>* src = S + sk<LOGSK>(j + bf * TN);
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[bf][r] = S[sk<LOGSK>(jj + r * (N / R))];
+    for (int r = 0; r < R; ++r) v[bf][r] = src[r * IN_OFF];
   }
   line_sync<TN>();
 #pragma unroll
@@ -114,13 +120,14 @@ __device__ __forceinline__ void fft_pass(Cpx<T>* __restrict__ S, int j, const Cp
     const int jj = j + bf * TN;
     const int k = jj % NS;
     if (NS > 1) {
+      const Cpx<T>* w = tw + k * TS;
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[bf][r] = cmul(v[bf][r], tw[(r * k) * (N / (NS * R))]);
+      for (int r = 1; r < R; ++r) v[bf][r] = cmul(v[bf][r], w[(r - 1) * k * TS]);   // tw[r*k*TS]
     }
     Dft<T, R>::run(v[bf]);
-    const int j0 = (jj / NS) * NS * R + k;
+    Cpx<T>* dst = S + sk<LOGSK>((jj / NS) * NS * R + k);
 #pragma unroll
-    for (int r = 0; r < R; ++r) S[sk<LOGSK>(j0 + r * NS)] = v[bf][r];
+    for (int r = 0; r < R; ++r) dst[r * OUT_OFF] = v[bf][r];
   }
   line_sync<TN>();
 }
@@ -148,162 +155,209 @@ template <int TN> __device__ __forceinline__ void line_sync() {
   if (TN <= 32) __syncwarp(); else __syncthreads();
 }
 
-template <typename T, int N>
-__global__ void __launch_bounds__(Geo<N>::TN >= 64 ? 512 : 256)
-fft_axis_kernel(const FftArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Cpx<T>* S = reinterpret_cast<Cpx<T>*>(smem_raw);
-  constexpr int TN = Geo<N>::TN, PITCH = Geo<N>::PITCH, LOGSK = Geo<N>::LOGSK, RMAX = Geo<N>::RMAX;
-  constexpr bool WARP_LINES = (TN <= 32);        // every line is owned by threads of a single warp
-  constexpr int LW = WARP_LINES ? 32 / TN : 1;    // lines per warp
-  const int lpb = a.lpb, log_lpb = a.log_lpb;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const long long line0 = (long long)blockIdx.x * lpb;
-  const Cpx<T>* __restrict__ tw = reinterpret_cast<const Cpx<T>*>(a.tw);
-  const Cpx<T>* __restrict__ half = reinterpret_cast<const Cpx<T>*>(a.half);
-  const Cpx<T>* __restrict__ pre = reinterpret_cast<const Cpx<T>*>(a.pre);
-  const bool strided = a.inner > 1;
-  const bool warp_local = WARP_LINES && !strided;  // stage loops touch only the warp's own lines
-  const int kind = a.kind;
-  const bool cheb = kind <= FAST_CHEB_SCALAR;
-  const int n_in = a.n_in, nout = a.n_out;
+enum { LAY_CONTIG = 0, LAY_STRIDED = 1, LAY_REALPAIR = 2 };
+enum { K_CHEB_BWD = 0, K_CHEB_FWD = 1, K_FOUR_BWD = 2, K_FOUR_FWD = 3 };
 
-  // tile element owned by this thread in stage iteration `it`: (local line, axis index)
-  auto tile_elem = [&](int it, int& ll, int& i) {
-    if (strided) { const int e = tid + it * nthr; ll = e & (lpb - 1); i = e >> log_lpb; }
-    else if (WARP_LINES) { const int e = it * 32 + lane; ll = warp * LW + e / N; i = e % N; }
-    else { const int e = tid + it * nthr; ll = e / N; i = e % N; }
-  };
-  // element (line l, axis index i) of the input / output arrays
-  auto load_in = [&](long long l, int i) -> Cpx<T> {
-    if (a.real_pair) {
-      const T* __restrict__ p = reinterpret_cast<const T*>(a.in);
-      const long long r0 = 2 * l, r1 = 2 * l + 1;
+// Per-thread view of the tile: which (local line, axis index) a thread touches in stage iteration
+// `it`, and where that line starts in the input / output arrays.  Everything that does not depend
+// on `it` is computed once.
+template <typename T, int N, int LAY> struct TileMap {
+  static constexpr int TN = Geo<N>::TN;
+  static constexpr bool WARP_LINES = (TN <= 32);
+  static constexpr int LW = WARP_LINES ? 32 / TN : 1;
+  int tid, lane, warp, nthr, lpb;
+  int ll_fixed, i_first;      // strided
+  long long lines, line0, real_lines;
+  int n_in, n_out;
+  long long inner;
+  size_t sb_in, sb_out;       // strided: element offset of (line, i = 0)
+
+  __device__ __forceinline__ TileMap(const FftArgs& a)
+      : tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), nthr(blockDim.x), lpb(a.lpb),
+        lines(a.lines), line0((long long)blockIdx.x * a.lpb), real_lines(a.real_lines), n_in(a.n_in),
+        n_out(a.n_out), inner(a.inner) {
+    ll_fixed = 0; i_first = 0; sb_in = sb_out = 0;
+    if (LAY == LAY_STRIDED) {
+      ll_fixed = tid & (lpb - 1);
+      i_first = tid >> a.log_lpb;
+      long long l = line0 + ll_fixed;
+      if (l >= lines) l = lines - 1;   // clamp: masked later
+      const long long o = l / inner, b = l - o * inner;
+      sb_in = (size_t)(o * n_in * inner + b);
+      sb_out = (size_t)(o * n_out * inner + b);
+    }
+  }
+  // (local line, axis index) of stage iteration `it` (compile-time after unrolling)
+  __device__ __forceinline__ void elem(int it, int& ll, int& i) const {
+    if (LAY == LAY_STRIDED) { ll = ll_fixed; i = i_first + it * TN; }
+    else if (WARP_LINES) {
+      if (N >= 32) { ll = warp * LW + (it * 32) / N; i = ((it * 32) % N) + lane; }
+      else { const int e = it * 32 + lane; ll = warp * LW + e / N; i = e % N; }
+    } else { const int e = tid + it * nthr; ll = e / N; i = e % N; }
+  }
+  __device__ __forceinline__ bool line_ok(int ll) const { return line0 + ll < lines; }
+  __device__ __forceinline__ Cpx<T> load(const void* in, int ll, int i) const {
+    if (LAY == LAY_REALPAIR) {
+      const long long l = line0 + ll;
+      const T* __restrict__ p = reinterpret_cast<const T*>(in) + (size_t)(2 * l) * n_in + i;
       Cpx<T> v;
-      v.x = __ldg(p + r0 * n_in + i);
-      v.y = (r1 < a.real_lines) ? __ldg(p + r1 * n_in + i) : T(0);
+      v.x = p[0];
+      v.y = (2 * l + 1 < real_lines) ? p[n_in] : T(0);
       return v;
     }
-    const long long o = l / a.inner, b = l % a.inner;
-    const Cpx<T>* __restrict__ p = reinterpret_cast<const Cpx<T>*>(a.in);
-    return p[(o * n_in + i) * a.inner + b];
-  };
-  auto store_out = [&](long long l, int i, Cpx<T> v) {
-    if (a.real_pair) {
-      T* p = reinterpret_cast<T*>(a.out);
-      const long long r0 = 2 * l, r1 = 2 * l + 1;
-      p[r0 * nout + i] = v.x;
-      if (r1 < a.real_lines) p[r1 * nout + i] = v.y;
+    const Cpx<T>* __restrict__ p = reinterpret_cast<const Cpx<T>*>(in);
+    if (LAY == LAY_STRIDED) return p[sb_in + (size_t)i * inner];
+    return p[(size_t)(line0 + ll) * n_in + i];
+  }
+  __device__ __forceinline__ void store(void* out, int ll, int i, Cpx<T> v) const {
+    if (LAY == LAY_REALPAIR) {
+      const long long l = line0 + ll;
+      T* p = reinterpret_cast<T*>(out) + (size_t)(2 * l) * n_out + i;
+      p[0] = v.x;
+      if (2 * l + 1 < real_lines) p[n_out] = v.y;
       return;
     }
-    const long long o = l / a.inner, b = l % a.inner;
-    reinterpret_cast<Cpx<T>*>(a.out)[(o * nout + i) * a.inner + b] = v;
-  };
+    Cpx<T>* p = reinterpret_cast<Cpx<T>*>(out);
+    if (LAY == LAY_STRIDED) p[sb_out + (size_t)i * inner] = v;
+    else p[(size_t)(line0 + ll) * n_out + i] = v;
+  }
+};
 
-  // ---------------- stage in: all global loads first (RMAX independent requests per thread) ------------
-  constexpr int CH = (RMAX < 4) ? RMAX : 4;   // loads in flight per thread per chunk (register budget)
-#pragma unroll 1
-  for (int it0 = 0; it0 < RMAX; it0 += CH) {
-  Cpx<T> z0[CH], z1[CH];
+template <typename T, int N, int KIND, int LAY>
+__device__ __forceinline__ void stage_in(const FftArgs& a, const TileMap<T, N, LAY>& tm, Cpx<T>* __restrict__ S) {
+  constexpr int PITCH = Geo<N>::PITCH, LOGSK = Geo<N>::LOGSK, RMAX = Geo<N>::RMAX;
+  constexpr int CH = (RMAX < 4) ? RMAX : 4;   // independent global requests in flight per thread
+  const Cpx<T>* __restrict__ half = reinterpret_cast<const Cpx<T>*>(a.half);
+  const Cpx<T>* __restrict__ pre = reinterpret_cast<const Cpx<T>*>(a.pre);
+  const int n_in = a.n_in;
 #pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const int it = c; int ll, i;
-    tile_elem(it0 + c, ll, i);
-    const long long l = line0 + ll;
-    z0[it] = Cpx<T>{T(0), T(0)};
-    z1[it] = Cpx<T>{T(0), T(0)};
-    if (l < a.lines) {
-      if (kind == FAST_FOURIER_BACKWARD) {
-        const int hlf = n_in / 2;               // padded spectrum position i <- coefficient p
-        int p = -1;
-        if (N == n_in) p = i;
-        else if (i < hlf) p = i;
-        else if (i >= N - (n_in - hlf)) p = i - (N - n_in);
-        if (p >= 0) { z0[it] = load_in(l, p); if (pre) z1[it] = pre[p]; }
-      } else if (kind == FAST_CHEB_BACKWARD) {
-        if (i < n_in) z0[it] = load_in(l, i);
+  for (int it0 = 0; it0 < RMAX; it0 += CH) {
+    Cpx<T> z0[CH], z1[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      int ll, i;
+      tm.elem(it0 + c, ll, i);
+      z0[c] = Cpx<T>{T(0), T(0)};
+      z1[c] = Cpx<T>{T(0), T(0)};
+      if (!tm.line_ok(ll)) continue;
+      if (KIND == K_FOUR_BWD) {
+        const int hlf = n_in >> 1;                 // padded spectrum position i <- coefficient p
+        int p = i;
+        if (n_in != N) p = (i < hlf) ? i : ((i >= N - (n_in - hlf)) ? i - (N - n_in) : -1);
+        if (p >= 0) { z0[c] = tm.load(a.in, ll, p); if (pre) z1[c] = pre[p]; }
+      } else if (KIND == K_CHEB_BWD) {
+        if (i < n_in) z0[c] = tm.load(a.in, ll, i);
         const int m = N - i;
-        if (i > 0 && m < n_in) z1[it] = load_in(l, m);
+        if (i > 0 && m < n_in) z1[c] = tm.load(a.in, ll, m);
       } else {
-        if (i < n_in) z0[it] = load_in(l, i);
+        z0[c] = tm.load(a.in, ll, i);               // forward kinds: n_in == N
       }
     }
-  }
 #pragma unroll
-  for (int c = 0; c < CH; ++c) {
-    const int it = c; int ll, i;
-    tile_elem(it0 + c, ll, i);
-    Cpx<T> z = z0[it];
-    int dst = i;
-    if (kind == FAST_FOURIER_BACKWARD) {
-      if (pre) z = cmul(z, z1[it]);
-      z = conj_(z);                                   // inverse DFT = conj(FFT(conj(.)))
-    } else if (kind == FAST_CHEB_BACKWARD) {
-      // z_0 = A_0 ; z_k = e^{+i pi k/(2n)}/2 * (A_k - i A_{n-k}),  A_k = c_k (-1)^k (0 beyond n_in)
-      Cpx<T> ak = z, am = z1[it];
-      if (i & 1) { ak.x = -ak.x; ak.y = -ak.y; }
-      if ((N - i) & 1) { am.x = -am.x; am.y = -am.y; }
-      if (i != 0) {
-        const Cpx<T> w{ak.x + am.y, ak.y - am.x};      // A_k - i A_{n-k}
-        const Cpx<T> t = conj_(half[i]);                // e^{+i pi k/(2n)}
-        z = cmul(t, w);
-        z.x *= T(0.5); z.y *= T(0.5);
-      } else z = ak;
-      z = conj_(z);
-    } else if (cheb) {
-      dst = (i & 1) ? (N - 1 - (i >> 1)) : (i >> 1);  // DCT-II: v[m] = x[2m], v[n-1-m] = x[2m+1]
+    for (int c = 0; c < CH; ++c) {
+      int ll, i;
+      tm.elem(it0 + c, ll, i);
+      Cpx<T> z = z0[c];
+      int dst = i;
+      if (KIND == K_FOUR_BWD) {
+        if (pre) z = cmul(z, z1[c]);
+        z = conj_(z);                                // inverse DFT = conj(FFT(conj(.)))
+      } else if (KIND == K_CHEB_BWD) {
+        // z_0 = A_0 ; z_k = e^{+i pi k/(2n)}/2 (A_k - i A_{n-k}),  A_k = c_k (-1)^k (0 beyond n_in)
+        Cpx<T> ak = z, am = z1[c];
+        if (i & 1) { ak.x = -ak.x; ak.y = -ak.y; }   // N even: (N - i) has the parity of i
+        if (i & 1) { am.x = -am.x; am.y = -am.y; }
+        if (i != 0) {
+          const Cpx<T> w{ak.x + am.y, ak.y - am.x};   // A_k - i A_{n-k}
+          const Cpx<T> t = half[i];                   // e^{-i pi k/(2n)}; we need its conjugate
+          z = Cpx<T>{T(0.5) * (t.x * w.x + t.y * w.y), T(0.5) * (t.x * w.y - t.y * w.x)};
+        } else z = ak;
+        z = conj_(z);
+      } else if (KIND == K_CHEB_FWD) {
+        dst = (i & 1) ? (N - 1 - (i >> 1)) : (i >> 1);  // DCT-II: v[m] = x[2m], v[n-1-m] = x[2m+1]
+      }
+      S[ll * PITCH + sk<LOGSK>(dst)] = z;
     }
-    S[ll * PITCH + sk<LOGSK>(dst)] = z;
   }
-  }
-  if (warp_local) __syncwarp(); else __syncthreads();
+}
 
-  // ---------------- FFT passes ----------------
+template <typename T, int N, int KIND, int LAY>
+__device__ __forceinline__ void stage_out(const FftArgs& a, const TileMap<T, N, LAY>& tm, const Cpx<T>* __restrict__ S) {
+  constexpr int PITCH = Geo<N>::PITCH, LOGSK = Geo<N>::LOGSK, RMAX = Geo<N>::RMAX;
+  const Cpx<T>* __restrict__ half = reinterpret_cast<const Cpx<T>*>(a.half);
+  const T scale = (T)a.scale;
+  const int nout = a.n_out;
+#pragma unroll
+  for (int it = 0; it < RMAX; ++it) {
+    int ll, q;
+    tm.elem(it, ll, q);
+    if (!tm.line_ok(ll) || q >= nout) continue;
+    const Cpx<T>* Sl = S + ll * PITCH;
+    Cpx<T> v;
+    if (KIND == K_FOUR_BWD) {
+      v = conj_(Sl[sk<LOGSK>(q)]);
+    } else if (KIND == K_CHEB_BWD) {
+      const int m = (q & 1) ? (N - 1 - (q >> 1)) : (q >> 1);
+      v = conj_(Sl[sk<LOGSK>(m)]);
+    } else if (KIND == K_CHEB_FWD) {
+      // C_k = t_k W[k] + conj(t_k) W[n-k],  t_k = e^{-i pi k/(2n)}
+      const Cpx<T> t = half[q];
+      const Cpx<T> wk = Sl[sk<LOGSK>(q)], wm = Sl[sk<LOGSK>((N - q) & (N - 1))];
+      v = cmul(t, wk) + cmul(conj_(t), wm);
+      T s = (q & 1) ? -scale : scale;
+      if (q == 0 && a.kind == FAST_CHEB_FORWARD) s *= T(0.5);
+      v.x *= s; v.y *= s;
+    } else {
+      const int nm = a.n_modes;                   // Fourier forward: wavenumber gather when truncating
+      int i = q;
+      if (N > nm && q >= ((nm + 1) >> 1)) i = N + q - nm;
+      v = Sl[sk<LOGSK>(i)];
+      v.x *= scale; v.y *= scale;
+    }
+    tm.store(a.out, ll, q, v);
+  }
+}
+
+template <typename T, int N, int KIND, int LAY>
+__device__ __forceinline__ void fft_tile(const FftArgs& a, Cpx<T>* S) {
+  constexpr int TN = Geo<N>::TN, PITCH = Geo<N>::PITCH;
+  constexpr bool WARP_LOCAL = (TN <= 32) && (LAY != LAY_STRIDED);  // stage loops touch only the warp's own lines
+  const TileMap<T, N, LAY> tm(a);
+  stage_in<T, N, KIND, LAY>(a, tm, S);
+  if (WARP_LOCAL) __syncwarp(); else __syncthreads();
   {
-    const int ll = tid / TN, j = tid % TN;
+    const int ll = threadIdx.x / TN, j = threadIdx.x % TN;
     Cpx<T>* Sl = S + ll * PITCH;
+    const Cpx<T>* __restrict__ tw = reinterpret_cast<const Cpx<T>*>(a.tw);
     using P = Plan<N>;
     fft_pass<T, N, P::R0, 1>(Sl, j, tw);
     fft_pass<T, N, P::R1, P::R0>(Sl, j, tw);
     if constexpr (P::R2 > 1) fft_pass<T, N, P::R2, P::R0 * P::R1>(Sl, j, tw);
   }
-  if (!warp_local) __syncthreads();
+  if (!WARP_LOCAL) __syncthreads();
+  stage_out<T, N, KIND, LAY>(a, tm, S);
+}
 
-  // ---------------- stage out ----------------
-  const T scale = (T)a.scale;
-#pragma unroll
-  for (int it = 0; it < RMAX; ++it) {
-    int ll, q;
-    tile_elem(it, ll, q);
-    const long long l = line0 + ll;
-    if (l >= a.lines || q >= nout) continue;
-    const Cpx<T>* Sl = S + ll * PITCH;
-    Cpx<T> v;
-    if (kind == FAST_FOURIER_BACKWARD) {
-      v = conj_(Sl[sk<LOGSK>(q)]);
-    } else if (kind == FAST_CHEB_BACKWARD) {
-      const int m = (q & 1) ? (N - 1 - (q >> 1)) : (q >> 1);
-      v = conj_(Sl[sk<LOGSK>(m)]);
-    } else if (cheb) {
-      // C_k = t_k W[k] + conj(t_k) W[n-k],  t_k = e^{-i pi k/(2n)}
-      const Cpx<T> t = half[q];
-      const Cpx<T> wk = Sl[sk<LOGSK>(q)], wm = Sl[sk<LOGSK>((N - q) & (N - 1))];
-      v = cmul(t, wk) + cmul(conj_(t), wm);
-      T s = scale;
-      if (q & 1) s = -s;
-      if (q == 0 && kind == FAST_CHEB_FORWARD) s *= T(0.5);
-      v.x *= s; v.y *= s;
-    } else {
-      // Fourier forward: gather by wavenumber when truncating
-      const int nm = a.n_modes;
-      int i = q;
-      if (N > nm && q >= (nm + 1) / 2) i = N + q - nm;
-      v = Sl[sk<LOGSK>(i)];
-      v.x *= scale; v.y *= scale;
-    }
-    store_out(l, q, v);
+template <typename T, int N>
+__global__ void __launch_bounds__(Geo<N>::TN > 128 ? 512 : 256)
+fft_axis_kernel(const FftArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cpx<T>* S = reinterpret_cast<Cpx<T>*>(smem_raw);
+  // uniform dispatch: one specialised (kind, layout) path per launch, no per-element branching
+  const int lay = a.real_pair ? LAY_REALPAIR : (a.inner > 1 ? LAY_STRIDED : LAY_CONTIG);
+  int k4;
+  switch (a.kind) {
+    case FAST_CHEB_BACKWARD: k4 = K_CHEB_BWD; break;
+    case FAST_CHEB_FORWARD: case FAST_CHEB_SCALAR: k4 = K_CHEB_FWD; break;
+    case FAST_FOURIER_BACKWARD: k4 = K_FOUR_BWD; break;
+    default: k4 = K_FOUR_FWD;
   }
+#define JFX_CASE(K, L) if (k4 == K && lay == L) { fft_tile<T, N, K, L>(a, S); return; }
+  JFX_CASE(K_CHEB_BWD, LAY_CONTIG) JFX_CASE(K_CHEB_BWD, LAY_STRIDED) JFX_CASE(K_CHEB_BWD, LAY_REALPAIR)
+  JFX_CASE(K_CHEB_FWD, LAY_CONTIG) JFX_CASE(K_CHEB_FWD, LAY_STRIDED) JFX_CASE(K_CHEB_FWD, LAY_REALPAIR)
+  JFX_CASE(K_FOUR_BWD, LAY_CONTIG) JFX_CASE(K_FOUR_BWD, LAY_STRIDED)
+  JFX_CASE(K_FOUR_FWD, LAY_CONTIG) JFX_CASE(K_FOUR_FWD, LAY_STRIDED)
+#undef JFX_CASE
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -412,7 +466,7 @@ template <typename T, int N>
 static int launch_n(cudaStream_t s, const FftArgs& a_in, bool strided) {
   FftArgs a = a_in;
   constexpr int TN = Geo<N>::TN;
-  const int max_threads = TN >= 64 ? 512 : 256;
+  const int max_threads = TN > 128 ? 512 : 256;
   const size_t line_bytes = (size_t)Geo<N>::PITCH * sizeof(Cpx<T>);
   int lpb = max_threads / TN;
   if (lpb < 1) lpb = 1;
@@ -420,6 +474,7 @@ static int launch_n(cudaStream_t s, const FftArgs& a_in, bool strided) {
   while (lpb > 1 && (size_t)lpb * line_bytes > smem_cap) lpb /= 2;
   // strided axes want >= 8 neighbouring lines (128 B rows); small problems shrink the tile
   while (lpb > 1 && (long long)(lpb / 2) >= a.lines) lpb /= 2;
+  if (TN <= 32 && lpb < 32 / TN) lpb = 32 / TN;   // whole warps: a warp owns 32/TN lines
   a.lpb = lpb;
   a.log_lpb = 0;
   while ((1 << a.log_lpb) < lpb) ++a.log_lpb;
