@@ -6,13 +6,15 @@ spectralDNS/jaxfun.  Every function names the reference lines i
 `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of `bench.py` may import
 this module; nothing under `jaxfun_b200/` does.
 
-Pinning status: the reference is pure Python on JAX and jax is not installable here, so the
-reference itself cannot be executed.  The oracle is pinned by (1) the reference's own known-answer
-tests re-run against it (`tests/test_oracle_pins.py`: numpy.polynomial Vandermondes,
-analytic derivatives, round trips, nonlinear identities — SURVEY.md §8c) and (2) golden vectors
-produced by running the reference's *source files* on a minimal numpy stand-in for the `jax`
-API (`tests/golden/make_golden.py`).  Bit-level agreement with XLA's own `cos`/FFT/dot is not
-verifiable in this environment ("parity unpinned at the bit level" — see DESIGN.md).
+Pinning status: PINNED against the reference's own source files.  jax is not installable here,
+so the reference cannot run as shipped; instead its unmodified modules (galerkin/*.py,
+utils/fastgl.py, galerkin/tensorproductspace.py, integrators/nonlinear.py) are executed on a
+numpy stand-in for the jax API (tools/jaxshim) by `tests/golden/make_golden.py`, and the
+resulting vectors (`tests/golden/reference_vectors.npz`: 1-D transforms of all six bases, padded /
+derivative / complex-line variants, mixed-basis tensor products, nonlinear terms, FastGL node
+tables) are replayed against this oracle in `tests/test_golden.py` (nodes / weights / wavenumbers
+bit-exact, transforms < 1e-12; observed <= 3e-15).  What that does NOT pin is XLA's last-bit rounding
+of cos / FFT / dot versus numpy / scipy ("bit level unpinned" — see DESIGN.md).
 
 Third-party arithmetic restated here: jax.numpy.fft / jax.scipy.fft.dct (jaxlib 0.11.0) ->
 numpy.fft / scipy.fft; scipy.special.roots_jacobi (scipy 1.17.0 pinned, 1.18.1 here).
