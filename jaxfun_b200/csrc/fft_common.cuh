@@ -1,0 +1,118 @@
+// Shared pieces of the fast-transform kernels (kernels_fft.cu: first-generation smem-staged kernel,
+// kernels_fft2.cu: direct global<->register kernel).  Internal header.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "jfx_common.h"
+
+namespace jfx {
+
+template <typename T> struct alignas(2 * sizeof(T)) Cpx { T x, y; };
+template <typename T> __device__ __forceinline__ Cpx<T> operator+(Cpx<T> a, Cpx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T> __device__ __forceinline__ Cpx<T> operator-(Cpx<T> a, Cpx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T> __device__ __forceinline__ Cpx<T> cmul(Cpx<T> a, Cpx<T> b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T> __device__ __forceinline__ Cpx<T> conj_(Cpx<T> a) { return {a.x, -a.y}; }
+
+// cos(2 pi k/16), sin(2 pi k/16), k = 0..7
+__device__ constexpr double kCos16[8] = {1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173,
+                                         0.0, -0.38268343236508977173, -0.70710678118654752440, -0.92387953251128673848};
+__device__ constexpr double kSin16[8] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128673848,
+                                         1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173};
+
+// In-register forward DFT of R points, natural order in and out (decimation in time).
+template <typename T, int R> struct Dft {
+  static __device__ __forceinline__ void run(Cpx<T>* v) {
+    Cpx<T> e[R / 2], o[R / 2];
+#pragma unroll
+    for (int i = 0; i < R / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    Dft<T, R / 2>::run(e);
+    Dft<T, R / 2>::run(o);
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      Cpx<T> t;
+      if (k == 0) t = o[k];
+      else if (4 * k == R) t = Cpx<T>{o[k].y, -o[k].x};   // * (-i)
+      else {
+        const T c = (T)kCos16[k * (16 / R)], s = (T)kSin16[k * (16 / R)];  // W = c - i s
+        t = Cpx<T>{o[k].x * c + o[k].y * s, o[k].y * c - o[k].x * s};
+      }
+      v[k] = e[k] + t;
+      v[k + R / 2] = e[k] - t;
+    }
+  }
+};
+template <typename T> struct Dft<T, 2> {
+  static __device__ __forceinline__ void run(Cpx<T>* v) {
+    Cpx<T> a = v[0] + v[1], b = v[0] - v[1];
+    v[0] = a; v[1] = b;
+  }
+};
+template <typename T> struct Dft<T, 1> { static __device__ __forceinline__ void run(Cpx<T>*) {} };
+
+// radix plans
+template <int N> struct Plan;
+template <> struct Plan<16>   { static constexpr int R0 = 4,  R1 = 4,  R2 = 1;  };
+template <> struct Plan<32>   { static constexpr int R0 = 4,  R1 = 8,  R2 = 1;  };
+template <> struct Plan<64>   { static constexpr int R0 = 8,  R1 = 8,  R2 = 1;  };
+template <> struct Plan<128>  { static constexpr int R0 = 8,  R1 = 16, R2 = 1;  };
+template <> struct Plan<256>  { static constexpr int R0 = 16, R1 = 16, R2 = 1;  };
+template <> struct Plan<512>  { static constexpr int R0 = 8,  R1 = 8,  R2 = 8;  };
+template <> struct Plan<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8;  };
+template <> struct Plan<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8;  };
+template <> struct Plan<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16; };
+
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
+template <int N> struct Geo {
+  static constexpr int RMAX = cmax(Plan<N>::R0, cmax(Plan<N>::R1, Plan<N>::R2));
+  static constexpr int TN = N / RMAX;                       // threads per line
+  static constexpr int LOGSK = ilog2(Plan<N>::R0);          // smem skew: i + (i >> LOGSK)
+  static constexpr int PITCH = N + (N >> LOGSK) + 1;        // odd -> conflict-free across lines
+};
+
+template <int LOGSK> __device__ __forceinline__ int sk(int i) { return i + (i >> LOGSK); }
+
+
+struct FftArgs {
+  const void* in;
+  void* out;
+  const void* tw;     // W_n^m = exp(-2 pi i m / n), m < n
+  const void* half;   // exp(-i pi k / (2n)), k < n          (Chebyshev)
+  const void* pre;    // per-coefficient complex prescale    (Fourier backward derivative), or null
+  long long lines;    // complex lines (real-pair mode: pairs of real lines)
+  long long inner;    // complex inner extent; 1 = contiguous axis
+  long long real_lines;
+  int n_in, n_out;    // axis extents of the input / output arrays
+  int n_modes;        // N
+  int kind;
+  int real_pair;
+  int lpb;
+  int log_lpb;
+  double scale;
+};
+
+
+struct FastTables {
+  int n = 0;
+  bool dbl = true;
+  void* d_tw = nullptr;
+  void* d_half = nullptr;
+  void* d_pre = nullptr;
+  ~FastTables() {
+    if (d_tw) cudaFree(d_tw);
+    if (d_half) cudaFree(d_half);
+    if (d_pre) cudaFree(d_pre);
+  }
+};
+
+
+enum { LAY_CONTIG = 0, LAY_STRIDED = 1, LAY_REALPAIR = 2 };
+enum { K_CHEB_BWD = 0, K_CHEB_FWD = 1, K_FOUR_BWD = 2, K_FOUR_FWD = 3 };
+
+// second-generation kernel (kernels_fft2.cu): returns 1 when it handled the launch, 0 when the
+// configuration is outside its envelope (caller falls back to the staged kernel), < 0 on error
+int launch_fast_axis_v2(cudaStream_t s, const FftArgs& a, int n, bool dbl);
+
+}  // namespace jfx

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 
@@ -40,6 +41,7 @@ struct jfx_plan {
   std::vector<jfx::Pass> passes;
   size_t buf_bytes = 0;  // one ping-pong buffer
   size_t ws_bytes = 0;
+  int slabs = 1;         // > 1: the last two passes run L2-blocked over slabs of the leading axis
   double flops = 0, bytes = 0;
   // host-pointer path (lazy, guarded)
   std::mutex host_mu;
@@ -65,6 +67,8 @@ static int64_t prod(const int64_t* s, int a, int b) {
   return p;
 }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t slab_target_bytes();
 
 static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
   JFX_REQUIRE(d->abi_version == JFX_ABI_VERSION, JFX_ERR_INVALID, "ABI version %d != %d", d->abi_version,
@@ -170,12 +174,42 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
   pl->bytes = (double)es * ((double)in_elems + (double)out_elems);
   pl->buf_bytes = pl->passes.size() > 1 ? align_up(max_inter, 256) : 0;
   pl->ws_bytes = pl->passes.size() > 2 ? 2 * pl->buf_bytes : pl->buf_bytes;
+  // L2 blocking of the last two passes (see execute_plan): both on axes >= 1, both bandwidth-bound
+  // (fast transforms), intermediate larger than what the L2 keeps anyway
+  pl->slabs = 1;
+  const size_t npass = pl->passes.size();
+  if (npass >= 2 && slab_target_bytes() > 0) {
+    const Pass& A = pl->passes[npass - 2];
+    const Pass& B = pl->passes[npass - 1];
+    const int64_t L = pl->shape_out[0];
+    const size_t inter = (size_t)A.geom.outer * A.geom.n_out * A.geom.inner * es;
+    if (A.axis >= 1 && B.axis >= 1 && A.fast && B.fast && L >= 2 && inter > 2 * slab_target_bytes()) {
+      int64_t want = (int64_t)((inter + slab_target_bytes() - 1) / slab_target_bytes());
+      pl->slabs = (int)std::min<int64_t>(want, L);
+    }
+  }
   return JFX_OK;
 }
 
+static int run_pass_geom(cudaStream_t s, const Pass& p, const AxisGeom& g, int dtype, const void* src, void* dst) {
+  if (p.fast) return launch_fast_axis(s, g, dtype, p.fp, p.ft, src, dst);
+  return launch_table_apply(s, g, dtype, p.d_table, p.table_complex, src, dst, nullptr);
+}
 static int run_pass(cudaStream_t s, const Pass& p, int dtype, const void* src, void* dst) {
-  if (p.fast) return launch_fast_axis(s, p.geom, dtype, p.fp, p.ft, src, dst);
-  return launch_table_apply(s, p.geom, dtype, p.d_table, p.table_complex, src, dst, nullptr);
+  return run_pass_geom(s, p, p.geom, dtype, src, dst);
+}
+
+// L2-blocked execution of the last two passes.  When both act on axes >= 1 the leading array axis is a
+// pure batch dimension for them, so the array can be walked in slabs of leading-axis planes: pass A
+// writes a slab-sized scratch that pass B consumes while it is still resident in the 126 MB L2.  The
+// intermediate array of the pair then never travels to HBM (one read + one write of the field saved).
+static size_t slab_target_bytes() {
+  static const size_t v = [] {
+    const char* e = getenv("JFX_SLAB_MB");
+    const long mb = e ? atol(e) : 0;   // opt-in: measured slower than plain passes at 256^3 (launch tails), see DESIGN.md
+    return (size_t)(mb < 0 ? 0 : mb) << 20;
+  }();
+  return v;
 }
 
 static int execute_plan(const jfx_plan* pl, cudaStream_t s, const void* in, void* out, void* ws) {
@@ -190,11 +224,34 @@ static int execute_plan(const jfx_plan* pl, cudaStream_t s, const void* in, void
   char* w0 = (char*)ws;
   char* w1 = w0 + pl->buf_bytes;
   const void* src = in;
-  for (size_t i = 0; i < np; ++i) {
+  size_t first_pair = np;   // index of pass A when the last two passes run slab-blocked
+  if (pl->slabs > 1) first_pair = np - 2;
+  for (size_t i = 0; i < first_pair; ++i) {
     void* dst = (i + 1 == np) ? out : (void*)((i & 1) ? w1 : w0);
     int rc = run_pass(s, pl->passes[i], pl->desc.dtype, src, dst);
     if (rc != JFX_OK) return rc;
     src = dst;
+  }
+  if (first_pair < np) {
+    const Pass& A = pl->passes[np - 2];
+    const Pass& B = pl->passes[np - 1];
+    const int64_t L = pl->shape_out[0];
+    // scratch = the ping-pong buffer `src` does not live in (src is `in` when the pair is the whole plan)
+    char* scratch = (src == (const void*)w0) ? w1 : w0;
+    const int64_t oA = A.geom.outer / L, oB = B.geom.outer / L;
+    const size_t inA = (size_t)oA * A.geom.n_in * A.geom.inner * es;     // bytes per leading-axis plane
+    const size_t outB = (size_t)oB * B.geom.n_out * B.geom.inner * es;
+    const int64_t per = (L + pl->slabs - 1) / pl->slabs;
+    for (int64_t a = 0; a < L; a += per) {
+      const int64_t b = std::min<int64_t>(L, a + per);
+      AxisGeom gA = A.geom, gB = B.geom;
+      gA.outer = (b - a) * oA;
+      gB.outer = (b - a) * oB;
+      int rc = run_pass_geom(s, A, gA, pl->desc.dtype, (const char*)src + (size_t)a * inA, scratch);
+      if (rc != JFX_OK) return rc;
+      rc = run_pass_geom(s, B, gB, pl->desc.dtype, scratch, (char*)out + (size_t)a * outB);
+      if (rc != JFX_OK) return rc;
+    }
   }
   return JFX_OK;
 }
@@ -277,7 +334,12 @@ int jfx_plan_work(const jfx_plan* plan, double* flops, double* bytes) {
 
 int jfx_plan_launches(const jfx_plan* plan) {
   if (!plan) return JFX_ERR_INVALID;
-  return plan->passes.empty() ? 0 : (int)plan->passes.size();
+  if (plan->passes.empty()) return 0;
+  if (plan->slabs > 1) {
+    const int64_t L = plan->shape_out[0], per = (L + plan->slabs - 1) / plan->slabs;
+    return (int)plan->passes.size() - 2 + 2 * (int)((L + per - 1) / per);
+  }
+  return (int)plan->passes.size();
 }
 
 int jfx_execute(const jfx_plan* plan, void* stream, const void* in, void* out, void* workspace) {
