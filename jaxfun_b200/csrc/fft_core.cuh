@@ -1,0 +1,77 @@
+// Register/shared-memory core of the Stockham FFT used by kernels_fft2.cu and kernels_fused.cu.
+#pragma once
+#include "fft_common.cuh"
+
+namespace jfx {
+
+// Forward DFT of one line of length N spread over TN = N/E threads (E = Geo<N>::RMAX points each).
+//   in : v[bf * R0 + r] = x[jj + r * (N / R0)],  jj = j + bf * TN          (pass-0 input stride)
+//   out: v[bf * RL + r] = X[jj + r * (N / RL)],  RL = radix of the last pass
+// Sl is the line's exchange buffer (Geo<N>::PITCH elements, skew-padded).  The caller must put a
+// barrier between the return of this function and its next write to Sl.
+template <typename T, int N, bool WARP_SYNC>
+__device__ __forceinline__ void fft_core(Cpx<T>* v, Cpx<T>* __restrict__ Sl, int j, const Cpx<T>* __restrict__ tw) {
+  using P = Plan<N>;
+  constexpr int R0 = P::R0, R1 = P::R1, R2 = P::R2;
+  constexpr int E = Geo<N>::RMAX, TN = N / E, LOGSK = Geo<N>::LOGSK;
+  constexpr bool THREE = (R2 > 1);
+  constexpr int RL = THREE ? R2 : R1, NSL = N / RL;
+  auto sync = [&]() { if (WARP_SYNC) __syncwarp(); else __syncthreads(); };
+  {
+    constexpr int BPT = E / R0;
+#pragma unroll
+    for (int bf = 0; bf < BPT; ++bf) Dft<T, R0>::run(&v[bf * R0]);
+#pragma unroll
+    for (int bf = 0; bf < BPT; ++bf) {
+      const int jj = j + bf * TN;
+      Cpx<T>* dst = Sl + jj * (R0 + 1);                  // sk(jj*R0 + r) = jj*(R0+1) + r
+#pragma unroll
+      for (int r = 0; r < R0; ++r) dst[r] = v[bf * R0 + r];
+    }
+  }
+  sync();
+  if constexpr (THREE) {
+    constexpr int R = R1, NS = R0, STR = N / R, BPT = E / R, TS = N / (NS * R);
+    constexpr int IN_OFF = STR + (STR >> LOGSK), OUT_OFF = NS + (NS >> LOGSK);
+#pragma unroll
+    for (int bf = 0; bf < BPT; ++bf) {
+      const Cpx<T>* src = Sl + sk<LOGSK>(j + bf * TN);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[bf * R + r] = src[r * IN_OFF];
+    }
+    sync();
+#pragma unroll
+    for (int bf = 0; bf < BPT; ++bf) {
+      const int jj = j + bf * TN, k = jj % NS;
+      const Cpx<T>* w = tw + k * TS;
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[bf * R + r] = cmul(v[bf * R + r], w[(r - 1) * k * TS]);
+      Dft<T, R>::run(&v[bf * R]);
+      Cpx<T>* dst = Sl + sk<LOGSK>((jj / NS) * NS * R + k);
+#pragma unroll
+      for (int r = 0; r < R; ++r) dst[r * OUT_OFF] = v[bf * R + r];
+    }
+    sync();
+  }
+  {
+    constexpr int R = RL, NS = NSL, STR = N / R, BPT = E / R, TS = N / (NS * R);
+    constexpr int IN_OFF = STR + (STR >> LOGSK);
+    static_assert(TS == 1, "last pass spans the whole transform");
+#pragma unroll
+    for (int bf = 0; bf < BPT; ++bf) {
+      const Cpx<T>* src = Sl + sk<LOGSK>(j + bf * TN);
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[bf * R + r] = src[r * IN_OFF];
+    }
+#pragma unroll
+    for (int bf = 0; bf < BPT; ++bf) {
+      const int k = j + bf * TN;                         // jj < NS: k = jj
+      const Cpx<T>* w = tw + k;
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[bf * R + r] = cmul(v[bf * R + r], w[(r - 1) * k]);
+      Dft<T, R>::run(&v[bf * R]);
+    }
+  }
+}
+
+}  // namespace jfx

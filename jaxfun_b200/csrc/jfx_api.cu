@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "jfx_common.h"
+#include "fft_common.cuh"
 
 namespace jfx {
 
@@ -262,6 +263,16 @@ static int execute_plan(const jfx_plan* pl, cudaStream_t s, const void* in, void
 struct jfx_nonlinear {
   std::vector<jfx_plan*> leaves;
   jfx_plan* final_plan = nullptr;
+  // ---- row-fused path (kernels_fused.cu): last axis Fourier, leaves + pointwise + forward in one kernel
+  bool fused = false;
+  std::vector<jfx_plan*> pre_plans;        // one per leaf group: the other axes -> physical (may be empty)
+  jfx_plan* post_plan = nullptr;           // the other axes of the final transform (may be null)
+  std::vector<jfx::FastTables*> tables;    // owned: twiddles + per-leaf derivative multipliers
+  jfx::FusedRowArgs fargs{};
+  int fused_n = 0;
+  size_t pre_bytes = 0, row_out_bytes = 0; // one pre-array / the row kernel's output
+  size_t scratch_bytes = 0;                // L2-resident leaf lines of the persistent grid
+  int n_groups = 0;
   jfx::PointwiseProgram prog{};
   const void* statics[JFX_MAX_LEAVES]{};
   int dtype = JFX_F64;
@@ -272,8 +283,136 @@ struct jfx_nonlinear {
   ~jfx_nonlinear() {
     for (auto* p : leaves) delete p;
     delete final_plan;
+    for (auto* p : pre_plans) delete p;
+    delete post_plan;
+    for (auto* t : tables) jfx::fast_tables_destroy(t);
   }
 };
+
+namespace jfx {
+
+// Decide whether the nonlinear term can run row-fused (kernels_fused.cu) and build what that path needs.
+// Conditions: complex data, the LAST array axis is a fast Fourier axis in the final transform and in every
+// leaf (same n_quad, same coefficient count), and the leaf lines of one row fit in shared memory.
+// Leaves are grouped by what they need from the OTHER axes (their derivative orders there): one
+// "pre-plan" per group takes those axes to physical space and leaves the last axis in coefficient space.
+static int try_fuse_rows(const jfx_nonlinear_desc* d, jfx_nonlinear* nl) {
+  static const bool disabled = [] { const char* e = getenv("JFX_NL_FUSE"); return e && e[0] == '0'; }();
+  if (disabled) return JFX_OK;
+  const jfx_plan_desc* fd = d->final_transform;
+  const int nd = fd->ndim, last = nd - 1;
+  if (!dtype_is_complex(fd->dtype)) return JFX_OK;
+  const jfx_axis_desc& fa = fd->axis[last];
+  if (fa.basis != JFX_BASIS_FOURIER) return JFX_OK;
+  const int n = fa.n_quad;
+  if (n < 64 || !fast_available(JFX_BASIS_FOURIER, n, fd->dtype)) return JFX_OK;
+  if (fd->shape_in[last] != n) return JFX_OK;
+  const int64_t n_coeff = d->leaves[0]->shape_in[last];
+  for (int l = 0; l < d->n_leaves; ++l) {
+    const jfx_axis_desc& la = d->leaves[l]->axis[last];
+    if (la.basis != JFX_BASIS_FOURIER || la.n_quad != n || d->leaves[l]->shape_in[last] != n_coeff) return JFX_OK;
+    if (la.domain_factor != d->leaves[0]->axis[last].domain_factor) return JFX_OK;
+  }
+  FusedRowArgs& fa_ = nl->fargs;
+  fa_ = FusedRowArgs{};
+  fa_.n_leaves = d->n_leaves;
+  fa_.rows = 1;   // placeholder for the query
+  fa_.n_coeff = (int)n_coeff;
+  fa_.n_out = fa.n_modes;
+  fa_.depth = program_depth(nl->prog);
+  size_t scratch_bytes = 0;
+  if (launch_fused_rows(nullptr, fd->dtype, n, fa_, &scratch_bytes) != 1) return JFX_OK;
+  nl->scratch_bytes = align_up(scratch_bytes, 256);
+
+  // ---- groups: leaves with identical specs on the other axes ----------------------------------------
+  bool other_axes = false;
+  for (int ax = 0; ax < last; ++ax) other_axes |= (fd->axis[ax].basis != JFX_BASIS_NONE);
+  std::vector<int> group_rep;   // representative leaf of each group
+  for (int l = 0; l < d->n_leaves; ++l) {
+    int g = -1;
+    for (size_t k = 0; k < group_rep.size() && g < 0; ++k) {
+      bool same = true;
+      for (int ax = 0; ax < last; ++ax) same &= (d->leaves[l]->axis[ax].deriv == d->leaves[group_rep[k]]->axis[ax].deriv);
+      if (same) g = (int)k;
+    }
+    if (g < 0) { g = (int)group_rep.size(); group_rep.push_back(l); }
+    fa_.leaf_group[l] = g;
+  }
+  nl->n_groups = (int)group_rep.size();
+  const size_t es = dtype_size(fd->dtype);
+  int64_t rows = 1;
+  for (int ax = 0; ax < last; ++ax) rows *= fd->shape_in[ax];
+  if (other_axes) {
+    for (int rep : group_rep) {
+      jfx_plan_desc pd = *d->leaves[rep];
+      pd.axis[last] = jfx_axis_desc{};
+      pd.axis[last].basis = JFX_BASIS_NONE;
+      bool any = false;
+      for (int ax = 0; ax < last; ++ax) any |= (pd.axis[ax].deriv != 0);
+      pd.op = any ? JFX_OP_BACKWARD_PRIMITIVE : JFX_OP_BACKWARD;
+      jfx_plan* p = nullptr;
+      int rc = jfx_plan_create(&pd, &p);
+      if (rc != JFX_OK) return rc;
+      nl->pre_plans.push_back(p);
+      nl->sub_ws = std::max(nl->sub_ws, p->ws_bytes);
+      for (int ax = 0; ax < last; ++ax)
+        JFX_REQUIRE(p->shape_out[ax] == fd->shape_in[ax], JFX_ERR_INVALID, "leaf physical shape differs on axis %d", ax);
+    }
+    jfx_plan_desc qd = *fd;
+    qd.axis[last] = jfx_axis_desc{};
+    qd.axis[last].basis = JFX_BASIS_NONE;
+    qd.shape_in[last] = fa.n_modes;
+    int rc = jfx_plan_create(&qd, &nl->post_plan);
+    if (rc != JFX_OK) return rc;
+    nl->sub_ws = std::max(nl->sub_ws, nl->post_plan->ws_bytes);
+    nl->pre_bytes = align_up((size_t)rows * n_coeff * es, 256);
+    nl->row_out_bytes = align_up((size_t)rows * fa.n_modes * es, 256);
+  }
+  // ---- tables: twiddles and per-leaf derivative multipliers --------------------------------------------
+  {
+    FastParams fp{};
+    fp.kind = FAST_FOURIER_FORWARD; fp.n_modes = fa.n_modes; fp.n_quad = n; fp.deriv = 0; fp.domain_factor = fa.domain_factor;
+    FastTables* t = nullptr;
+    int rc = fast_tables_create(fp, fd->dtype, &t);
+    if (rc != JFX_OK) return rc;
+    nl->tables.push_back(t);
+    fa_.tw = t->d_tw;
+  }
+  for (int l = 0; l < d->n_leaves; ++l) {
+    const jfx_axis_desc& la = d->leaves[l]->axis[last];
+    const int k = d->leaves[l]->op == JFX_OP_BACKWARD_PRIMITIVE ? la.deriv : 0;
+    fa_.mult[l] = nullptr;
+    if (k > 0) {
+      FastParams fp{};
+      fp.kind = FAST_FOURIER_BACKWARD; fp.n_modes = (int)n_coeff; fp.n_quad = n; fp.deriv = k; fp.domain_factor = la.domain_factor;
+      FastTables* t = nullptr;
+      int rc = fast_tables_create(fp, fd->dtype, &t);
+      if (rc != JFX_OK) return rc;
+      nl->tables.push_back(t);
+      fa_.mult[l] = t->d_pre;
+    }
+  }
+  const double PI = 3.14159265358979323846;
+  fa_.scale = 1.0 / n;
+  if (fd->op == JFX_OP_SCALAR_PRODUCT) fa_.scale *= 2.0 * PI / fa.domain_factor;
+  fa_.rows = rows;
+  fa_.n_coeff = (int)n_coeff;
+  fa_.n_out = fa.n_modes;
+  fa_.n_instr = nl->prog.n_instr;
+  memcpy(fa_.instr, nl->prog.instr, sizeof(jfx_pw_instr) * nl->prog.n_instr);
+  memcpy(fa_.consts, nl->prog.consts, sizeof(fa_.consts));
+  for (int i = 0; i < JFX_MAX_LEAVES; ++i) fa_.statics[i] = nl->statics[i];
+  {
+    int rc = validate_program(nl->prog, nl->statics);
+    if (rc != JFX_OK) return rc;
+  }
+  nl->fused = true;
+  nl->fused_n = n;
+  nl->ws_bytes = (size_t)nl->n_groups * nl->pre_bytes + nl->row_out_bytes + nl->scratch_bytes + align_up(nl->sub_ws, 256);
+  return JFX_OK;
+}
+
+}  // namespace jfx
 
 extern "C" {
 
@@ -428,6 +567,10 @@ int jfx_nonlinear_create(const jfx_nonlinear_desc* d, jfx_nonlinear** out) {
   nl->field_bytes = align_up((size_t)nl->phys_elems * dtype_size(nl->dtype), 256);
   // workspace = leaf fields + pointwise result + sub-plan workspace
   nl->ws_bytes = (size_t)(d->n_leaves + 1) * nl->field_bytes + align_up(nl->sub_ws, 256);
+  {
+    const int rc = try_fuse_rows(d, nl.get());
+    if (rc != JFX_OK) return rc;
+  }
   *out = nl.release();
   return JFX_OK;
 }
@@ -450,6 +593,11 @@ int jfx_nonlinear_shape_out(const jfx_nonlinear* nl, int64_t* shape_out, int* nd
 
 int jfx_nonlinear_launches(const jfx_nonlinear* nl) {
   if (!nl) return JFX_ERR_INVALID;
+  if (nl->fused) {
+    int n = 1 + (nl->post_plan ? jfx_plan_launches(nl->post_plan) : 0);
+    for (auto* p : nl->pre_plans) n += jfx_plan_launches(p);
+    return n;
+  }
   int n = 1 + jfx_plan_launches(nl->final_plan);
   for (auto* p : nl->leaves) n += std::max(1, jfx_plan_launches(p));
   return n;
@@ -460,6 +608,28 @@ int jfx_nonlinear_execute(const jfx_nonlinear* nl, void* stream, const void* uh,
   JFX_REQUIRE(nl && uh && out && workspace, JFX_ERR_INVALID, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
   char* base = (char*)workspace;
+  if (nl->fused) {
+    FusedRowArgs fa = nl->fargs;
+    fa.scratch = base + (size_t)nl->n_groups * nl->pre_bytes + nl->row_out_bytes;
+    char* sub = (char*)fa.scratch + nl->scratch_bytes;
+    if (nl->pre_plans.empty()) {
+      for (int g = 0; g < nl->n_groups; ++g) fa.src[g] = uh;
+      fa.out = out;
+    } else {
+      for (int g = 0; g < nl->n_groups; ++g) {
+        void* dst = base + (size_t)g * nl->pre_bytes;
+        int rc = execute_plan(nl->pre_plans[g], s, uh, dst, sub);
+        if (rc != JFX_OK) return rc;
+        fa.src[g] = dst;
+      }
+      fa.out = base + (size_t)nl->n_groups * nl->pre_bytes;
+    }
+    int rc = launch_fused_rows(s, nl->dtype, nl->fused_n, fa, nullptr);
+    if (rc < 0) return rc;
+    JFX_REQUIRE(rc == 1, JFX_ERR_UNSUPPORTED, "row-fused nonlinear kernel refused a configuration it accepted at plan time");
+    if (nl->post_plan) return execute_plan(nl->post_plan, s, fa.out, out, sub);
+    return JFX_OK;
+  }
   const size_t nleaf = nl->leaves.size();
   char* sub = base + (nleaf + 1) * nl->field_bytes;
   const void* fields[JFX_MAX_LEAVES];

@@ -100,8 +100,30 @@ struct PointwiseProgram {
   double consts[32][2];
   int n_leaves;
 };
+int validate_program(const PointwiseProgram& prog, const void* const* statics);
+int program_depth(const PointwiseProgram& prog);
 int launch_pointwise(cudaStream_t s, const PointwiseProgram& prog, const void* const* leaves,
                      const void* const* statics, void* out, int64_t n, int dtype);
+
+// Row-fused nonlinear term along a Fourier last axis (kernels_fused.cu)
+struct FusedRowArgs {
+  const void* src[JFX_MAX_LEAVES];     // coefficient rows per leaf group: [rows, n_coeff] complex
+  const void* mult[JFX_MAX_LEAVES];    // per-leaf spectral multiplier over the coefficient index, or null
+  const void* statics[JFX_MAX_LEAVES]; // mesh-sampled statics: [rows, N] complex
+  int leaf_group[JFX_MAX_LEAVES];
+  int n_leaves;
+  void* out;                           // [rows, n_out] complex
+  void* scratch;                       // leaf lines of the resident CTAs (bytes: see launch_fused_rows query)
+  const void* tw;                      // exp(-2 pi i m / N)
+  long long rows;
+  int n_coeff, n_out;
+  double scale;
+  int n_instr;
+  int depth;                           // operand-stack depth of the program
+  jfx_pw_instr instr[JFX_MAX_PROGRAM];
+  double consts[32][2];
+};
+int launch_fused_rows(cudaStream_t s, int dtype, int n, const FusedRowArgs& a, size_t* scratch_query);
 
 int calibrate_dmma(cudaStream_t s, int iters, double* tflops);
 int calibrate_dfma(cudaStream_t s, int iters, double* tflops);

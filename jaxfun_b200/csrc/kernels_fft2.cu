@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "fft_common.cuh"
+#include "fft_core.cuh"
 
 namespace jfx {
 namespace f2 {
@@ -174,62 +175,10 @@ fft2_kernel(const FftArgs a) {
         v[bf * R0 + r] = z;
       }
     }
-#pragma unroll
-    for (int bf = 0; bf < BPT; ++bf) Dft<T, R0>::run(&v[bf * R0]);
-#pragma unroll
-    for (int bf = 0; bf < BPT; ++bf) {
-      const int jj = j + bf * TN;
-      Cpx<T>* dst = Sl + jj * (R0 + 1);                  // sk(jj*R0 + r) = jj*(R0+1) + r
-#pragma unroll
-      for (int r = 0; r < R0; ++r) dst[r] = v[bf * R0 + r];
-    }
   }
-  sync();
-
-  // ================================ middle pass (3-pass sizes) =================================
-  if constexpr (THREE) {
-    constexpr int R = R1, NS = R0, STR = N / R, BPT = E / R, TS = N / (NS * R);
-    constexpr int IN_OFF = STR + (STR >> LOGSK), OUT_OFF = NS + (NS >> LOGSK);
-#pragma unroll
-    for (int bf = 0; bf < BPT; ++bf) {
-      const Cpx<T>* src = Sl + sk<LOGSK>(j + bf * TN);
-#pragma unroll
-      for (int r = 0; r < R; ++r) v[bf * R + r] = src[r * IN_OFF];
-    }
-    sync();
-#pragma unroll
-    for (int bf = 0; bf < BPT; ++bf) {
-      const int jj = j + bf * TN, k = jj % NS;
-      const Cpx<T>* w = tw + k * TS;
-#pragma unroll
-      for (int r = 1; r < R; ++r) v[bf * R + r] = cmul(v[bf * R + r], w[(r - 1) * k * TS]);
-      Dft<T, R>::run(&v[bf * R]);
-      Cpx<T>* dst = Sl + sk<LOGSK>((jj / NS) * NS * R + k);
-#pragma unroll
-      for (int r = 0; r < R; ++r) dst[r * OUT_OFF] = v[bf * R + r];
-    }
-    sync();
-  }
-
-  // ================================ last pass: registers -> global =============================
+  fft_core<T, N, WARP_SYNC>(v, Sl, j, tw);
   {
-    constexpr int R = RL, NS = NSL, STR = N / R, BPT = E / R, TS = N / (NS * R);
-    constexpr int IN_OFF = STR + (STR >> LOGSK);
-    static_assert(TS == 1, "last pass spans the whole transform");
-#pragma unroll
-    for (int bf = 0; bf < BPT; ++bf) {
-      const Cpx<T>* src = Sl + sk<LOGSK>(j + bf * TN);
-#pragma unroll
-      for (int r = 0; r < R; ++r) v[bf * R + r] = src[r * IN_OFF];
-    }
-#pragma unroll
-    for (int bf = 0; bf < BPT; ++bf) {
-      const int k = j + bf * TN;                         // jj < NS: k = jj
-      const Cpx<T>* w = tw + k;
-#pragma unroll
-      for (int r = 1; r < R; ++r) v[bf * R + r] = cmul(v[bf * R + r], w[(r - 1) * k]);
-      Dft<T, R>::run(&v[bf * R]);
-    }
+    constexpr int R = RL, NS = NSL, BPT = E / R;
     // thread now holds FFT bins b = jj + r * NS
 
     if (KIND == K_FOUR_BWD) {

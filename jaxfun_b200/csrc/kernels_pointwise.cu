@@ -8,160 +8,41 @@
 #include <math.h>
 
 #include "jfx_common.h"
+#include "pointwise.cuh"
 
 namespace jfx {
 
-// ---------------------------------------------------------------------------------------------
-// complex helpers
-// ---------------------------------------------------------------------------------------------
-template <typename T> struct C2 { T re, im; };
-
-template <typename T> __device__ __forceinline__ C2<T> cmul(C2<T> a, C2<T> b) {
-  return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
-}
-template <typename T> __device__ __forceinline__ C2<T> cdiv(C2<T> a, C2<T> b) {
-  T d = b.re * b.re + b.im * b.im;
-  return {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d};
-}
-template <typename T> __device__ __forceinline__ C2<T> cexp(C2<T> a) {
-  T e = exp(a.re), s, c;
-  sincos(a.im, &s, &c);
-  return {e * c, e * s};
-}
-template <typename T> __device__ __forceinline__ C2<T> clog(C2<T> a) {
-  return {log(hypot(a.re, a.im)), atan2(a.im, a.re)};
-}
-template <typename T> __device__ __forceinline__ C2<T> cpowi(C2<T> a, int n) {
-  bool neg = n < 0;
-  unsigned m = neg ? (unsigned)(-n) : (unsigned)n;
-  C2<T> r{T(1), T(0)};
-  while (m) {
-    if (m & 1u) r = cmul(r, a);
-    a = cmul(a, a);
-    m >>= 1;
-  }
-  if (neg) r = cdiv(C2<T>{T(1), T(0)}, r);
-  return r;
-}
-template <typename T> __device__ __forceinline__ C2<T> csqrt_(C2<T> a) {
-  if (a.im == T(0)) {
-    if (a.re >= T(0)) return {sqrt(a.re), T(0)};
-    return {T(0), sqrt(-a.re)};
-  }
-  T m = hypot(a.re, a.im);
-  T sr = sqrt((m + a.re) * T(0.5));
-  T si = sqrt((m - a.re) * T(0.5));
-  return {sr, a.im < 0 ? -si : si};
-}
-
-template <typename T> __device__ C2<T> apply_func(int fn, C2<T> v) {
-  const bool real_arg = (v.im == T(0));
-  switch (fn) {
-    case JFX_FN_EXP: return cexp(v);
-    case JFX_FN_LOG: return clog(v);
-    case JFX_FN_SIN: {
-      if (real_arg) return {sin(v.re), T(0)};
-      return {sin(v.re) * cosh(v.im), cos(v.re) * sinh(v.im)};
-    }
-    case JFX_FN_COS: {
-      if (real_arg) return {cos(v.re), T(0)};
-      return {cos(v.re) * cosh(v.im), -sin(v.re) * sinh(v.im)};
-    }
-    case JFX_FN_TAN: {
-      if (real_arg) return {tan(v.re), T(0)};
-      C2<T> s{sin(v.re) * cosh(v.im), cos(v.re) * sinh(v.im)};
-      C2<T> c{cos(v.re) * cosh(v.im), -sin(v.re) * sinh(v.im)};
-      return cdiv(s, c);
-    }
-    case JFX_FN_SINH: {
-      if (real_arg) return {sinh(v.re), T(0)};
-      return {sinh(v.re) * cos(v.im), cosh(v.re) * sin(v.im)};
-    }
-    case JFX_FN_COSH: {
-      if (real_arg) return {cosh(v.re), T(0)};
-      return {cosh(v.re) * cos(v.im), sinh(v.re) * sin(v.im)};
-    }
-    case JFX_FN_TANH: {
-      if (real_arg) return {tanh(v.re), T(0)};
-      C2<T> s{sinh(v.re) * cos(v.im), cosh(v.re) * sin(v.im)};
-      C2<T> c{cosh(v.re) * cos(v.im), sinh(v.re) * sin(v.im)};
-      return cdiv(s, c);
-    }
-    case JFX_FN_SQRT: return csqrt_(v);
-    case JFX_FN_SIGN: {
-      if (real_arg) return {T((v.re > 0) - (v.re < 0)), T(0)};
-      T m = hypot(v.re, v.im);
-      return m == T(0) ? C2<T>{T(0), T(0)} : C2<T>{v.re / m, v.im / m};
-    }
-    case JFX_FN_HEAVISIDE: return {v.re > 0 ? T(1) : (v.re < 0 ? T(0) : T(0.5)), T(0)};
-    case JFX_FN_ASIN: return {asin(v.re), T(0)};
-    case JFX_FN_ACOS: return {acos(v.re), T(0)};
-    case JFX_FN_ATAN: return {atan(v.re), T(0)};
-    case JFX_FN_ASINH: return {asinh(v.re), T(0)};
-    case JFX_FN_ACOSH: return {acosh(v.re), T(0)};
-    case JFX_FN_ATANH: return {atanh(v.re), T(0)};
-    case JFX_FN_RE: return {v.re, T(0)};
-    case JFX_FN_IM: return {v.im, T(0)};
-  }
-  return v;
-}
-
-// ---------------------------------------------------------------------------------------------
-// pointwise stack machine
-// ---------------------------------------------------------------------------------------------
-struct PwArgs {
-  const void* leaves[JFX_MAX_LEAVES];
-  const void* statics[JFX_MAX_LEAVES];
-  int n_instr;
-  jfx_pw_instr instr[JFX_MAX_PROGRAM];
-  double consts[32][2];
-};
-
-template <typename T, bool CPLX>
+template <typename T, bool CPLX, int DEPTH>
 __global__ void __launch_bounds__(256) pointwise_kernel(const __grid_constant__ PwArgs a, void* out_,
                                                         int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
-    C2<T> st[8];
-    int sp = 0;
-    for (int pc = 0; pc < a.n_instr; ++pc) {
-      const int op = a.instr[pc].op, arg = a.instr[pc].arg;
-      switch (op) {
-        case JFX_PW_LEAF:
-          if (CPLX) st[sp++] = reinterpret_cast<const C2<T>*>(a.leaves[arg])[i];
-          else st[sp++] = {reinterpret_cast<const T*>(a.leaves[arg])[i], T(0)};
-          break;
-        case JFX_PW_STATIC:
-          if (CPLX) st[sp++] = reinterpret_cast<const C2<T>*>(a.statics[arg])[i];
-          else st[sp++] = {reinterpret_cast<const T*>(a.statics[arg])[i], T(0)};
-          break;
-        case JFX_PW_CONST: st[sp++] = {T(a.consts[arg][0]), T(a.consts[arg][1])}; break;
-        case JFX_PW_ADD: --sp; st[sp - 1] = {st[sp - 1].re + st[sp].re, st[sp - 1].im + st[sp].im}; break;
-        case JFX_PW_MUL: --sp; st[sp - 1] = cmul(st[sp - 1], st[sp]); break;
-        case JFX_PW_POWI: st[sp - 1] = cpowi(st[sp - 1], arg); break;
-        case JFX_PW_ABS: st[sp - 1] = {CPLX ? hypot(st[sp - 1].re, st[sp - 1].im) : fabs(st[sp - 1].re), T(0)}; break;
-        case JFX_PW_NEG: st[sp - 1] = {-st[sp - 1].re, -st[sp - 1].im}; break;
-        case JFX_PW_CONJ: st[sp - 1].im = -st[sp - 1].im; break;
-        case JFX_PW_FUNC: st[sp - 1] = apply_func<T>(arg, st[sp - 1]); break;
-        case JFX_PW_POWR: {
-          const T e = T(a.consts[arg][0]);
-          C2<T> v = st[sp - 1];
-          if (v.im == T(0) && (v.re >= T(0) || !CPLX)) st[sp - 1] = {pow(v.re, e), T(0)};
-          else {
-            C2<T> l = clog(v);
-            st[sp - 1] = cexp(C2<T>{l.re * e, l.im * e});
-          }
-        } break;
-      }
-    }
-    if (CPLX) reinterpret_cast<C2<T>*>(out_)[i] = st[0];
-    else reinterpret_cast<T*>(out_)[i] = st[0].re;
+    auto leaf = [&](int l) -> C2<T> {
+      if (CPLX) return reinterpret_cast<const C2<T>*>(a.leaves[l])[i];
+      return C2<T>{reinterpret_cast<const T*>(a.leaves[l])[i], T(0)};
+    };
+    auto stat = [&](int l) -> C2<T> {
+      if (CPLX) return reinterpret_cast<const C2<T>*>(a.statics[l])[i];
+      return C2<T>{reinterpret_cast<const T*>(a.statics[l])[i], T(0)};
+    };
+    const C2<T> r = pw_eval<T, CPLX, DEPTH>(a.instr, a.n_instr, a.consts, leaf, stat);
+    if (CPLX) reinterpret_cast<C2<T>*>(out_)[i] = r;
+    else reinterpret_cast<T*>(out_)[i] = r.re;
   }
 }
 
-int launch_pointwise(cudaStream_t s, const PointwiseProgram& prog, const void* const* leaves,
-                     const void* const* statics, void* out, int64_t n, int dtype) {
-  JFX_REQUIRE(prog.n_instr > 0 && prog.n_instr <= JFX_MAX_PROGRAM, JFX_ERR_INVALID, "bad program length");
+int program_depth(const PointwiseProgram& prog) {
+  int sp = 0, mx = 0;
+  for (int i = 0; i < prog.n_instr; ++i) {
+    const int op = prog.instr[i].op;
+    if (op == JFX_PW_LEAF || op == JFX_PW_CONST || op == JFX_PW_STATIC) ++sp;
+    else if (op == JFX_PW_ADD || op == JFX_PW_MUL) --sp;
+    mx = sp > mx ? sp : mx;
+  }
+  return mx;
+}
+
+int validate_program(const PointwiseProgram& prog, const void* const* statics) {
   // validate stack discipline on the host so the kernel cannot run off its 8-entry stack
   int sp = 0;
   for (int i = 0; i < prog.n_instr; ++i) {
@@ -181,6 +62,13 @@ int launch_pointwise(cudaStream_t s, const PointwiseProgram& prog, const void* c
     JFX_REQUIRE(sp <= 8, JFX_ERR_UNSUPPORTED, "pointwise stack deeper than 8");
   }
   JFX_REQUIRE(sp == 1, JFX_ERR_INVALID, "program leaves %d values on the stack", sp);
+  return JFX_OK;
+}
+
+int launch_pointwise(cudaStream_t s, const PointwiseProgram& prog, const void* const* leaves,
+                     const void* const* statics, void* out, int64_t n, int dtype) {
+  JFX_REQUIRE(prog.n_instr > 0 && prog.n_instr <= JFX_MAX_PROGRAM, JFX_ERR_INVALID, "bad program length");
+  { const int rc = validate_program(prog, statics); if (rc != JFX_OK) return rc; }
   if (n == 0) return JFX_OK;
   PwArgs a{};
   for (int i = 0; i < prog.n_leaves; ++i) a.leaves[i] = leaves[i];
@@ -190,13 +78,20 @@ int launch_pointwise(cudaStream_t s, const PointwiseProgram& prog, const void* c
   memcpy(a.consts, prog.consts, sizeof(a.consts));
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  const bool deep = program_depth(prog) > 4;
+#define JFX_PW_LAUNCH(TT, CP) \
+  do { \
+    if (deep) pointwise_kernel<TT, CP, 8><<<(unsigned)blocks, 256, 0, s>>>(a, out, n); \
+    else pointwise_kernel<TT, CP, 4><<<(unsigned)blocks, 256, 0, s>>>(a, out, n); \
+  } while (0)
   switch (dtype) {
-    case JFX_F32: pointwise_kernel<float, false><<<(unsigned)blocks, 256, 0, s>>>(a, out, n); break;
-    case JFX_F64: pointwise_kernel<double, false><<<(unsigned)blocks, 256, 0, s>>>(a, out, n); break;
-    case JFX_C64: pointwise_kernel<float, true><<<(unsigned)blocks, 256, 0, s>>>(a, out, n); break;
-    case JFX_C128: pointwise_kernel<double, true><<<(unsigned)blocks, 256, 0, s>>>(a, out, n); break;
+    case JFX_F32: JFX_PW_LAUNCH(float, false); break;
+    case JFX_F64: JFX_PW_LAUNCH(double, false); break;
+    case JFX_C64: JFX_PW_LAUNCH(float, true); break;
+    case JFX_C128: JFX_PW_LAUNCH(double, true); break;
     default: set_error("bad dtype"); return JFX_ERR_INVALID;
   }
+#undef JFX_PW_LAUNCH
   JFX_CUDA_OK(cudaGetLastError());
   return JFX_OK;
 }
