@@ -311,8 +311,8 @@ def run_ours(args):
             "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
             "traffic": ncu_traffic("dgemm_dmma"), "launches_per_step": n_l, "avg_launch_ms": tL / n_l,
             "flops_per_launch": flops_L / n_l,
-            "peak_source": "live calibration: max(register-resident DMMA, DFMA, cuBLAS DGEMM 8192^3); "
-                           "MEASURED_PEAKS.json has no FP64 figure",
+            "peak_source": "live calibration: max(register-resident DMMA loop [best of 1/2/8 CTAs per SM], DFMA loop, "
+                           "cuBLAS DGEMM 8192^3); MEASURED_PEAKS.json has no FP64 figure",
             "fp64_calibration_tflops": {"dmma_regs": dm.value, "dfma_regs": df.value, "cublas_dgemm_8192": cublas_tf,
                                         "nominal": 37.0},
         }

@@ -16,6 +16,7 @@
 //     Complex interleaved data on a non-last axis is the NN case with inner' = 2*inner.
 #include <cuda_runtime.h>
 #include <cuComplex.h>
+#include <stdlib.h>
 
 #include "jfx_common.h"
 
@@ -135,40 +136,46 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_dmma(const Params p) {
 
   const int ktiles = (p.K + BK - 1) / BK;
 
-  auto load_stage = [&](int stage, int kt) {
-    const int k0 = kt * BK;
-    // A tile: BM rows x 16 doubles = 8 chunks of 16 B per row
-    double* as = As + stage * A_STAGE;
+  // ---- loader state, hoisted out of the k loop -------------------------------------------------
+  // Every thread copies 4 A chunks and 4 B chunks (16 B each) per k-tile.  Their global pointers only
+  // advance by a constant per k-tile and their shared-memory offsets never change, so nothing but a
+  // pointer bump and the k-bound test is left inside the loop; part `kk` of the copies is issued in
+  // front of butterfly step kk so the DMMA stream of a warp is never interrupted by a long burst of
+  // address arithmetic right after the barrier (which is when the other warp of the SMSP does the same).
+  constexpr int NCH = (BM * BK / 2) / THREADS;           // chunks per thread and operand (4)
+  static_assert(NCH == BK / 4, "one A and one B chunk per butterfly step");
+  const int a_row = tid >> 3, a_kc = (tid & 7) * 2;       // A / NT-B: 8 chunks per row, +32 rows per chunk
+  const int b_row = NN ? (tid >> 6) : a_row;              // NN-B: 64 chunks per row, +4 rows per chunk
+  const int b_col = NN ? (tid & 63) * 2 : a_kc;
+  const double* a_ptr = A + (int64_t)(bm0 + a_row) * p.lda + a_kc;
+  const double* b_ptr = NN ? B + (int64_t)b_row * p.ldb + bn0 + b_col : B + (int64_t)(bn0 + b_row) * p.ldb + b_col;
+  const int64_t a_step = 32 * p.lda;                     // between a thread's chunks
+  const int64_t b_step = NN ? 4 * p.ldb : 32 * p.ldb;
+  const int64_t b_adv = NN ? (int64_t)BK * p.ldb : BK;   // per k-tile (A advances by BK)
+  const int a_soff = a_row * LDA + a_kc;
+  const int b_soff = NN ? b_row * LDB_NN + b_col : b_row * LDB_NT + b_col;
+  constexpr int A_SSTEP = 32 * LDA, B_SSTEP = NN ? 4 * LDB_NN : 32 * LDB_NT;
+  bool a_ok[NCH], b_ok[NCH];
 #pragma unroll
-    for (int it = 0; it < (BM * BK / 2) / THREADS; ++it) {
-      const int c = tid + it * THREADS;
-      const int row = c >> 3, kc = (c & 7) * 2;
-      const bool ok = (bm0 + row < p.M) && (k0 + kc < p.K);
-      const double* src = ok ? A + (int64_t)(bm0 + row) * p.lda + k0 + kc : A;
-      cp_async16(as + row * LDA + kc, src, ok);
+  for (int it = 0; it < NCH; ++it) {
+    a_ok[it] = bm0 + a_row + 32 * it < p.M;
+    b_ok[it] = NN ? (bn0 + b_col < p.N) : (bn0 + b_row + 32 * it < p.N);
+  }
+  int l_k0 = 0;   // k origin of the next tile to load
+
+  auto load_part = [&](int stage, int it) {
+    // A chunk `it`
+    {
+      const bool ok = a_ok[it] && (l_k0 + a_kc < p.K);
+      cp_async16(As + stage * A_STAGE + a_soff + it * A_SSTEP, ok ? a_ptr + it * a_step : A, ok);
     }
-    double* bs = Bs + stage * B_STAGE;
-    if (!NN) {
-#pragma unroll
-      for (int it = 0; it < (BN * BK / 2) / THREADS; ++it) {
-        const int c = tid + it * THREADS;
-        const int row = c >> 3, kc = (c & 7) * 2;
-        const bool ok = (bn0 + row < p.N) && (k0 + kc < p.K);
-        const double* src = ok ? B + (int64_t)(bn0 + row) * p.ldb + k0 + kc : B;
-        cp_async16(bs + row * LDB_NT + kc, src, ok);
-      }
-    } else {
-      // B tile: BK rows x 128 doubles = 64 chunks per row
-#pragma unroll
-      for (int it = 0; it < (BK * BN / 2) / THREADS; ++it) {
-        const int c = tid + it * THREADS;
-        const int row = c >> 6, nc = (c & 63) * 2;
-        const bool ok = (k0 + row < p.K) && (bn0 + nc < p.N);
-        const double* src = ok ? B + (int64_t)(k0 + row) * p.ldb + bn0 + nc : B;
-        cp_async16(bs + row * LDB_NN + nc, src, ok);
-      }
+    {
+      const bool kin = NN ? (l_k0 + b_row + 4 * it < p.K) : (l_k0 + b_col < p.K);
+      const bool ok = b_ok[it] && kin;
+      cp_async16(Bs + stage * B_STAGE + b_soff + it * B_SSTEP, ok ? b_ptr + it * b_step : B, ok);
     }
   };
+  auto advance = [&]() { a_ptr += BK; b_ptr += b_adv; l_k0 += BK; };
 
   double acc[WM / 8][WN / 8][2];
 #pragma unroll
@@ -179,23 +186,26 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_dmma(const Params p) {
   // prologue
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < ktiles) load_stage(s, s);
+    if (s < ktiles) {
+#pragma unroll
+      for (int it = 0; it < NCH; ++it) load_part(s, it);
+      advance();
+    }
     cp_async_commit();
   }
 
   for (int kt = 0; kt < ktiles; ++kt) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    // prefetch tile kt + STAGES - 1 into the slot freed at iteration kt - 1
-    {
-      const int nk = kt + STAGES - 1;
-      if (nk < ktiles) load_stage(nk % STAGES, nk);
-      cp_async_commit();
-    }
+    // tile kt + STAGES - 1 goes into the slot freed at iteration kt - 1, one part per butterfly step
+    const int nk = kt + STAGES - 1;
+    const bool more = nk < ktiles;
+    const int lstage = nk % STAGES;
     const double* as = As + (kt % STAGES) * A_STAGE + (wm * WM + g) * LDA + q;
     const double* bs = Bs + (kt % STAGES) * B_STAGE;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
+      if (more) load_part(lstage, kk);
       double a[WM / 8], b[WN / 8];
 #pragma unroll
       for (int i = 0; i < WM / 8; ++i) a[i] = as[i * 8 * LDA + kk * 4];
@@ -209,6 +219,8 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_dmma(const Params p) {
 #pragma unroll
         for (int j = 0; j < WN / 8; ++j) mma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+    if (more) advance();
+    cp_async_commit();
   }
   cp_async_wait<0>();
 
@@ -230,6 +242,189 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_dmma(const Params p) {
       }
     }
   }
+}
+
+// ---- persistent variant -------------------------------------------------------------------------
+// One CTA per SM walks its share of the (batch, M-tile, N-tile) tiles.  The cp.async pipeline runs
+// STAGES-1 k-tiles ahead ACROSS tile boundaries, so the loads of the next tile are in flight while the
+// epilogue of the current one stores C: the per-tile pipeline fill / drain of the one-tile-per-CTA kernel
+// (~20 % of its time at K = 256) disappears.  BK = 32 halves the number of CTA-wide barriers.
+namespace pers {
+constexpr int BK = 32, STAGES = 3;
+constexpr int LDA = BK + 4, LDB_NT = BK + 4, LDB_NN = BN + 4;
+constexpr int A_STAGE = BM * LDA, B_STAGE_NT = BN * LDB_NT, B_STAGE_NN = BK * LDB_NN;
+constexpr size_t smem_bytes(bool nn) {
+  return (size_t)STAGES * (A_STAGE + (nn ? B_STAGE_NN : B_STAGE_NT)) * sizeof(double);
+}
+}  // namespace pers
+
+struct PParams {
+  Params p;
+  int tiles_n, tiles_m, batch;   // tile grid; n fastest
+};
+
+template <bool NN>
+__global__ void __launch_bounds__(THREADS, 1) dgemm_dmma_persistent(const PParams pp) {
+  constexpr int BK = pers::BK, STAGES = pers::STAGES, LDA = pers::LDA, LDB_NT = pers::LDB_NT, LDB_NN = pers::LDB_NN;
+  constexpr int A_STAGE = pers::A_STAGE, B_STAGE_NT = pers::B_STAGE_NT, B_STAGE_NN = pers::B_STAGE_NN;
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + STAGES * A_STAGE;
+  constexpr int B_STAGE = NN ? B_STAGE_NN : B_STAGE_NT;
+  const Params& p = pp.p;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+  const int g = lane >> 2, q = lane & 3;
+
+  const int ktiles = (p.K + BK - 1) / BK;
+  const long long total_tiles = (long long)pp.tiles_n * pp.tiles_m * pp.batch;
+  const long long my_tiles = total_tiles > blockIdx.x ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long total_iters = my_tiles * ktiles;
+
+  // tile t -> (batch z, m-tile, n-tile); n fastest so CTAs that share an A panel run together
+  auto tile_origin = [&](long long t, int& bm0, int& bn0, long long& z) {
+    const int tn = (int)(t % pp.tiles_n);
+    const long long r = t / pp.tiles_n;
+    bm0 = (int)(r % pp.tiles_m) * BM;
+    bn0 = tn * BN;
+    z = r / pp.tiles_m;
+  };
+
+  // ---- loader: per-thread chunk geometry is fixed, pointers / predicates are refreshed once per tile ---
+  constexpr int NCH = (BM * BK / 2) / THREADS;           // chunks per thread and operand per k-tile (8)
+  constexpr int CPR = BK / 2;                            // 16-byte chunks per A / NT-B row
+  constexpr int RSTEP = THREADS / CPR;                   // rows between a thread's chunks (16)
+  constexpr int NN_RSTEP = THREADS / (BN / 2);           // NN-B: rows between a thread's chunks (4)
+  static_assert(NCH == BK / 4, "one A and one B chunk per butterfly step");
+  const int a_row = tid / CPR, a_kc = (tid % CPR) * 2;
+  const int b_row = NN ? (tid / (BN / 2)) : a_row;
+  const int b_col = NN ? (tid % (BN / 2)) * 2 : a_kc;
+  const int64_t a_step = (int64_t)RSTEP * p.lda;
+  const int64_t b_step = NN ? (int64_t)NN_RSTEP * p.ldb : (int64_t)RSTEP * p.ldb;
+  const int64_t b_adv = NN ? (int64_t)BK * p.ldb : BK;
+  const int a_soff = a_row * LDA + a_kc;
+  const int b_soff = NN ? b_row * LDB_NN + b_col : b_row * LDB_NT + b_col;
+  constexpr int A_SSTEP = RSTEP * LDA, B_SSTEP = NN ? NN_RSTEP * LDB_NN : RSTEP * LDB_NT;
+
+  long long l_it = 0, l_tile = blockIdx.x;
+  int l_kt = 0, l_k0 = 0;
+  const double *a_ptr = p.A, *b_ptr = p.B;
+  unsigned a_okm = 0, b_okm = 0;                         // bit it: chunk `it` is inside the matrix
+  auto refresh = [&]() {
+    int bm0, bn0;
+    long long z;
+    tile_origin(l_tile, bm0, bn0, z);
+    a_ptr = p.A + z * p.strideA + (int64_t)(bm0 + a_row) * p.lda + a_kc;
+    b_ptr = NN ? p.B + z * p.strideB + (int64_t)b_row * p.ldb + bn0 + b_col
+               : p.B + z * p.strideB + (int64_t)(bn0 + b_row) * p.ldb + b_col;
+    a_okm = b_okm = 0;
+#pragma unroll
+    for (int it = 0; it < NCH; ++it) {
+      if (bm0 + a_row + RSTEP * it < p.M) a_okm |= 1u << it;
+      if (NN ? (bn0 + b_col < p.N) : (bn0 + b_row + RSTEP * it < p.N)) b_okm |= 1u << it;
+    }
+    l_k0 = 0;
+  };
+  if (my_tiles > 0) refresh();
+
+  auto load_part = [&](int it) {
+    if (l_it >= total_iters) return;
+    const int stage = (int)(l_it % STAGES);
+    {
+      const bool ok = ((a_okm >> it) & 1u) && (l_k0 + a_kc < p.K);
+      cp_async16(As + stage * A_STAGE + a_soff + it * A_SSTEP, ok ? a_ptr + it * a_step : p.A, ok);
+    }
+    {
+      const bool kin = NN ? (l_k0 + b_row + NN_RSTEP * it < p.K) : (l_k0 + b_col < p.K);
+      const bool ok = ((b_okm >> it) & 1u) && kin;
+      cp_async16(Bs + stage * B_STAGE + b_soff + it * B_SSTEP, ok ? b_ptr + it * b_step : p.B, ok);
+    }
+  };
+  auto advance = [&]() {   // after the last part of a k-tile
+    if (l_it >= total_iters) return;
+    ++l_it;
+    if (++l_kt == ktiles) {
+      l_kt = 0;
+      l_tile += gridDim.x;
+      if (l_it < total_iters) refresh();
+    } else {
+      a_ptr += BK; b_ptr += b_adv; l_k0 += BK;
+    }
+  };
+
+  double acc[WM / 8][WN / 8][2];
+#pragma unroll
+  for (int i = 0; i < WM / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < WN / 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+#pragma unroll
+    for (int it = 0; it < NCH; ++it) load_part(it);
+    advance();
+    cp_async_commit();
+  }
+
+  // ---- compute cursor ----------------------------------------------------------------------------
+  long long c_tile = blockIdx.x;
+  int c_kt = 0;
+  for (long long it = 0; it < total_iters; ++it) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const int stage = (int)(it % STAGES);
+    const double* as = As + stage * A_STAGE + (wm * WM + g) * LDA + q;
+    const double* bs = Bs + stage * B_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      load_part(kk);   // refills the stage consumed at iteration it - 1, one part per butterfly step
+      double a[WM / 8], b[WN / 8];
+#pragma unroll
+      for (int i = 0; i < WM / 8; ++i) a[i] = as[i * 8 * LDA + kk * 4];
+#pragma unroll
+      for (int j = 0; j < WN / 8; ++j) {
+        if (!NN) b[j] = bs[(wn * WN + j * 8 + g) * LDB_NT + kk * 4 + q];
+        else     b[j] = bs[(kk * 4 + q) * LDB_NN + wn * WN + j * 8 + g];
+      }
+#pragma unroll
+      for (int i = 0; i < WM / 8; ++i)
+#pragma unroll
+        for (int j = 0; j < WN / 8; ++j) mma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    advance();
+    cp_async_commit();
+    if (++c_kt == ktiles) {
+      // epilogue of this tile (the next tile's loads are already in flight)
+      int bm0, bn0;
+      long long z;
+      tile_origin(c_tile, bm0, bn0, z);
+      double* C = p.C + z * p.strideC;
+      const bool vec_ok = ((p.ldc & 1) == 0) && ((((uintptr_t)C) & 15) == 0);
+#pragma unroll
+      for (int i = 0; i < WM / 8; ++i) {
+        const int row = bm0 + wm * WM + i * 8 + g;
+#pragma unroll
+        for (int j = 0; j < WN / 8; ++j) {
+          const int col = bn0 + wn * WN + j * 8 + 2 * q;
+          double* dst = C + (int64_t)row * p.ldc + col;
+          if (row < p.M) {
+            if (vec_ok && col + 1 < p.N) {
+              *reinterpret_cast<double2*>(dst) = make_double2(acc[i][j][0], acc[i][j][1]);
+            } else {
+              if (col < p.N) dst[0] = acc[i][j][0];
+              if (col + 1 < p.N) dst[1] = acc[i][j][1];
+            }
+          }
+          acc[i][j][0] = acc[i][j][1] = 0.0;
+        }
+      }
+      c_kt = 0;
+      c_tile += gridDim.x;
+    }
+  }
+  cp_async_wait<0>();
 }
 
 constexpr size_t smem_bytes(bool nn) {
@@ -254,33 +449,50 @@ static int run_dmma(cudaStream_t s, const AxisGeom& g, int dtype, const void* ta
                     void* out) {
   using namespace dmma;
   static bool attr_set = false;
+  static int sms = 148;
   if (!attr_set) {
     JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_bytes(false)));
     JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_bytes(true)));
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)pers::smem_bytes(false)));
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)pers::smem_bytes(true)));
+    int dev = 0;
+    JFX_CUDA_OK(cudaGetDevice(&dev));
+    JFX_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
+  static const bool force_pers = [] { const char* e = getenv("JFX_DMMA_PERSISTENT"); return e && e[0] == '1'; }();
   const int64_t inner = g.inner * (dtype == JFX_C128 ? 2 : 1);
   Params p{};
-  if (inner == 1) {
+  dim3 grid;
+  const bool nn = inner != 1;
+  if (!nn) {
     p.A = (const double*)in; p.B = (const double*)table; p.C = (double*)out;
     p.M = (int)g.outer; p.N = g.n_out; p.K = g.n_in;
     JFX_REQUIRE(g.outer < (1ll << 31), JFX_ERR_UNSUPPORTED, "outer extent too large");
     p.lda = g.n_in; p.ldb = g.n_in; p.ldc = g.n_out;
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, 1);
-    JFX_REQUIRE(grid.y <= 65535, JFX_ERR_UNSUPPORTED, "too many row tiles (%u)", grid.y);
-    dgemm_dmma<false><<<grid, THREADS, smem_bytes(false), s>>>(p);
+    grid = dim3((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, 1);
   } else {
     JFX_REQUIRE(inner < (1ll << 31), JFX_ERR_UNSUPPORTED, "inner extent too large");
     p.A = (const double*)table; p.B = (const double*)in; p.C = (double*)out;
     p.M = g.n_out; p.N = (int)inner; p.K = g.n_in;
     p.lda = g.n_in; p.ldb = inner; p.ldc = inner;
     p.strideA = 0; p.strideB = (int64_t)g.n_in * inner; p.strideC = (int64_t)g.n_out * inner;
-    JFX_REQUIRE(g.outer <= 65535, JFX_ERR_UNSUPPORTED, "outer extent %lld > 65535 on a non-last axis",
-                (long long)g.outer);
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, (unsigned)g.outer);
-    dgemm_dmma<true><<<grid, THREADS, smem_bytes(true), s>>>(p);
+    JFX_REQUIRE(g.outer < (1ll << 31), JFX_ERR_UNSUPPORTED, "outer extent too large");
+    grid = dim3((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, (unsigned)g.outer);
+  }
+  if (force_pers || grid.y > 65535 || grid.z > 65535) {
+    PParams pp{p, (int)grid.x, (int)grid.y, (int)grid.z};
+    const long long tiles = (long long)grid.x * grid.y * grid.z;
+    const unsigned ctas = (unsigned)(tiles < sms ? tiles : sms);
+    if (nn) dgemm_dmma_persistent<true><<<ctas, THREADS, pers::smem_bytes(true), s>>>(pp);
+    else dgemm_dmma_persistent<false><<<ctas, THREADS, pers::smem_bytes(false), s>>>(pp);
+  } else {
+    if (nn) dgemm_dmma<true><<<grid, THREADS, smem_bytes(true), s>>>(p);
+    else dgemm_dmma<false><<<grid, THREADS, smem_bytes(false), s>>>(p);
   }
   JFX_CUDA_OK(cudaGetLastError());
   return JFX_OK;
@@ -291,7 +503,7 @@ int launch_table_apply(cudaStream_t s, const AxisGeom& g, int dtype, const void*
   if (used_dmma) *used_dmma = 0;
   if (g.outer * g.inner * g.n_out == 0) return JFX_OK;
   if (table_apply_uses_dmma(g, dtype, table_complex) &&
-      (g.inner * (dtype == JFX_C128 ? 2 : 1) == 1 ? g.outer < (1ll << 31) : g.outer <= 65535)) {
+      g.outer < (1ll << 31)) {
     if (used_dmma) *used_dmma = 1;
     return run_dmma(s, g, dtype, table, in, out);
   }
@@ -331,6 +543,60 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) 
   if (sacc == 123.456) out[0] = sacc;
 }
 
+// same, but with the operand pattern of the GEMM inner loop: acc[i][j] += a[i] * b[j], 8 x 4 fragments;
+// MODE 1 additionally reloads the fragments from shared memory every step (LDS.64, conflict-free layout),
+// MODE 2 also puts a CTA barrier every 8 steps (one k-tile of BK = 32)
+template <int MODE>
+__global__ void __launch_bounds__(256) dmma_peak_kernel_frag(double* out, int iters) {
+  __shared__ double sm[2][128 * 20];
+  extern __shared__ __align__(16) double sm2[];
+  double d[8][4][2];
+  double a[8], b[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3, wm = warp >> 2, wn = warp & 3;
+  for (int i = threadIdx.x; i < 2 * 128 * 20; i += 256) (&sm[0][0])[i] = 1.0 + i * 1e-12;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = 1.0 + (threadIdx.x + i) * 1e-12;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { d[i][j][0] = threadIdx.x * 1e-9; d[i][j][1] = (i + j) * 1e-9; }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j] = 1.0 - (threadIdx.x + j) * 1e-12;
+  for (int it = 0; it < iters; ++it) {
+    if (MODE >= 1) {
+      const double* as = &sm[0][(wm * 64 + g) * 20 + q + (it & 3) * 4];
+      const double* bs = &sm[1][(wn * 32 + g) * 20 + q + (it & 3) * 4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = as[i * 8 * 20];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = bs[j * 8 * 20];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma::mma_884(d[i][j][0], d[i][j][1], a[i], b[j]);
+    if (MODE == 2 && (it & 7) == 7) __syncthreads();
+    if (MODE >= 3 && (it & 3) == 3) {
+      // one k-tile of BK = 16: 8 x 16-byte cp.async per thread (the GEMM's A + B stage), then wait + barrier
+      const double* src = out + 1024 + ((size_t)blockIdx.x * 8192 + ((it >> 2) & 3) * 2048 + threadIdx.x * 2) ;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        dmma::cp_async16(&sm2[(((it >> 2) % 3) * 4096) + c * 512 + threadIdx.x * 2], src + c * 512, true);
+      dmma::cp_async_commit();
+      dmma::cp_async_wait<1>();
+      __syncthreads();
+    }
+  }
+  double sacc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sacc += d[i][j][0] + d[i][j][1];
+  if (sacc == 123.456) out[0] = sacc;
+}
+
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
   double d[16];
 #pragma unroll
@@ -347,21 +613,34 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
 }
 
 template <typename K>
-static int time_peak(cudaStream_t s, K kernel, int iters, double flops_per_thread_iter, double* tflops) {
+static int time_peak(cudaStream_t s, K kernel, int iters, double flops_per_thread_iter, double* tflops, int dyn_smem = 0) {
   double* dummy = nullptr;
-  JFX_CUDA_OK(cudaMalloc(&dummy, 8));
+  JFX_CUDA_OK(cudaMalloc(&dummy, (size_t)(1024 + 148 * 8 * 8192 + 8192) * 8));
+  if (dyn_smem) JFX_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
   cudaEvent_t e0, e1;
   JFX_CUDA_OK(cudaEventCreate(&e0));
   JFX_CUDA_OK(cudaEventCreate(&e1));
-  const int blocks = 148 * 8, threads = 256;
-  kernel<<<blocks, threads, 0, s>>>(dummy, iters);  // warm-up
-  JFX_CUDA_OK(cudaEventRecord(e0, s));
-  kernel<<<blocks, threads, 0, s>>>(dummy, iters);
-  JFX_CUDA_OK(cudaEventRecord(e1, s));
-  JFX_CUDA_OK(cudaEventSynchronize(e1));
-  float ms = 0;
-  JFX_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
-  *tflops = flops_per_thread_iter * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+  // best over 1, 2 and 8 resident CTAs per SM (8 warps each): the pipes saturate at 2 warps per SM
+  // sub-partition, and grids that are not a whole number of waves lose throughput to the tail
+  const char* e_ = getenv("JFX_CAL_BLOCKS_PER_SM");
+  const int fixed = e_ ? atoi(e_) : 0;
+  const int tries[3] = {1, 2, 8};
+  double best = 0;
+  for (int t = 0; t < 3; ++t) {
+    const int per_sm = fixed ? fixed : tries[t];
+    const int blocks = 148 * per_sm, threads = 256;
+    kernel<<<blocks, threads, dyn_smem, s>>>(dummy, iters);  // warm-up
+    JFX_CUDA_OK(cudaEventRecord(e0, s));
+    kernel<<<blocks, threads, dyn_smem, s>>>(dummy, iters);
+    JFX_CUDA_OK(cudaEventRecord(e1, s));
+    JFX_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0;
+    JFX_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = flops_per_thread_iter * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+    if (fixed) break;
+  }
+  *tflops = best;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(dummy);
@@ -370,6 +649,11 @@ static int time_peak(cudaStream_t s, K kernel, int iters, double flops_per_threa
 
 int calibrate_dmma(cudaStream_t s, int iters, double* tflops) {
   // per warp-instruction 8*8*4 FMAs = 512 flops -> 16 flops per thread per mma; 16 mma per iter
+  const char* e_ = getenv("JFX_CAL_FRAG");
+  if (e_ && e_[0] == '1') return time_peak(s, dmma_peak_kernel_frag<0>, iters, 16.0 * 32.0, tflops);
+  if (e_ && e_[0] == '2') return time_peak(s, dmma_peak_kernel_frag<1>, iters, 16.0 * 32.0, tflops);
+  if (e_ && e_[0] == '3') return time_peak(s, dmma_peak_kernel_frag<2>, iters, 16.0 * 32.0, tflops);
+  if (e_ && e_[0] == '4') return time_peak(s, dmma_peak_kernel_frag<3>, iters, 16.0 * 32.0, tflops, 3 * 4096 * 8);
   return time_peak(s, dmma_peak_kernel, iters, 16.0 * 16.0, tflops);
 }
 int calibrate_dfma(cudaStream_t s, int iters, double* tflops) {
