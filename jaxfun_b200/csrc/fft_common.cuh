@@ -115,4 +115,12 @@ enum { K_CHEB_BWD = 0, K_CHEB_FWD = 1, K_FOUR_BWD = 2, K_FOUR_FWD = 3 };
 // configuration is outside its envelope (caller falls back to the staged kernel), < 0 on error
 int launch_fast_axis_v2(cudaStream_t s, const FftArgs& a, int n, bool dbl);
 
+int make_fft_args(const AxisGeom& g, int dtype, const FastParams& p, const FastTables* t, const void* in, void* out,
+                  FftArgs* out_args, bool* empty);
+
+// plane-fused two-axis pass (kernels_fft2_pair.cu)
+size_t fast_pair_counter_bytes(long long planes);
+int launch_fast_pair(cudaStream_t s, FftArgs a, FftArgs b, int n, bool dbl, long long planes, void* ring_buf,
+                     size_t ring_bytes, void* counters, bool query);
+
 }  // namespace jfx

@@ -43,6 +43,8 @@ struct jfx_plan {
   size_t buf_bytes = 0;  // one ping-pong buffer
   size_t ws_bytes = 0;
   int slabs = 1;         // > 1: the last two passes run L2-blocked over slabs of the leading axis
+  bool pair = false;     // the last two passes run as ONE plane-fused launch (kernels_fft2_pair.cu)
+  size_t pair_counter_off = 0, pair_ring_off = 0, pair_ring_bytes = 0;
   double flops = 0, bytes = 0;
   // host-pointer path (lazy, guarded)
   std::mutex host_mu;
@@ -189,6 +191,38 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
       pl->slabs = (int)std::min<int64_t>(want, L);
     }
   }
+  // plane-fused pair (preferred over slabs): both passes fast, same length, no padding
+  // opt-in (JFX_PAIR=1, read at plan creation): measured on par with / slightly slower than two plain passes
+  // at 256^3 — the single passes are latency-bound, not DRAM-bound, so saving the HBM round trip of the
+  // intermediate does not pay yet
+  const char* pair_env = getenv("JFX_PAIR");
+  const bool pair_on = pair_env && pair_env[0] == '1';
+  if (pair_on && npass >= 2 && pl->slabs == 1) {
+    const Pass& A = pl->passes[npass - 2];
+    const Pass& B = pl->passes[npass - 1];
+    if (A.fast && B.fast && A.axis >= 1 && B.axis == d->ndim - 1 && A.axis == d->ndim - 2 && pl->shape_out[0] >= 8) {
+      FftArgs fa, fb;
+      bool ea, eb;
+      // dummy non-null pointers: only the geometry matters for the query
+      if (make_fft_args(A.geom, d->dtype, A.fp, A.ft, (void*)16, (void*)16, &fa, &ea) == JFX_OK &&
+          make_fft_args(B.geom, d->dtype, B.fp, B.ft, (void*)16, (void*)16, &fb, &eb) == JFX_OK && !ea && !eb) {
+        // ring: up to 64 MB of the intermediate (L2-resident), counters after it
+        const size_t inter = (size_t)A.geom.outer * A.geom.n_out * A.geom.inner * es;
+        const size_t plane_bytes = inter / (size_t)pl->shape_out[0];
+        size_t ring_bytes = std::min<size_t>(inter, std::max<size_t>(32u << 20, 64 * plane_bytes));
+        ring_bytes = ring_bytes / plane_bytes * plane_bytes;
+        if (launch_fast_pair(nullptr, fa, fb, A.fp.n_quad, dtype_is_double(d->dtype), pl->shape_out[0], (void*)16,
+                             ring_bytes, (void*)16, /*query=*/true) == 1 && A.fp.n_quad == B.fp.n_quad) {
+          pl->pair = true;
+          pl->pair_ring_bytes = ring_bytes;
+          // workspace layout: [ping-pong buffers as before][ring][counters]
+          pl->pair_ring_off = align_up(pl->ws_bytes, 256);
+          pl->pair_counter_off = pl->pair_ring_off + align_up(ring_bytes, 256);
+          pl->ws_bytes = pl->pair_counter_off + align_up(fast_pair_counter_bytes(pl->shape_out[0]), 256);
+        }
+      }
+    }
+  }
   return JFX_OK;
 }
 
@@ -226,12 +260,28 @@ static int execute_plan(const jfx_plan* pl, cudaStream_t s, const void* in, void
   char* w1 = w0 + pl->buf_bytes;
   const void* src = in;
   size_t first_pair = np;   // index of pass A when the last two passes run slab-blocked
-  if (pl->slabs > 1) first_pair = np - 2;
+  if (pl->slabs > 1 || pl->pair) first_pair = np - 2;
   for (size_t i = 0; i < first_pair; ++i) {
     void* dst = (i + 1 == np) ? out : (void*)((i & 1) ? w1 : w0);
     int rc = run_pass(s, pl->passes[i], pl->desc.dtype, src, dst);
     if (rc != JFX_OK) return rc;
     src = dst;
+  }
+  if (pl->pair) {
+    const Pass& A = pl->passes[np - 2];
+    const Pass& B = pl->passes[np - 1];
+    FftArgs fa, fb;
+    bool ea, eb;
+    char* ring = w0 + pl->pair_ring_off;
+    int rc = make_fft_args(A.geom, pl->desc.dtype, A.fp, A.ft, src, ring, &fa, &ea);
+    if (rc != JFX_OK) return rc;
+    rc = make_fft_args(B.geom, pl->desc.dtype, B.fp, B.ft, ring, out, &fb, &eb);
+    if (rc != JFX_OK) return rc;
+    rc = launch_fast_pair(s, fa, fb, A.fp.n_quad, dtype_is_double(pl->desc.dtype), pl->shape_out[0], ring,
+                          pl->pair_ring_bytes, w0 + pl->pair_counter_off, false);
+    if (rc < 0) return rc;
+    JFX_REQUIRE(rc == 1, JFX_ERR_UNSUPPORTED, "plane-fused pass refused a configuration it accepted at plan time");
+    return JFX_OK;
   }
   if (first_pair < np) {
     const Pass& A = pl->passes[np - 2];
@@ -474,6 +524,7 @@ int jfx_plan_work(const jfx_plan* plan, double* flops, double* bytes) {
 int jfx_plan_launches(const jfx_plan* plan) {
   if (!plan) return JFX_ERR_INVALID;
   if (plan->passes.empty()) return 0;
+  if (plan->pair) return (int)plan->passes.size() - 1;
   if (plan->slabs > 1) {
     const int64_t L = plan->shape_out[0], per = (L + plan->slabs - 1) / plan->slabs;
     return (int)plan->passes.size() - 2 + 2 * (int)((L + per - 1) / per);

@@ -411,12 +411,16 @@ static int launch_t(cudaStream_t s, const FftArgs& a, int n, bool strided) {
   return JFX_ERR_UNSUPPORTED;
 }
 
-int launch_fast_axis(cudaStream_t s, const AxisGeom& g, int dtype, const FastParams& p, const FastTables* t,
-                     const void* in, void* out) {
+// Arguments of one axis pass (shared by the single-pass kernels and the plane-fused pair kernel).
+// *empty is set when the pass has no lines.
+int make_fft_args(const AxisGeom& g, int dtype, const FastParams& p, const FastTables* t, const void* in, void* out,
+                  FftArgs* out_args, bool* empty) {
   JFX_REQUIRE(t != nullptr, JFX_ERR_INVALID, "missing fast tables");
   const bool cplx = dtype_is_complex(dtype);
   const bool cheb = p.kind <= FAST_CHEB_SCALAR;
-  FftArgs a{};
+  FftArgs& a = *out_args;
+  a = FftArgs{};
+  *empty = false;
   a.in = in; a.out = out;
   a.tw = t->d_tw; a.half = t->d_half; a.pre = t->d_pre;
   a.n_in = g.n_in; a.n_out = g.n_out; a.n_modes = p.n_modes; a.kind = p.kind;
@@ -429,7 +433,7 @@ int launch_fast_axis(cudaStream_t s, const AxisGeom& g, int dtype, const FastPar
     case FAST_FOURIER_SCALAR: a.scale = (1.0 / n) * 2.0 * PI / p.domain_factor; break;
     default: a.scale = 1.0;
   }
-  if (g.outer * g.inner == 0) return JFX_OK;
+  if (g.outer * g.inner == 0) { *empty = true; return JFX_OK; }
   if (cplx) {
     a.inner = g.inner; a.lines = g.outer * g.inner; a.real_pair = 0;
   } else {
@@ -443,6 +447,15 @@ int launch_fast_axis(cudaStream_t s, const AxisGeom& g, int dtype, const FastPar
       return JFX_ERR_UNSUPPORTED;
     }
   }
+  return JFX_OK;
+}
+
+int launch_fast_axis(cudaStream_t s, const AxisGeom& g, int dtype, const FastParams& p, const FastTables* t,
+                     const void* in, void* out) {
+  FftArgs a;
+  bool empty;
+  { const int rc = make_fft_args(g, dtype, p, t, in, out, &a, &empty); if (rc != JFX_OK) return rc; }
+  if (empty) return JFX_OK;
   // second-generation kernel first (direct global<->register passes); the staged kernel below is the
   // fallback for configurations outside its envelope and, with JFX_FFT_V1=1, an A/B switch for tests
   static const bool force_v1 = [] { const char* e = getenv("JFX_FFT_V1"); return e && e[0] == '1'; }();

@@ -149,9 +149,15 @@ class NonlinearTerm:
         if u is None:
             u, coords = field(space)
         self.compiled = CompiledExpression(expr, u, coords)
+        self._ctor = dict(expr=expr, N=N, testspace=testspace, u=u, coords=coords)
         self.final = {"forward": L.OP_FORWARD, "scalar_product": L.OP_SCALAR_PRODUCT}[final]
         self.N = N
         self._cache = {}
+
+    def with_final(self, final: str) -> "NonlinearTerm":
+        """The same term with another final transform ('forward' | 'scalar_product'), base.py:230-248."""
+        c = self._ctor
+        return NonlinearTerm(self.space, c["expr"], final=final, N=c["N"], testspace=c["testspace"], u=c["u"], coords=c["coords"])
 
     def _spaces(self, space):
         return list(space.basespaces) if hasattr(space, "basespaces") else [space]

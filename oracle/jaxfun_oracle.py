@@ -826,3 +826,59 @@ def rk4_step(u_hat, dt, rhs):
     k3 = rhs(u_hat + 0.5 * dt * k2)
     k4 = rhs(u_hat + dt * k3)
     return u_hat + (dt / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+
+
+def backward_euler_step(u_hat, dt, M, Lw, Nsp, forcing=None):
+    """backward_euler.py:29-39 with diagonal mass M and weak-form linear operator Lw; Nsp = scalar-product
+    nonlinear term (base.py:238-248)."""
+    rhs = M * u_hat
+    if forcing is not None:
+        rhs = rhs + dt * forcing
+    if Nsp is not None:
+        rhs = rhs + dt * Nsp(u_hat)
+    return rhs / (M - dt * Lw)
+
+
+def imex_rk_step(u_hat, dt, tableau, M, Lw, Nsp, forcing=None):
+    """imex_rk.py:54-159 for diagonal operators.  `tableau` has .explicit/.implicit with A, b, c and the
+    stiff-accuracy properties (tableau.py:43-127)."""
+    a_e, a_i = tableau.explicit.A, tableau.implicit.A
+    b_e, b_i, c_i = tableau.explicit.b, tableau.implicit.b, tableau.implicit.c
+    s = tableau.stages
+    full = tableau.is_stiffly_accurate
+    impl_only = (not full) and tableau.implicit_is_stiffly_accurate
+    m_u = M * u_hat
+    stages, nls, lins = [], [], []
+    for i in range(s):
+        rhs = m_u
+        for j in range(i):
+            if a_e[i][j] != 0.0:
+                rhs = rhs + dt * a_e[i][j] * nls[j]
+            if a_i[i][j] != 0.0:
+                rhs = rhs + dt * a_i[i][j] * lins[j]
+        if forcing is not None and c_i[i] != 0.0:
+            rhs = rhs + dt * c_i[i] * forcing
+        a_ii = a_i[i][i]
+        st = rhs / M if a_ii == 0.0 else rhs / (M - dt * a_ii * Lw)
+        stages.append(st)
+        last = i == s - 1
+        nls.append(None if (last and full) else Nsp(st))
+        lins.append(None if (last and (full or impl_only)) else Lw * st)
+    if full:
+        return stages[-1]
+    if impl_only:
+        rhs = M * stages[-1]
+        for j in range(s):
+            w = b_e[j] - a_e[-1][j]
+            if w != 0.0:
+                rhs = rhs + dt * w * nls[j]
+        return rhs / M
+    rhs = m_u
+    for j in range(s):
+        if b_e[j] != 0.0:
+            rhs = rhs + dt * b_e[j] * nls[j]
+        if b_i[j] != 0.0:
+            rhs = rhs + dt * b_i[j] * lins[j]
+    if forcing is not None:
+        rhs = rhs + dt * forcing
+    return rhs / M

@@ -123,3 +123,39 @@ def test_batched_1d_config_c3_properties(cuda):
     assert abs(lhs - rhs) < 1e-12 * rhs
     back = F.forward(u)
     assert float((back - c).abs().max()) < 1e-12 * float(c.abs().max())
+
+
+@pytest.mark.parametrize("names,N", [
+    (("Chebyshev", "Chebyshev", "Chebyshev"), (16, 128, 128)),
+    (("Chebyshev", "Chebyshev", "Chebyshev"), (8, 256, 256)),
+    (("Fourier", "Fourier", "Fourier"), (16, 128, 128)),
+    (("Legendre", "Chebyshev", "Chebyshev"), (24, 128, 128)),
+    (("Fourier", "Chebyshev", "Chebyshev"), (8, 128, 128)),
+])
+def test_plane_fused_pair_vs_oracle(cuda, names, N, monkeypatch):
+    """Shapes whose last two axes run as ONE plane-fused launch (kernels_fft2_pair.cu: ticketed A/B tiles,
+    ring-buffered intermediate; opt-in with JFX_PAIR=1 at plan creation) against the oracle, all three
+    directions."""
+    monkeypatch.setenv("JFX_PAIR", "1")
+    import jaxfun_oracle as O
+    import jaxfun_b200 as jf
+    rng = np.random.default_rng(sum(N))
+    To = O.TensorProductSpace(*[getattr(O, n)(Ni) for n, Ni in zip(names, N)])
+    Tp = jf.TensorProduct(*[getattr(jf, n)(Ni) for n, Ni in zip(names, N)])
+    cplx = "Fourier" in names
+    c = rng.standard_normal(N) + (1j * rng.standard_normal(N) if cplx else 0)
+    u_ref = To.backward(c)
+    cd = torch.from_numpy(c).to(cuda)
+    plan = Tp._plan(2, cd)   # OP_BACKWARD
+    assert plan.launches == 2, "expected axis-0 pass + one plane-fused launch"
+    u = Tp.backward(cd)
+    scale = np.abs(u_ref).max()
+    assert np.abs(u.cpu().numpy() - u_ref).max() < 1e-12 * scale
+    ud = torch.from_numpy(u_ref).to(cuda)
+    f_ref, s_ref = To.forward(u_ref), To.scalar_product(u_ref)
+    assert np.abs(Tp.forward(ud).cpu().numpy() - f_ref).max() < 1e-12 * np.abs(f_ref).max()
+    assert np.abs(Tp.scalar_product(ud).cpu().numpy() - s_ref).max() < 1e-12 * np.abs(s_ref).max()
+    # repeated execution reuses ring + counters
+    for _ in range(3):
+        u2 = Tp.backward(cd)
+    assert torch.equal(u2, u)
