@@ -23,7 +23,16 @@ template <int N, int LAY> struct Cta {
 template <typename T> __device__ __forceinline__ Cpx<T> ldg(const Cpx<T>* p) { return *p; }
 
 // ---- per-thread view of one line ----------------------------------------------------------------
-template <typename T, int LAY, bool CG> struct LineIO {
+enum { SRC_GLOBAL = 0, SRC_GLOBAL_CG = 1, SRC_STAGED = 2 };
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// SRC: where pass 0 reads from — global memory, global memory through L2 only (ld.global.cg), or a
+// shared-memory staging tile that a bulk async copy filled (kernels_fft2_stream.cu); SLPB = lines per
+// staging row of a strided tile ([n][SLPB] layout), unused otherwise
+template <typename T, int LAY, int SRC, int SLPB> struct LineIO {
+  const Cpx<T>* __restrict__ st;    // SRC_STAGED: element 0 of this line in the staging tile
+  const T* __restrict__ sr0;        // SRC_STAGED, REALPAIR: the two staged real rows
+  const T* __restrict__ sr1;
   const Cpx<T>* __restrict__ cin;   // CONTIG / STRIDED: element 0 of the line
   Cpx<T>* __restrict__ cout;
   const T* __restrict__ r0i;        // REALPAIR: the two real rows packed as (re, im)
@@ -34,7 +43,12 @@ template <typename T, int LAY, bool CG> struct LineIO {
   bool valid, valid1;               // line exists / second real row exists
 
   __device__ __forceinline__ Cpx<T> load(int idx) const {
-    if (CG) {
+    if (SRC == SRC_STAGED) {
+      if (LAY == LAY_REALPAIR) return Cpx<T>{sr0[idx], sr1[idx]};
+      if (LAY == LAY_STRIDED) return st[idx * SLPB];
+      return st[idx];
+    }
+    if (SRC == SRC_GLOBAL_CG) {
       if (LAY == LAY_REALPAIR) return Cpx<T>{__ldcg(r0i + idx), __ldcg(r1i + idx)};
       const Cpx<T>* p = (LAY == LAY_STRIDED) ? cin + (long long)idx * is : cin + idx;
       if (sizeof(T) == 8) {
@@ -63,9 +77,11 @@ template <typename T, int LAY, bool CG> struct LineIO {
 
 // One tile (LPB lines) of an axis pass.  `tile` is the global tile index over all lines of the array,
 // S the CTA's exchange buffer (LPB * Geo<N>::PITCH elements).  CG: read the input with ld.global.cg
-// (L2 only) — for data produced earlier in the SAME launch by other SMs (fft2_pair.cu).
-template <typename T, int N, int KIND, int LAY, bool GEN, bool CG = false>
-__device__ __forceinline__ void fft2_tile(const FftArgs& a, long long tile, Cpx<T>* __restrict__ S) {
+// (L2 only) — for data produced earlier in the SAME launch by other SMs (fft2_pair.cu).  `after_load`
+// runs once all of the tile's input has been consumed into registers (before any other barrier).
+template <typename T, int N, int KIND, int LAY, bool GEN, int SRC = SRC_GLOBAL, typename Hook = NoHook>
+__device__ __forceinline__ void fft2_tile(const FftArgs& a, long long tile, Cpx<T>* __restrict__ S,
+                                          const void* stage = nullptr, Hook after_load = Hook()) {
   constexpr int THREADS = Cta<N, LAY>::THREADS;
   using P = Plan<N>;
   constexpr int R0 = P::R0, R1 = P::R1, R2 = P::R2;
@@ -90,7 +106,7 @@ __device__ __forceinline__ void fft2_tile(const FftArgs& a, long long tile, Cpx<
   auto sync = [&]() { if (WARP_SYNC) __syncwarp(); else __syncthreads(); };
 
   // ---- line addressing -----------------------------------------------------------------------
-  LineIO<T, LAY, CG> io;
+  LineIO<T, LAY, SRC, LPB> io;
   {
     long long l = tile * LPB + ll;
     io.valid = true; io.valid1 = true;
@@ -113,6 +129,17 @@ __device__ __forceinline__ void fft2_tile(const FftArgs& a, long long tile, Cpx<
     } else {
       io.cin = reinterpret_cast<const Cpx<T>*>(a.in) + (size_t)l * a.n_in;
       io.cout = reinterpret_cast<Cpx<T>*>(a.out) + (size_t)l * a.n_out;
+    }
+  }
+  if (SRC == SRC_STAGED) {
+    const Cpx<T>* sg = reinterpret_cast<const Cpx<T>*>(stage);
+    if (LAY == LAY_REALPAIR) {
+      io.sr0 = reinterpret_cast<const T*>(stage) + (size_t)(2 * ll) * N;
+      io.sr1 = io.sr0 + N;
+    } else if (LAY == LAY_STRIDED) {
+      io.st = sg + ll;                  // [n][LPB]
+    } else {
+      io.st = sg + (size_t)ll * N;      // [LPB][n]
     }
   }
   const Cpx<T>* __restrict__ tw = reinterpret_cast<const Cpx<T>*>(a.tw);
@@ -170,6 +197,7 @@ __device__ __forceinline__ void fft2_tile(const FftArgs& a, long long tile, Cpx<
       }
     }
   }
+  after_load();
   fft_core<T, N, WARP_SYNC>(v, Sl, j, tw);
   {
     constexpr int R = RL, NS = NSL, BPT = E / R;

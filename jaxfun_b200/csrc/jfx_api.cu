@@ -534,7 +534,10 @@ int jfx_plan_launches(const jfx_plan* plan) {
 
 int jfx_execute(const jfx_plan* plan, void* stream, const void* in, void* out, void* workspace) {
   using namespace jfx;
-  JFX_REQUIRE(plan && in && out, JFX_ERR_INVALID, "null argument");
+  JFX_REQUIRE(plan, JFX_ERR_INVALID, "null argument");
+  // empty arrays are valid requests (and have null data pointers in most array libraries)
+  if (prod(plan->shape_in, 0, plan->ndim) == 0 || prod(plan->shape_out, 0, plan->ndim) == 0) return JFX_OK;
+  JFX_REQUIRE(in && out, JFX_ERR_INVALID, "null argument");
   return execute_plan(plan, (cudaStream_t)stream, in, out, workspace);
 }
 

@@ -80,7 +80,7 @@ static int run_generic(cudaStream_t s, const AxisGeom& g, const void* table, con
 namespace dmma {
 
 constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int THREADS = 256;
 constexpr int WM = 64, WN = 32;          // warp tile
 constexpr int LDA = BK + 4;              // As[m][k]   pitch (doubles), == 4 mod 16 -> conflict free
@@ -115,8 +115,13 @@ struct Params {
   int64_t strideA, strideB, strideC;  // per batch (blockIdx.z)
 };
 
-template <bool NN>
-__global__ void __launch_bounds__(THREADS, 1) dgemm_dmma(const Params p) {
+// WM x WN = warp tile; the CTA tile is always 128 x 128, so THREADS = (128/WM) * (128/WN) * 32:
+//   64 x 32 -> 8 warps (2 per SM sub-partition, 64 accumulators per thread),
+//   32 x 32 -> 16 warps (4 per sub-partition: more latency tolerance, 0.5 instead of 0.375 LDS per DMMA)
+template <bool NN, int WM, int WN>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) dgemm_dmma(const Params p) {
+  constexpr int THREADS = (BM / WM) * (BN / WN) * 32;
+  constexpr int WARPS_N = BN / WN;
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + STAGES * A_STAGE;
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_dmma(const Params p) {
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   const int g = lane >> 2, q = lane & 3;
 
   // blockIdx.x walks N tiles fastest so CTAs sharing an A panel run together (L2 reuse)
@@ -142,24 +147,27 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_dmma(const Params p) {
   // pointer bump and the k-bound test is left inside the loop; part `kk` of the copies is issued in
   // front of butterfly step kk so the DMMA stream of a warp is never interrupted by a long burst of
   // address arithmetic right after the barrier (which is when the other warp of the SMSP does the same).
-  constexpr int NCH = (BM * BK / 2) / THREADS;           // chunks per thread and operand (4)
-  static_assert(NCH == BK / 4, "one A and one B chunk per butterfly step");
-  const int a_row = tid >> 3, a_kc = (tid & 7) * 2;       // A / NT-B: 8 chunks per row, +32 rows per chunk
-  const int b_row = NN ? (tid >> 6) : a_row;              // NN-B: 64 chunks per row, +4 rows per chunk
+  constexpr int NCH = (BM * BK / 2) / THREADS;           // chunks per thread and operand (4 or 2)
+  constexpr int KSTEPS = BK / 4;                         // butterfly steps per k-tile
+  static_assert(KSTEPS % NCH == 0, "chunks are spread evenly over the butterfly steps");
+  constexpr int RSTEP = THREADS / 8;                     // A / NT-B: 8 chunks per row -> rows between a thread's chunks
+  constexpr int NN_RSTEP = THREADS / 64;                 // NN-B: 64 chunks per row
+  const int a_row = tid >> 3, a_kc = (tid & 7) * 2;
+  const int b_row = NN ? (tid >> 6) : a_row;
   const int b_col = NN ? (tid & 63) * 2 : a_kc;
   const double* a_ptr = A + (int64_t)(bm0 + a_row) * p.lda + a_kc;
   const double* b_ptr = NN ? B + (int64_t)b_row * p.ldb + bn0 + b_col : B + (int64_t)(bn0 + b_row) * p.ldb + b_col;
-  const int64_t a_step = 32 * p.lda;                     // between a thread's chunks
-  const int64_t b_step = NN ? 4 * p.ldb : 32 * p.ldb;
+  const int64_t a_step = (int64_t)RSTEP * p.lda;         // between a thread's chunks
+  const int64_t b_step = NN ? (int64_t)NN_RSTEP * p.ldb : (int64_t)RSTEP * p.ldb;
   const int64_t b_adv = NN ? (int64_t)BK * p.ldb : BK;   // per k-tile (A advances by BK)
   const int a_soff = a_row * LDA + a_kc;
   const int b_soff = NN ? b_row * LDB_NN + b_col : b_row * LDB_NT + b_col;
-  constexpr int A_SSTEP = 32 * LDA, B_SSTEP = NN ? 4 * LDB_NN : 32 * LDB_NT;
+  constexpr int A_SSTEP = RSTEP * LDA, B_SSTEP = NN ? NN_RSTEP * LDB_NN : RSTEP * LDB_NT;
   bool a_ok[NCH], b_ok[NCH];
 #pragma unroll
   for (int it = 0; it < NCH; ++it) {
-    a_ok[it] = bm0 + a_row + 32 * it < p.M;
-    b_ok[it] = NN ? (bn0 + b_col < p.N) : (bn0 + b_row + 32 * it < p.N);
+    a_ok[it] = bm0 + a_row + RSTEP * it < p.M;
+    b_ok[it] = NN ? (bn0 + b_col < p.N) : (bn0 + b_row + RSTEP * it < p.N);
   }
   int l_k0 = 0;   // k origin of the next tile to load
 
@@ -170,7 +178,7 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_dmma(const Params p) {
       cp_async16(As + stage * A_STAGE + a_soff + it * A_SSTEP, ok ? a_ptr + it * a_step : A, ok);
     }
     {
-      const bool kin = NN ? (l_k0 + b_row + 4 * it < p.K) : (l_k0 + b_col < p.K);
+      const bool kin = NN ? (l_k0 + b_row + NN_RSTEP * it < p.K) : (l_k0 + b_col < p.K);
       const bool ok = b_ok[it] && kin;
       cp_async16(Bs + stage * B_STAGE + b_soff + it * B_SSTEP, ok ? b_ptr + it * b_step : B, ok);
     }
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_dmma(const Params p) {
     const double* bs = Bs + (kt % STAGES) * B_STAGE;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; ++kk) {
-      if (more) load_part(lstage, kk);
+      if (more && kk % (KSTEPS / NCH) == 0) load_part(lstage, kk / (KSTEPS / NCH));
       double a[WM / 8], b[WN / 8];
 #pragma unroll
       for (int i = 0; i < WM / 8; ++i) a[i] = as[i * 8 * LDA + kk * 4];
@@ -451,9 +459,13 @@ static int run_dmma(cudaStream_t s, const AxisGeom& g, int dtype, const void* ta
   static bool attr_set = false;
   static int sms = 148;
   if (!attr_set) {
-    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma<false, 64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_bytes(false)));
-    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma<true, 64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes(true)));
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma<false, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes(false)));
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma<true, 32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_bytes(true)));
     JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)pers::smem_bytes(false)));
@@ -491,8 +503,14 @@ static int run_dmma(cudaStream_t s, const AxisGeom& g, int dtype, const void* ta
     if (nn) dgemm_dmma_persistent<true><<<ctas, THREADS, pers::smem_bytes(true), s>>>(pp);
     else dgemm_dmma_persistent<false><<<ctas, THREADS, pers::smem_bytes(false), s>>>(pp);
   } else {
-    if (nn) dgemm_dmma<true><<<grid, THREADS, smem_bytes(true), s>>>(p);
-    else dgemm_dmma<false><<<grid, THREADS, smem_bytes(false), s>>>(p);
+    static const bool w16 = [] { const char* e = getenv("JFX_DMMA_WARPS"); return e && atoi(e) == 16; }();
+    if (w16) {
+      if (nn) dgemm_dmma<true, 32, 32><<<grid, 512, smem_bytes(true), s>>>(p);
+      else dgemm_dmma<false, 32, 32><<<grid, 512, smem_bytes(false), s>>>(p);
+    } else {
+      if (nn) dgemm_dmma<true, 64, 32><<<grid, THREADS, smem_bytes(true), s>>>(p);
+      else dgemm_dmma<false, 64, 32><<<grid, THREADS, smem_bytes(false), s>>>(p);
+    }
   }
   JFX_CUDA_OK(cudaGetLastError());
   return JFX_OK;

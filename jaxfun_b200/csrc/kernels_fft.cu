@@ -459,6 +459,14 @@ int launch_fast_axis(cudaStream_t s, const AxisGeom& g, int dtype, const FastPar
   // second-generation kernel first (direct global<->register passes); the staged kernel below is the
   // fallback for configurations outside its envelope and, with JFX_FFT_V1=1, an A/B switch for tests
   static const bool force_v1 = [] { const char* e = getenv("JFX_FFT_V1"); return e && e[0] == '1'; }();
+  // streaming variant (persistent CTAs, bulk-async prefetch of the next tile) for full, unpadded tiles.
+  // Opt-in (JFX_FFT_STREAM=1, read per call): measured 2x slower on strided axes (n bulk copies of 128 B
+  // per tile) and within +-7 % of the plain kernel on contiguous axes — see DESIGN.md.
+  const char* stream_env = getenv("JFX_FFT_STREAM");
+  if (!force_v1 && stream_env && stream_env[0] == '1') {
+    const int rc = launch_fast_axis_stream(s, a, p.n_quad, dtype_is_double(dtype));
+    if (rc != 0) return rc < 0 ? rc : JFX_OK;
+  }
   if (!force_v1) {
     const int rc = launch_fast_axis_v2(s, a, p.n_quad, dtype_is_double(dtype));
     if (rc != 0) return rc < 0 ? rc : JFX_OK;

@@ -78,7 +78,7 @@ fft2_pair_kernel(const __grid_constant__ PairArgs pa) {
       __syncthreads();
       FftArgs b = pa.b;
       b.in = reinterpret_cast<const Cpx<T>*>(b.in) + ((long long)slot - (long long)plane) * pa.slot_elems_a_out;
-      fft2_tile<T, N, KIND, LAYB, false, true>(b, (long long)plane * blk_b + t, S);
+      fft2_tile<T, N, KIND, LAYB, false, SRC_GLOBAL_CG>(b, (long long)plane * blk_b + t, S);
       __syncthreads();
       if (threadIdx.x == 0) atomicAdd(pa.consumed + plane, 1u);
     }
