@@ -168,7 +168,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n, gpus):
@@ -460,12 +460,30 @@ def run_ours(args):
                                 "note": "NumPy/SciPy oracle of the reference algorithm (threaded BLAS + scipy.fft workers), "
                                         "not XLA: jax is not installable in this image"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if multi:
         dist.destroy_process_group()
 
 
+def emit(line: dict) -> None:
+    """The ONE JSON line, on the real stdout (see _quiet_stdout)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _quiet_stdout() -> None:
+    """Libraries (NCCL's version banner, NCCL_DEBUG output, torch warnings) write to fd 1 from C code; send
+    everything that is not the result line to stderr so that stdout carries exactly one JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 if __name__ == "__main__":
+    _quiet_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)

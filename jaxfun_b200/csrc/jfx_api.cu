@@ -369,7 +369,12 @@ static int try_fuse_rows(const jfx_nonlinear_desc* d, jfx_nonlinear* nl) {
   fa_.rows = 1;   // placeholder for the query
   fa_.n_coeff = (int)n_coeff;
   fa_.n_out = fa.n_modes;
+  {
+    int rc = validate_program(nl->prog, nl->statics);
+    if (rc != JFX_OK) return rc;
+  }
   fa_.depth = program_depth(nl->prog);
+  if (!program_to_poly(nl->prog, &fa_.poly)) fa_.poly.n_terms = 0;
   size_t scratch_bytes = 0;
   if (launch_fused_rows(nullptr, fd->dtype, n, fa_, &scratch_bytes) != 1) return JFX_OK;
   nl->scratch_bytes = align_up(scratch_bytes, 256);

@@ -93,6 +93,24 @@ int launch_slab_unpack(cudaStream_t s, const void* in, void* out, const int64_t*
                        int ndim, int concat_axis, int parts, int dtype);
 int launch_axpby_diag(cudaStream_t s, int n_terms, const void* const* coeff, const double* alpha,
                       const void* const* x, void* out, int64_t n, int dtype, int coeff_is_complex);
+// Polynomial normal form of a pointwise program:  sum_t coeff_t * prod_f x_f,  x_f = leaf or conj(leaf).
+// Every nonlinear term of the reference's examples and tests has this form (u u_x, (u+u_x)^2,
+// 6u(u_x^2+u_y^2)+3u^2(u_xx+u_yy), |u|^2 u, ...); it evaluates with three fixed registers instead of an
+// operand stack.  program_to_poly() derives it from the postfix program by symbolic execution.
+#define JFX_POLY_MAX_TERMS 16
+#define JFX_POLY_MAX_FACTORS 8
+struct PolyTerm {
+  double cre, cim;
+  int nf;
+  unsigned char fac[JFX_POLY_MAX_FACTORS];   // leaf index | 0x80 = conjugated
+  int pad_;
+};
+struct PolyProgram {
+  int n_terms;   // 0 = not a polynomial: use the stack machine
+  int pad_;
+  PolyTerm t[JFX_POLY_MAX_TERMS];
+};
+
 struct PointwiseProgram {
   int n_instr;
   jfx_pw_instr instr[JFX_MAX_PROGRAM];
@@ -102,6 +120,7 @@ struct PointwiseProgram {
 };
 int validate_program(const PointwiseProgram& prog, const void* const* statics);
 int program_depth(const PointwiseProgram& prog);
+bool program_to_poly(const PointwiseProgram& prog, PolyProgram* out);
 int launch_pointwise(cudaStream_t s, const PointwiseProgram& prog, const void* const* leaves,
                      const void* const* statics, void* out, int64_t n, int dtype);
 
@@ -120,6 +139,7 @@ struct FusedRowArgs {
   double scale;
   int n_instr;
   int depth;                           // operand-stack depth of the program
+  PolyProgram poly;                    // polynomial normal form (n_terms = 0: none)
   jfx_pw_instr instr[JFX_MAX_PROGRAM];
   double consts[32][2];
 };

@@ -107,7 +107,8 @@ fused_rows_kernel(const __grid_constant__ FusedRowArgs a) {
         const Cpx<T> z = reinterpret_cast<const Cpx<T>*>(a.statics[s])[(size_t)row * N + m];
         return C2<T>{z.x, z.y};
       };
-      const C2<T> r = pw_eval<T, true, DEPTH>(a.instr, a.n_instr, a.consts, leaf, stat);
+      const C2<T> r = a.poly.n_terms > 0 ? poly_eval<T>(a.poly, leaf)
+                                         : pw_eval<T, true, DEPTH>(a.instr, a.n_instr, a.consts, leaf, stat);
       Lb[m] = Cpx<T>{r.re, r.im};
     }
 #pragma unroll

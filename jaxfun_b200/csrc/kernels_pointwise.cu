@@ -7,6 +7,11 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <algorithm>
+#include <complex>
+#include <map>
+#include <vector>
+
 #include "jfx_common.h"
 #include "pointwise.cuh"
 
@@ -25,7 +30,8 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const __grid_constant__ 
       if (CPLX) return reinterpret_cast<const C2<T>*>(a.statics[l])[i];
       return C2<T>{reinterpret_cast<const T*>(a.statics[l])[i], T(0)};
     };
-    const C2<T> r = pw_eval<T, CPLX, DEPTH>(a.instr, a.n_instr, a.consts, leaf, stat);
+    const C2<T> r = a.poly.n_terms > 0 ? poly_eval<T>(a.poly, leaf)
+                                       : pw_eval<T, CPLX, DEPTH>(a.instr, a.n_instr, a.consts, leaf, stat);
     if (CPLX) reinterpret_cast<C2<T>*>(out_)[i] = r;
     else reinterpret_cast<T*>(out_)[i] = r.re;
   }
@@ -40,6 +46,104 @@ int program_depth(const PointwiseProgram& prog) {
     mx = sp > mx ? sp : mx;
   }
   return mx;
+}
+
+// postfix program -> polynomial normal form by symbolic execution (false: not a polynomial in the leaves)
+bool program_to_poly(const PointwiseProgram& prog, PolyProgram* out) {
+  using Mono = std::vector<unsigned char>;                 // sorted factor list
+  using Poly = std::map<Mono, std::complex<double>>;
+  out->n_terms = 0;
+  std::vector<Poly> st;
+  auto mul = [](const Poly& a, const Poly& b, Poly* r) -> bool {
+    r->clear();
+    for (const auto& x : a)
+      for (const auto& y : b) {
+        Mono m = x.first;
+        m.insert(m.end(), y.first.begin(), y.first.end());
+        if (m.size() > JFX_POLY_MAX_FACTORS) return false;
+        std::sort(m.begin(), m.end());
+        (*r)[m] += x.second * y.second;
+      }
+    return r->size() <= 4 * JFX_POLY_MAX_TERMS;
+  };
+  for (int i = 0; i < prog.n_instr; ++i) {
+    const int op = prog.instr[i].op, arg = prog.instr[i].arg;
+    switch (op) {
+      case JFX_PW_LEAF: {
+        if (arg < 0 || arg >= 0x80) return false;
+        Poly p; p[Mono{(unsigned char)arg}] = 1.0; st.push_back(p);
+      } break;
+      case JFX_PW_CONST: {
+        Poly p; p[Mono{}] = std::complex<double>(prog.consts[arg][0], prog.consts[arg][1]); st.push_back(p);
+      } break;
+      case JFX_PW_ADD: {
+        if (st.size() < 2) return false;
+        Poly b = st.back(); st.pop_back();
+        for (const auto& y : b) st.back()[y.first] += y.second;
+      } break;
+      case JFX_PW_MUL: {
+        if (st.size() < 2) return false;
+        Poly b = st.back(); st.pop_back();
+        Poly r;
+        if (!mul(st.back(), b, &r)) return false;
+        st.back() = r;
+      } break;
+      case JFX_PW_NEG:
+        if (st.empty()) return false;
+        for (auto& y : st.back()) y.second = -y.second;
+        break;
+      case JFX_PW_CONJ: {
+        if (st.empty()) return false;
+        Poly r;
+        for (const auto& y : st.back()) {
+          Mono m = y.first;
+          for (auto& f : m) f ^= 0x80;
+          std::sort(m.begin(), m.end());
+          r[m] += std::conj(y.second);
+        }
+        st.back() = r;
+      } break;
+      case JFX_PW_ABS: {
+        // |z|^(2k) = (z conj z)^k: only in front of an even integer power
+        if (st.empty() || i + 1 >= prog.n_instr || prog.instr[i + 1].op != JFX_PW_POWI) return false;
+        const int n = prog.instr[i + 1].arg;
+        if (n < 2 || (n & 1) || n > 8) return false;
+        Poly c;
+        for (const auto& y : st.back()) {
+          Mono m = y.first;
+          for (auto& f : m) f ^= 0x80;
+          std::sort(m.begin(), m.end());
+          c[m] += std::conj(y.second);
+        }
+        Poly zz, r;
+        if (!mul(st.back(), c, &zz)) return false;
+        r = zz;
+        for (int k = 1; k < n / 2; ++k) { Poly tmp; if (!mul(r, zz, &tmp)) return false; r = tmp; }
+        st.back() = r;
+        ++i;   // the POWI was consumed
+      } break;
+      case JFX_PW_POWI: {
+        if (st.empty() || arg < 0 || arg > 8) return false;
+        Poly r; r[Mono{}] = 1.0;
+        for (int k = 0; k < arg; ++k) { Poly tmp; if (!mul(r, st.back(), &tmp)) return false; r = tmp; }
+        st.back() = r;
+      } break;
+      default: return false;   // statics, functions, real powers: stack machine
+    }
+  }
+  if (st.size() != 1) return false;
+  int n = 0;
+  for (const auto& y : st.back()) {
+    if (y.second == std::complex<double>(0.0, 0.0)) continue;
+    if (n >= JFX_POLY_MAX_TERMS) return false;
+    PolyTerm& t = out->t[n++];
+    t.cre = y.second.real(); t.cim = y.second.imag();
+    t.nf = (int)y.first.size();
+    for (int f = 0; f < JFX_POLY_MAX_FACTORS; ++f) t.fac[f] = f < t.nf ? y.first[f] : 0;
+  }
+  if (n == 0) { out->t[0] = PolyTerm{}; n = 1; }   // identically zero: one zero term
+  out->n_terms = n;
+  return true;
 }
 
 int validate_program(const PointwiseProgram& prog, const void* const* statics) {
@@ -76,6 +180,7 @@ int launch_pointwise(cudaStream_t s, const PointwiseProgram& prog, const void* c
   a.n_instr = prog.n_instr;
   memcpy(a.instr, prog.instr, sizeof(jfx_pw_instr) * prog.n_instr);
   memcpy(a.consts, prog.consts, sizeof(a.consts));
+  if (!program_to_poly(prog, &a.poly)) a.poly.n_terms = 0;
   int64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   const bool deep = program_depth(prog) > 4;

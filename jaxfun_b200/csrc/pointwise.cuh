@@ -112,6 +112,7 @@ struct PwArgs {
   int n_instr;
   jfx_pw_instr instr[JFX_MAX_PROGRAM];
   double consts[32][2];
+  PolyProgram poly;   // n_terms > 0: evaluate the polynomial normal form instead of the stack program
 };
 
 
@@ -163,6 +164,30 @@ __device__ __forceinline__ C2<T> pw_eval(const jfx_pw_instr* __restrict__ instr,
     }
   }
   return st[0];
+}
+
+// Polynomial normal form: acc += coeff * prod(factors), three live values, no operand stack.
+template <typename T, typename LeafFn>
+__device__ __forceinline__ C2<T> poly_eval(const PolyProgram& P, LeafFn leaf) {
+  C2<T> acc{T(0), T(0)};
+  for (int t = 0; t < P.n_terms; ++t) {
+    const PolyTerm& tm = P.t[t];
+    C2<T> p{T(tm.cre), T(tm.cim)};
+    int prev = -1;
+    C2<T> x{T(0), T(0)};
+    for (int f = 0; f < tm.nf; ++f) {
+      const int fc = tm.fac[f];
+      if (fc != prev) {
+        x = leaf(fc & 0x7f);
+        if (fc & 0x80) x.im = -x.im;
+        prev = fc;
+      }
+      p = cmul(p, x);
+    }
+    acc.re += p.re;
+    acc.im += p.im;
+  }
+  return acc;
 }
 
 }  // namespace jfx
