@@ -311,7 +311,7 @@ def run_ours(args):
         n_l = pLb.launches + pLf.launches
         ach = flops_L / (tL * 1e-3) / 1e12
         line["roofline"] = {
-            "kernel": "dgemm_dmma (FP64 tensor-core per-axis Vandermonde contraction)", "bound": "tensor",
+            "kernel": "dgemm_dmma_tma (FP64 tensor-core per-axis Vandermonde contraction, TMA-fed mbarrier pipeline)", "bound": "tensor",
             "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
             "traffic": ncu_traffic("dgemm_dmma"), "launches_per_step": n_l, "avg_launch_ms": tL / n_l,
             "flops_per_launch": flops_L / n_l,

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "jfx_common.h"
+#include "dmma_params.h"
 
 namespace jfx {
 
@@ -106,14 +107,6 @@ __device__ __forceinline__ void mma_884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
-struct Params {
-  const double* A;  // [M, K] row-major (lda)
-  const double* B;  // NT: [N, K] row-major (ldb); NN: [K, N] row-major (ldb)
-  double* C;        // [M, N] row-major (ldc)
-  int M, N, K;
-  int64_t lda, ldb, ldc;
-  int64_t strideA, strideB, strideC;  // per batch (blockIdx.z)
-};
 
 // WM x WN = warp tile; the CTA tile is always 128 x 128, so THREADS = (128/WM) * (128/WN) * 32:
 //   64 x 32 -> 8 warps (2 per SM sub-partition, 64 accumulators per thread),
@@ -495,6 +488,12 @@ static int run_dmma(cudaStream_t s, const AxisGeom& g, int dtype, const void* ta
     p.strideA = 0; p.strideB = (int64_t)g.n_in * inner; p.strideC = (int64_t)g.n_out * inner;
     JFX_REQUIRE(g.outer < (1ll << 31), JFX_ERR_UNSUPPORTED, "outer extent too large");
     grid = dim3((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, (unsigned)g.outer);
+  }
+  static const bool no_tma = [] { const char* e = getenv("JFX_DMMA_TMA"); return e && e[0] == '0'; }();
+  if (!no_tma && !force_pers) {
+    const int rc = launch_dmma_tma(s, p, nn, (int)grid.x, (int)grid.y, (int)grid.z, sms);
+    if (rc < 0) return rc;
+    if (rc == 1) return JFX_OK;
   }
   if (force_pers || grid.y > 65535 || grid.z > 65535) {
     PParams pp{p, (int)grid.x, (int)grid.y, (int)grid.z};
