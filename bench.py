@@ -325,11 +325,25 @@ def run_ours(args):
         achC = bytes_C / (tC * 1e-3) / 1e9                 # whole transform: compulsory bytes / time
         per_launch_bytes = 2.0 * 8 * n**3                   # one axis pass reads the field once and writes it once
         ach_launch = per_launch_bytes / (tC / n_c * 1e-3) / 1e9
+        # context for the HBM fraction: what a plain device copy of ONE field of this size reaches (the
+        # MEASURED_PEAKS figure is a 2 GiB copy; a 134 MB launch also pays its ramp-up and tail)
+        cp_src, cp_dst = torch.empty_like(cC), torch.empty_like(cC)
+        for _ in range(3):
+            cp_dst.copy_(cp_src)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(10):
+            cp_dst.copy_(cp_src)
+        k1.record()
+        torch.cuda.synchronize()
+        copy_gbs = per_launch_bytes / (k0.elapsed_time(k1) / 10 * 1e-3) / 1e9
+        del cp_src, cp_dst
         line["roofline_hbm"] = {
             "kernel": "fft2_kernel (Chebyshev DCT axis pass; Chebyshev^3 backward+forward = 6 launches)",
             "bound": "hbm", "achieved": ach_launch, "peak": hbm, "unit": "GB/s", "frac": ach_launch / hbm,
             "traffic": ncu_traffic("fft2_kernel"), "launches_per_step": n_c, "avg_launch_ms": tC / n_c,
             "bytes_per_launch": per_launch_bytes,
+            "copy_same_size_gbs": copy_gbs, "frac_of_copy_same_size": ach_launch / copy_gbs,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650",
             "transform_level": {"algorithmic_bytes_per_step": bytes_C, "achieved": achC, "frac": achC / hbm,
                                 "note": "SURVEY 8(d) view: input read once + output written once per 3-D transform; "
