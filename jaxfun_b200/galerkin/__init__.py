@@ -8,3 +8,4 @@ from . import (  # noqa: F401
     orthogonal as orthogonal,
 )
 from .tensorproductspace import TensorProduct as TensorProduct, TensorProductSpace as TensorProductSpace  # noqa: F401
+from .composite import Composite as Composite, FunctionSpace as FunctionSpace  # noqa: F401,E402

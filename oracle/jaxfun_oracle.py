@@ -882,3 +882,75 @@ def imex_rk_step(u_hat, dt, tableau, M, Lw, Nsp, forcing=None):
     if forcing is not None:
         rhs = rhs + dt * forcing
     return rhs / M
+
+
+# =================================================================================================
+# Composite (boundary-condition) bases  (galerkin/composite.py:121-349) — SURVEY §8(f) rank 1
+# =================================================================================================
+class Composite(OrthogonalSpace):
+    """phi_i = sum_j S_ij P_j.  Each method applies the stencil around the orthogonal transform exactly as
+    the reference does (composite.py:205-208, 277-284, 339-349); the mass solve is a dense solve here
+    (the reference uses a banded LU of the same matrix, la/diamatrix.py:394-773)."""
+
+    def __init__(self, N, orthogonal, stencil, scaling=1, domain=None, **kw):
+        self.orthogonal = orthogonal(N, domain=domain, **kw)
+        self.N = N
+        self.num_quad_points = N
+        self.domain = self.orthogonal.domain
+        k = np.arange(N - 1)
+        nsym = sp.Symbol("n", integer=True)
+        shifts = sorted(int(s) for s in stencil)
+        self.width = max(shifts) - min(shifts)
+        rows = N - self.width
+        S = np.zeros((rows, N))
+        for sh in shifts:
+            v = sp.lambdify(nsym, sp.sympify(stencil[sh]) / sp.sympify(scaling), modules="numpy")(k)
+            v = np.atleast_1d(np.asarray(v, dtype=float))
+            if v.shape[0] == 1:
+                v = np.full(N - 1, float(v[0]))
+            for i in range(rows):
+                if 0 <= i + sh < N:
+                    S[i, i + sh] = v[i]
+        self.S = S
+        h = np.asarray(self.orthogonal.norm_squared(), dtype=float) * np.ones(N) / float(self.orthogonal.domain_factor)
+        self.mass = S @ np.diag(h) @ S.T                       # composite.py:310-313
+
+    @property
+    def reference_domain(self):
+        return self.orthogonal.reference_domain
+
+    @property
+    def dim(self):
+        return self.N - self.width
+
+    def quad_points_and_weights(self, N=None):
+        return self.orthogonal.quad_points_and_weights(N)
+
+    def mesh(self, kind="quadrature", N=None):
+        return self.orthogonal.mesh(kind, N)
+
+    def to_orthogonal(self, a, axis=-1):                       # composite.py:277-280: a @ S
+        return _along(lambda am: self.S.T @ am, a, axis)
+
+    def from_orthogonal(self, a, axis=-1):                     # composite.py:282-284
+        return _along(lambda am: np.linalg.solve(self.S @ self.S.T, self.S @ am), a, axis)
+
+    def backward(self, c, N=None, axis=-1):                    # composite.py:205-208
+        return self.orthogonal.backward(self.to_orthogonal(c, axis), N=N, axis=axis)
+
+    def backward_primitive(self, c, k=0, N=None, axis=-1):     # composite.py:210-218
+        return self.orthogonal.backward_primitive(self.to_orthogonal(c, axis), k=k, N=N, axis=axis)
+
+    def scalar_product(self, u, axis=-1):                      # composite.py:346-349
+        P = self.orthogonal.scalar_product(u, axis=axis)
+        return _along(lambda pm: self.S @ pm, P, axis)
+
+    def forward(self, u, axis=-1):                             # composite.py:339-344
+        Lp = self.scalar_product(u, axis)
+        return _along(lambda lm: np.linalg.solve(self.mass, lm), Lp, axis)
+
+    def eval_basis_functions(self, X):
+        return self.orthogonal.eval_basis_functions(X) @ self.S.T
+
+    def evaluate(self, x, c, axis=-1):
+        return self.orthogonal.evaluate(x, self.to_orthogonal(c, axis), axis)
