@@ -115,9 +115,27 @@ def measured_peaks():
 # --------------------------------------------------------------------------------------------------
 # CPU side (oracle)
 # --------------------------------------------------------------------------------------------------
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs must use every host core (BLAS via threadpoolctl,
+    scipy.fft via its `workers` argument in the oracle)."""
+    cores = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=cores)
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(cores)
+    except Exception:
+        pass
+    return cores
+
+
 def oracle_spaces(n, dims=3):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import jaxfun_oracle as O
+    use_all_host_threads()
     O.Jacobi.fast_backward = True  # Vandermonde matmul instead of the scan: the faster CPU form
     return (O, O.TensorProductSpace(*[O.Legendre(n) for _ in range(dims)]),
             O.TensorProductSpace(*[O.Chebyshev(n) for _ in range(dims)]))
