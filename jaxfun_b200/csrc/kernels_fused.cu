@@ -25,11 +25,14 @@
 
 namespace jfx {
 
+#ifndef JFX_FUSED_TPS
+#define JFX_FUSED_TPS 512   /* resident threads per SM the register budget is sized for */
+#endif
 constexpr int FUSED_THREADS = 128;
 
 template <typename T, int N, bool PAD, int DEPTH>
 __global__ void __launch_bounds__((N / Geo<N>::RMAX) > FUSED_THREADS ? (N / Geo<N>::RMAX) : FUSED_THREADS,
-                                  512 / ((N / Geo<N>::RMAX) > FUSED_THREADS ? (N / Geo<N>::RMAX) : FUSED_THREADS))
+                                  JFX_FUSED_TPS / ((N / Geo<N>::RMAX) > FUSED_THREADS ? (N / Geo<N>::RMAX) : FUSED_THREADS))
 fused_rows_kernel(const __grid_constant__ FusedRowArgs a) {
   using P = Plan<N>;
   constexpr int R0 = P::R0;
