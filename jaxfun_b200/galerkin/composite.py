@@ -32,6 +32,14 @@ def _stencil_rows(stencil: dict, scaling, N: int) -> tuple[list[int], list[np.nd
     k = np.arange(N - 1)
     shifts, vals = [], []
     for shift, val in sorted(stencil.items()):
+        if isinstance(val, np.ndarray):     # numeric stencil (stencil_from_bcs): one value per basis index
+            sc = np.atleast_1d(np.asarray(sp.lambdify(n, sp.sympify(scaling), modules="numpy")(k), dtype=float))
+            v = np.zeros(N - 1)
+            v[: val.shape[0]] = val[: N - 1]
+            v = v / (sc if sc.shape[0] > 1 else float(sc[0]))
+            shifts.append(int(shift))
+            vals.append(v)
+            continue
         expr = sp.sympify(val) / sp.sympify(scaling)
         f = sp.lambdify(n, expr, modules="numpy")
         v = np.atleast_1d(np.asarray(f(k), dtype=float))
@@ -156,6 +164,52 @@ class Composite(OrthogonalSpace):
         return self._run(L.OP_APPLY, c, axis, table=T, cache=False)
 
 
+_BC_ORDER = {"D": 0, "N": 1, "N2": 2, "N3": 3, "N4": 4}
+
+
+def ordered_bc_names(bcs: dict) -> list[tuple[str, str]]:
+    """[(side, kind)] in the reference's order: left before right, by derivative order
+    (`BoundaryConditions.orderednames`, composite.py:40-118)."""
+    out = []
+    for side in ("left", "right"):
+        for kind in sorted(bcs.get(side, {}), key=lambda v: _BC_ORDER[v]):
+            out.append((side, kind))
+    return out
+
+
+def stencil_from_bcs(bcs: dict, orthogonal) -> dict:
+    """Numeric counterpart of `get_stencil_matrix` (composite.py:765-838): phi_n = P_n + sum_{j=1..nb} d_j(n) P_{n+j}
+    with d(n) solving  sum_j d_j f_b(n + j) = -f_b(n)  for every homogeneous boundary functional
+    f_b(m) = d^k P_m / dX^k at X = -1 or +1.  The reference solves this system symbolically in n; here it is
+    solved per basis index from the boundary values of the (derivative) Vandermonde.  Robin conditions are
+    not covered."""
+    names = ordered_bc_names(bcs)
+    nb = len(names)
+    N = orthogonal.N
+    F = np.empty((nb, N))
+    for b, (side, kind) in enumerate(names):
+        if kind not in _BC_ORDER:
+            raise NotImplementedError(f"boundary condition kind {kind!r} (Robin) has no numeric stencil here")
+        if bcs[side][kind] != 0:
+            raise NotImplementedError("inhomogeneous boundary values need the DirectSum lifting (composite.py:502-634)")
+        X = np.array([-1.0 if side == "left" else 1.0])
+        F[b] = orthogonal.evaluate_basis_derivative(X, _BC_ORDER[kind])[0]
+    rows = N - nb
+    d = np.zeros((nb, rows))
+    for i in range(rows):
+        A = F[:, i + 1: i + 1 + nb]
+        d[:, i] = np.linalg.solve(A, -F[:, i])
+    st = {0: np.ones(rows)}
+    for j in range(nb):
+        if np.abs(d[j]).max() > 1e-14:
+            dj = d[j].copy()
+            dj[np.abs(dj) < 1e-15] = 0.0
+            st[j + 1] = dj
+    if max(st) != nb:                       # keep the full width even when the last diagonal vanishes
+        st[nb] = np.zeros(rows)
+    return st
+
+
 def FunctionSpace(N: int, space, bcs=None, domain=None, name: str = "fun", fun_str: str = "phi", scaling=None, **kw):
     """`jaxfun.galerkin.functionspace.FunctionSpace` (functionspace.py:63-173) for the cases whose stencil is
     known in closed form: no BCs -> the orthogonal space; homogeneous Dirichlet on both ends of a Chebyshev /
@@ -167,5 +221,7 @@ def FunctionSpace(N: int, space, bcs=None, domain=None, name: str = "fun", fun_s
             space.__name__ in ("Chebyshev", "Legendre"):
         return Composite(N, space, bcs=bcs, domain=domain, name=name, fun_str=fun_str, stencil={0: 1, 2: -1},
                          scaling=scaling)
-    raise NotImplementedError(f"no closed-form stencil for boundary conditions {bcs} on {space.__name__}; pass "
-                              "Composite(..., stencil=...) explicitly")
+    # any other set of homogeneous Dirichlet / Neumann / higher-derivative conditions: numeric stencil
+    orth = space(N, domain=domain, **kw)
+    return Composite(N, space, bcs=bcs, domain=domain, name=name, fun_str=fun_str, stencil=stencil_from_bcs(bcs, orth),
+                     scaling=scaling, **kw)

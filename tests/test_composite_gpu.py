@@ -99,3 +99,27 @@ def test_poisson3d_example(cuda):
     uej = sp.lambdify((x, y, z), ue, "numpy")(*xj)
     error = np.linalg.norm(uj.cpu().numpy() - uej) / np.sqrt(T.dim)
     assert error < ULP1000, error
+
+
+@pytest.mark.parametrize("base", ["Chebyshev", "Legendre"])
+@pytest.mark.parametrize("bcs", [{"left": {"D": 0, "N": 0}, "right": {"D": 0, "N": 0}}, {"left": {"N": 0}, "right": {"N": 0}},
+                                 {"left": {"D": 0}, "right": {"N": 0}}])
+def test_composite_general_boundary_conditions(cuda, base, bcs):
+    """Numeric stencils (stencil_from_bcs == get_stencil_matrix, composite.py:765-838): round trip and the
+    boundary conditions themselves, on the device."""
+    N = 24
+    C = jf.FunctionSpace(N, getattr(jf, base), bcs)
+    nb = sum(len(v) for v in bcs.values())
+    assert C.dim == N - nb
+    rng = np.random.default_rng(nb)
+    c = dev(rng.standard_normal((4, C.dim)), cuda)
+    u = C.backward(c)
+    assert rel(C.forward(u), c.cpu().numpy()) < 1e-10
+    ends = {"left": float(C.domain[0]), "right": float(C.domain[1])}
+    for side, kinds in bcs.items():
+        for kind in kinds:
+            k = {"D": 0, "N": 1}[kind]
+            X = np.array([ends[side]])
+            T = np.ascontiguousarray(C.evaluate_basis_derivative(X, k))
+            val = C._run(jf._lib.OP_APPLY, c, -1, table=T, cache=False)
+            assert float(val.abs().max()) < 1e-8 * max(1.0, float(u.abs().max()))

@@ -43,3 +43,33 @@ def test_host_poisson_assembly_and_diagonalisation():
         f = A @ u @ B.T + B @ u @ A.T
         u2 = S.V[0] @ ((S.W[0] @ f @ S.W[1].T) * S.Dinv) @ S.V[1].T
         assert np.abs(u2 - u).max() < 1e-9 * np.abs(u).max()
+
+
+@pytest.mark.parametrize("base", ["Chebyshev", "Legendre"])
+def test_numeric_stencils_match_the_reference_closed_forms(base):
+    """get_stencil_matrix special cases (composite.py:783-797) and the Neumann example of its docstring."""
+    import jaxfun_b200 as jf
+    from jaxfun_b200.galerkin.composite import stencil_from_bcs
+    N = 24
+    orth = getattr(jf, base)(N)
+    k = np.arange(N)
+    st = stencil_from_bcs({"left": {"D": 0}, "right": {"D": 0}}, orth)
+    assert np.allclose(st[0], 1) and np.allclose(st[2], -1) and (1 not in st or np.allclose(st[1], 0))
+    st = stencil_from_bcs({"left": {"D": 0, "N": 0}, "right": {"D": 0, "N": 0}}, orth)
+    kk = k[: N - 4].astype(float)
+    if base == "Legendre":
+        d2, d4 = 2 * (-2 * kk - 5) / (2 * kk + 7), (2 * kk + 3) / (2 * kk + 7)
+    else:
+        d2, d4 = 2 * (-kk - 2) / (kk + 3), (kk + 1) / (kk + 3)
+    assert np.abs(st[2] - d2).max() < 1e-10 and np.abs(st[4] - d4).max() < 1e-10
+    assert all(np.abs(st.get(j, 0)).max() < 1e-10 for j in (1, 3))
+    if base == "Chebyshev":
+        st = stencil_from_bcs({"left": {"N": 0}, "right": {"N": 0}}, orth)
+        kk = k[: N - 2].astype(float)
+        assert np.abs(st[2] + kk**2 / (kk + 2) ** 2).max() < 1e-10
+    # the composite basis built from a numeric stencil satisfies its boundary conditions
+    C = jf.FunctionSpace(N, getattr(jf, base), {"left": {"D": 0, "N": 0}, "right": {"D": 0, "N": 0}})
+    assert C.dim == N - 4
+    ends = np.array([-1.0, 1.0])
+    assert np.abs(C.eval_basis_functions(ends)).max() < 1e-10
+    assert np.abs(C.evaluate_basis_derivative(ends, 1)).max() < 1e-7
