@@ -185,3 +185,40 @@ def test_evaluate_and_derivative_coeffs(cuda):
         assert relerr(p.evaluate_mesh(dev(c, cuda), "uniform", 21), o.evaluate_mesh(c, "uniform", 21)) < TOL64
         for k in (1, 2):
             assert relerr(p.derivative_coeffs(dev(c, cuda), k), o.derivative_coeffs(c, k)) < 1e-11
+
+
+def test_cuda_graph_capture_and_replay(cuda):
+    """jfx_execute / jfx_nonlinear_execute enqueue only kernels and async copies (no allocation, no host
+    synchronisation): a transform pair and a nonlinear term captured into ONE CUDA graph replay correctly on
+    new input (what a `lax.fori_loop` body lowered to a command buffer needs)."""
+    from jaxfun_b200.integrators import NonlinearTerm, field
+    T = jf.TensorProduct(jf.Legendre(32), jf.Chebyshev(64), jf.Chebyshev(64))
+    V = jf.Fourier(256)
+    u, (x,) = field(V)
+    term = NonlinearTerm(V, -u * u.diff(x))
+    c = torch.randn(32, 64, 64, dtype=torch.float64, device=cuda)
+    uh = 0.1 * torch.randn(64, 256, dtype=torch.complex128, device=cuda)
+    out_c, out_n = torch.empty_like(c), torch.empty_like(uh)
+    s = torch.cuda.Stream(device=cuda)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):          # warm-up on the capture stream: plans, tables, workspaces exist afterwards
+        for _ in range(2):
+            out_c.copy_(T.forward(T.backward(c)))
+            term(uh, out_n)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        out_c.copy_(T.forward(T.backward(c)))
+        term(uh, out_n)
+    # new inputs, replay, compare with eager execution
+    c.copy_(torch.randn_like(c))
+    uh.copy_(0.1 * torch.randn_like(uh))
+    g.replay()
+    torch.cuda.synchronize()
+    ref_c = T.forward(T.backward(c))
+    ref_n = term(uh)
+    torch.cuda.synchronize()
+    assert torch.equal(out_c, ref_c)
+    assert torch.equal(out_n, ref_n)
+    assert float((out_c - c).abs().max()) < 1e-11
