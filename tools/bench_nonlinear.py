@@ -15,6 +15,7 @@ def main():
     ap.add_argument("what")
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--step", action="store_true", help="also time one full ETDRK4 step (ch)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     n = a.n
@@ -38,6 +39,24 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    if a.what == "ch" and a.step:
+        # one full ETDRK4 step of Cahn-Hilliard (examples/cahn_hilliard2D_etdrk4.py:52-53, 86): 4 nonlinear terms +
+        # the diagonal stage arithmetic
+        import numpy as np
+        from jaxfun_b200.integrators import ETDRK4
+        k = np.asarray(V.basespaces[0].wavenumbers(), dtype=float) * float(V.basespaces[0].domain_factor)
+        k2 = k[:, None] ** 2 + k[None, :] ** 2
+        Ldiag = torch.from_numpy((-k2 - 1.5e-2 * k2**2) * (1.0 + 0j)).to(dev)   # nu = -1 Laplacian + mu = -1.5e-2 bi-Laplacian
+        integ = ETDRK4(V, linear_diag=Ldiag, nonlinear=nl)
+        dt = 5e-2 / 320
+        u1 = integ.step(uh, dt)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(5):
+            u1 = integ.step(uh, dt)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"ch n={n} ETDRK4 step: {e0.elapsed_time(e1) / 5:.3f} ms  (finite: {bool(torch.isfinite(torch.view_as_real(u1)).all())})")
     comp = 2 * uh.numel() * 16
     print(f"{a.what} n={n} fused={os.environ.get('JFX_NL_FUSE', '1')}: {ms * 1e3:9.1f} us per nonlinear term, "
           f"launches={nl.launches(uh)}, compulsory {comp / 1e6:.0f} MB -> {comp / ms / 1e6:.1f} GB/s")
