@@ -222,3 +222,14 @@ def test_cuda_graph_capture_and_replay(cuda):
     assert torch.equal(out_c, ref_c)
     assert torch.equal(out_n, ref_n)
     assert float((out_c - c).abs().max()) < 1e-11
+
+
+def test_many_batches_on_a_middle_axis(cuda):
+    """More than 65 535 outer blocks on a non-last table axis (3-D tensor-map batch / persistent tile walk)."""
+    o, p = O.Legendre(16), jf.Legendre(16)
+    rng = np.random.default_rng(9)
+    c = rng.standard_normal((70000, 16, 4))
+    u = p.backward(dev(c, cuda), axis=1)
+    ref = o.backward(c[::7000], axis=1)
+    assert relerr(u[::7000], ref) < TOL64
+    assert relerr(p.forward(u, axis=1), c) < 1e-11
