@@ -16,7 +16,7 @@ struct Params {
 };
 
 // TMA-fed persistent kernel.  1 = launched, 0 = outside its envelope (use the cp.async kernel), < 0 = error.
-int launch_dmma_tma(cudaStream_t s, const Params& p, bool nn, int tiles_n, int tiles_m, int batch, int sms);
+int launch_dmma_tma(cudaStream_t s, const Params& p, bool nn, int batch, int sms);
 
 }  // namespace dmma
 }  // namespace jfx

@@ -491,7 +491,7 @@ static int run_dmma(cudaStream_t s, const AxisGeom& g, int dtype, const void* ta
   }
   static const bool no_tma = [] { const char* e = getenv("JFX_DMMA_TMA"); return e && e[0] == '0'; }();
   if (!no_tma && !force_pers) {
-    const int rc = launch_dmma_tma(s, p, nn, (int)grid.x, (int)grid.y, (int)grid.z, sms);
+    const int rc = launch_dmma_tma(s, p, nn, (int)grid.z, sms);
     if (rc < 0) return rc;
     if (rc == 1) return JFX_OK;
   }

@@ -25,12 +25,21 @@ namespace jfx {
 namespace dmma {
 
 namespace tma {
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 6;
+constexpr int BK = 16;
 constexpr int MMA_WARPS = 8, THREADS = MMA_WARPS * 32;
 constexpr int WM = 64, WN = 32;
-constexpr int A_TILE = BM * BK, B_TILE = BN * BK;                    // doubles (16 KB each)
-constexpr unsigned STAGE_BYTES = (A_TILE + B_TILE) * sizeof(double);
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8;
+// CTA tile shapes (always 8 warps of 64 x 32): 128 x 128, and 64 x 256 / 256 x 64 for table extents that are odd
+// multiples of 64 (96 -> no gain, 192, 320, ...), where a 128-wide tile would be a quarter padding
+template <int SHAPE> struct Tile {
+  static constexpr int BM = SHAPE == 0 ? 128 : (SHAPE == 1 ? 64 : 256);
+  static constexpr int BN = SHAPE == 0 ? 128 : (SHAPE == 1 ? 256 : 64);
+  static constexpr int WARPS_N = BN / WN;
+  static constexpr int A_TILE = BM * BK, B_TILE = BN * BK;             // doubles
+  static constexpr unsigned STAGE_BYTES = (A_TILE + B_TILE) * sizeof(double);
+  static constexpr int STAGES = SHAPE == 0 ? 6 : 5;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8;
+  static_assert((BM / WM) * (BN / WN) == MMA_WARPS, "8 MMA warps");
+};
 constexpr unsigned SPIN_LIMIT = 1u << 27;
 
 __device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -83,10 +92,13 @@ struct TmaArgs {
 // cost a 384-thread budget (170 registers per thread, spills).  Instead lane 0 of warp 0 refills, before
 // each k-tile it computes, the stage that was consumed LAG = 2 k-tiles earlier — by then every warp has
 // normally released it, so the "empty" wait returns at once and warp 0 is not held up.
-template <bool NN, bool PW>
+template <bool NN, bool PW, int SHAPE>
 __global__ void __launch_bounds__(tma::THREADS + (PW ? 32 : 0), 1)
 dgemm_dmma_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TmaArgs q) {
   using namespace tma;
+  using TL = Tile<SHAPE>;
+  constexpr int BM = TL::BM, BN = TL::BN, STAGES = TL::STAGES, A_TILE = TL::A_TILE;
+  constexpr unsigned STAGE_BYTES = TL::STAGE_BYTES;
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte aligned tile ring (the 128 B swizzle is a function of address bits 4..9)
   const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;
@@ -156,7 +168,7 @@ dgemm_dmma_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   // ================================ MMA warps ================================
-  const int wm = warp >> 2, wn = warp & 3;   // 2 x 4 warps
+  const int wm = warp / TL::WARPS_N, wn = warp % TL::WARPS_N;
   const int g = lane >> 2, qd = lane & 3;
   const int nn_x = (g >> 1) ^ (qd >> 1);
   const int nn_base0 = wn * 512 + qd * 8 + (nn_x << 1) + (g & 1);
@@ -260,35 +272,30 @@ static bool encode(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t*
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int launch_dmma_tma(cudaStream_t s, const Params& p, bool nn, int tiles_n, int tiles_m, int batch, int sms) {
+template <bool NN, int SHAPE>
+static int launch_shape(cudaStream_t s, const Params& p, int batch, int sms) {
   using namespace tma;
-  // envelope: 16-byte aligned bases and strides (cuTensorMapEncodeTiled), no batch stride on the table
-  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
-  if (!al16(p.A) || !al16(p.B) || (p.lda & 1) || (p.ldb & 1)) return 0;
-  if (p.strideA != 0 && (p.strideA & 1)) return 0;
-  if (nn && batch > 1 && (p.strideB & 1)) return 0;
-  if (!nn && batch != 1) return 0;
-  if (nn && p.strideA != 0) return 0;
+  using TL = Tile<SHAPE>;
   static bool attr = false;
   if (!attr) {
-    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_tma<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_tma<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_tma<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_tma<NN, true, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)TL::SMEM_BYTES));
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_tma<NN, false, SHAPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)TL::SMEM_BYTES));
     attr = true;
   }
   CUtensorMap tmA, tmB;
   {
-    // A: [M, K] row-major, K contiguous -> box {16 k, 128 m}
+    // A: [M, K] row-major, K contiguous -> box {16 k, BM m}
     const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
     const cuuint64_t str[1] = {(cuuint64_t)p.lda * 8};
-    const cuuint32_t box[2] = {BK, BM};
+    const cuuint32_t box[2] = {BK, (cuuint32_t)TL::BM};
     if (!encode(&tmA, p.A, 2, dims, str, box)) return 0;
   }
-  if (!nn) {
+  if (!NN) {
     const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
     const cuuint64_t str[1] = {(cuuint64_t)p.ldb * 8};
-    const cuuint32_t box[2] = {BK, BN};
+    const cuuint32_t box[2] = {BK, (cuuint32_t)TL::BN};
     if (!encode(&tmB, p.B, 2, dims, str, box)) return 0;
   } else {
     // B: [batch][K][N] with N contiguous -> boxes {8 n, 16 k, 1}, 64 B swizzle
@@ -298,20 +305,33 @@ int launch_dmma_tma(cudaStream_t s, const Params& p, bool nn, int tiles_n, int t
     const cuuint32_t box[3] = {8, BK, 1};
     if (!encode(&tmB, p.B, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 0;
   }
+  const int tiles_m = (p.M + TL::BM - 1) / TL::BM, tiles_n = (p.N + TL::BN - 1) / TL::BN;
   TmaArgs q{p.M, p.N, p.K, p.C, p.ldc, p.strideC, tiles_n, tiles_m, batch};
   const long long tiles = (long long)tiles_n * tiles_m * batch;
   const unsigned ctas = (unsigned)(tiles < sms ? tiles : sms);
   // dedicated producer warp (default) or lane 0 of MMA warp 0 (JFX_DMMA_TMA_PW=0)
   static const bool pw = [] { const char* e = getenv("JFX_DMMA_TMA_PW"); return !(e && e[0] == '0'); }();
-  if (pw) {
-    if (nn) dgemm_dmma_tma<true, true><<<ctas, THREADS + 32, SMEM_BYTES, s>>>(tmA, tmB, q);
-    else dgemm_dmma_tma<false, true><<<ctas, THREADS + 32, SMEM_BYTES, s>>>(tmA, tmB, q);
-  } else {
-    if (nn) dgemm_dmma_tma<true, false><<<ctas, THREADS, SMEM_BYTES, s>>>(tmA, tmB, q);
-    else dgemm_dmma_tma<false, false><<<ctas, THREADS, SMEM_BYTES, s>>>(tmA, tmB, q);
-  }
+  if (pw) dgemm_dmma_tma<NN, true, SHAPE><<<ctas, THREADS + 32, TL::SMEM_BYTES, s>>>(tmA, tmB, q);
+  else dgemm_dmma_tma<NN, false, SHAPE><<<ctas, THREADS, TL::SMEM_BYTES, s>>>(tmA, tmB, q);
   JFX_CUDA_OK(cudaGetLastError());
   return 1;
+}
+
+int launch_dmma_tma(cudaStream_t s, const Params& p, bool nn, int batch, int sms) {
+  // envelope: 16-byte aligned bases and strides (cuTensorMapEncodeTiled), no batch stride on the table
+  auto al16 = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
+  if (!al16(p.A) || !al16(p.B) || (p.lda & 1) || (p.ldb & 1)) return 0;
+  if (p.strideA != 0 && (p.strideA & 1)) return 0;
+  if (nn && batch > 1 && (p.strideB & 1)) return 0;
+  if (!nn && batch != 1) return 0;
+  if (nn && p.strideA != 0) return 0;
+  // tile shape: the table extent (M in the NN order, N in the NT order) decides; a 64-wide tile pays when it
+  // removes padding (192 -> 3 x 64 instead of 2 x 128) and the other extent is long enough for a 256-wide tile
+  const int table_extent = nn ? p.M : p.N, other = nn ? p.N : p.M;
+  const int pad128 = (table_extent + 127) / 128 * 128, pad64 = (table_extent + 63) / 64 * 64;
+  const bool narrow = pad64 < pad128 && other >= 512;
+  if (nn) return narrow ? launch_shape<true, 1>(s, p, batch, sms) : launch_shape<true, 0>(s, p, batch, sms);
+  return narrow ? launch_shape<false, 2>(s, p, batch, sms) : launch_shape<false, 0>(s, p, batch, sms);
 }
 
 }  // namespace dmma
