@@ -283,7 +283,7 @@ __device__ __forceinline__ void fft2_tile(const FftArgs& a, long long tile, Cpx<
           const int b = jj + r * NS;
           if (GEN && b >= nout) continue;
           const Cpx<T> wk = v[bf * R + r];
-          const Cpx<T> wm = Sl[sk<LOGSK>((N - b) & (N - 1))];
+          const Cpx<T> wm = Sl[sk<LOGSK>(b == 0 ? 0 : N - b)];
           const Cpx<T> t = half[b];
           Cpx<T> c;
           c.x = t.x * (wk.x + wm.x) - t.y * (wk.y - wm.y);   // t wk + conj(t) wm

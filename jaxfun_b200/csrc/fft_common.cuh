@@ -21,6 +21,10 @@ __device__ constexpr double kCos16[8] = {1.0, 0.92387953251128673848, 0.70710678
 __device__ constexpr double kSin16[8] = {0.0, 0.38268343236508977173, 0.70710678118654752440, 0.92387953251128673848,
                                          1.0, 0.92387953251128673848, 0.70710678118654752440, 0.38268343236508977173};
 
+// cos(2 pi k/12), sin(2 pi k/12), k = 0..5 (radices 6 and 12 of the 3 * 2^m lengths 48, 96, 192)
+__device__ constexpr double kCos12[6] = {1.0, 0.86602540378443864676, 0.5, 0.0, -0.5, -0.86602540378443864676};
+__device__ constexpr double kSin12[6] = {0.0, 0.5, 0.86602540378443864676, 1.0, 0.86602540378443864676, 0.5};
+
 // In-register forward DFT of R points, natural order in and out (decimation in time).
 template <typename T, int R> struct Dft {
   static __device__ __forceinline__ void run(Cpx<T>* v) {
@@ -35,7 +39,8 @@ template <typename T, int R> struct Dft {
       if (k == 0) t = o[k];
       else if (4 * k == R) t = Cpx<T>{o[k].y, -o[k].x};   // * (-i)
       else {
-        const T c = (T)kCos16[k * (16 / R)], s = (T)kSin16[k * (16 / R)];  // W = c - i s
+        const T c = (R % 3 == 0) ? (T)kCos12[k * (12 / R)] : (T)kCos16[k * (16 / R)];   // W = c - i s
+        const T s = (R % 3 == 0) ? (T)kSin12[k * (12 / R)] : (T)kSin16[k * (16 / R)];
         t = Cpx<T>{o[k].x * c + o[k].y * s, o[k].y * c - o[k].x * s};
       }
       v[k] = e[k] + t;
@@ -50,6 +55,18 @@ template <typename T> struct Dft<T, 2> {
   }
 };
 template <typename T> struct Dft<T, 1> { static __device__ __forceinline__ void run(Cpx<T>*) {} };
+template <typename T> struct Dft<T, 3> {
+  static __device__ __forceinline__ void run(Cpx<T>* v) {
+    // X1 = v0 - (v1+v2)/2 - i (sqrt3/2)(v1 - v2),  X2 = conj-mirror
+    const Cpx<T> s = v[1] + v[2], d = v[1] - v[2];
+    const Cpx<T> t{v[0].x - T(0.5) * s.x, v[0].y - T(0.5) * s.y};
+    const T h = (T)0.86602540378443864676;
+    const Cpx<T> u{h * d.y, -h * d.x};     // -i * h * d
+    v[0] = v[0] + s;
+    v[1] = t + u;
+    v[2] = t - u;
+  }
+};
 
 // radix plans
 template <int N> struct Plan;
@@ -62,11 +79,20 @@ template <> struct Plan<512>  { static constexpr int R0 = 8,  R1 = 8,  R2 = 8;  
 template <> struct Plan<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8;  };
 template <> struct Plan<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8;  };
 template <> struct Plan<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16; };
+// 3 * 2^m: the first radix stays a power of two (it defines the shared-memory skew), the factor 3 sits in the
+// last pass; a thread owns 12 points so that every pass holds a whole number of butterflies
+template <> struct Plan<48>   { static constexpr int R0 = 4,  R1 = 12, R2 = 1;  };
+template <> struct Plan<96>   { static constexpr int R0 = 4,  R1 = 4,  R2 = 6;  };
+template <> struct Plan<192>  { static constexpr int R0 = 4,  R1 = 4,  R2 = 12; };
 
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
+template <int N> struct PointsPerThread { static constexpr int value = cmax(Plan<N>::R0, cmax(Plan<N>::R1, Plan<N>::R2)); };
+template <> struct PointsPerThread<48> { static constexpr int value = 12; };
+template <> struct PointsPerThread<96> { static constexpr int value = 12; };
+template <> struct PointsPerThread<192> { static constexpr int value = 12; };
 template <int N> struct Geo {
-  static constexpr int RMAX = cmax(Plan<N>::R0, cmax(Plan<N>::R1, Plan<N>::R2));
+  static constexpr int RMAX = PointsPerThread<N>::value;   // points a thread owns (= largest radix for 2^m)
   static constexpr int TN = N / RMAX;                       // threads per line
   static constexpr int LOGSK = ilog2(Plan<N>::R0);          // smem skew: i + (i >> LOGSK)
   static constexpr int PITCH = N + (N >> LOGSK) + 1;        // odd -> conflict-free across lines

@@ -74,6 +74,9 @@ template <typename T>
 static int launch_t(cudaStream_t s, const FftArgs& a, int n) {
   switch (n) {
     case 16: return launch_n<T, 16>(s, a);
+    case 48: return launch_n<T, 48>(s, a);
+    case 96: return launch_n<T, 96>(s, a);
+    case 192: return launch_n<T, 192>(s, a);
     case 32: return launch_n<T, 32>(s, a);
     case 64: return launch_n<T, 64>(s, a);
     case 128: return launch_n<T, 128>(s, a);
