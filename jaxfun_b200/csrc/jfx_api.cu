@@ -355,7 +355,7 @@ static int try_fuse_rows(const jfx_nonlinear_desc* d, jfx_nonlinear* nl) {
   const jfx_axis_desc& fa = fd->axis[last];
   if (fa.basis != JFX_BASIS_FOURIER) return JFX_OK;
   const int n = fa.n_quad;
-  if (n < 64 || !fast_available(JFX_BASIS_FOURIER, n, fd->dtype)) return JFX_OK;
+  if (n < 48 || !fast_available(JFX_BASIS_FOURIER, n, fd->dtype)) return JFX_OK;
   if (fd->shape_in[last] != n) return JFX_OK;
   const int64_t n_coeff = d->leaves[0]->shape_in[last];
   for (int l = 0; l < d->n_leaves; ++l) {

@@ -199,7 +199,10 @@ static int launch_fused_n(cudaStream_t s, const FusedRowArgs& a, size_t* q) {
 template <typename T>
 static int launch_fused_t(cudaStream_t s, int n, const FusedRowArgs& a, size_t* q) {
   switch (n) {
+    case 48: return launch_fused_n<T, 48>(s, a, q);
     case 64: return launch_fused_n<T, 64>(s, a, q);
+    case 96: return launch_fused_n<T, 96>(s, a, q);
+    case 192: return launch_fused_n<T, 192>(s, a, q);
     case 128: return launch_fused_n<T, 128>(s, a, q);
     case 256: return launch_fused_n<T, 256>(s, a, q);
     case 512: return launch_fused_n<T, 512>(s, a, q);

@@ -244,3 +244,18 @@ def test_backward_euler_step_matches_oracle(cuda):
     uh = crand(rng, (N,), 0.05)
     dt = 1e-3
     assert relerr(integ.step(dev(uh, cuda), dt), O.backward_euler_step(uh, dt, M, M * Ldiag, Nsp)) < 1e-12
+
+
+@pytest.mark.parametrize("N,M", [(32, 48), (64, 96), (128, 192)])
+def test_three_halves_rule_padding_is_row_fused(cuda, N, M):
+    """3/2-rule de-aliasing: N modes evaluated on M = 3N/2 points (a 3 * 2^m transform length) — the padded
+    nonlinear term runs as ONE row-fused launch and matches the oracle (nonlinear_rhs(uh, N=M), base.py:230-236)."""
+    rng = np.random.default_rng(N)
+    V, Vo = jf.Fourier(N), O.Fourier(N)
+    u, (x,) = field(V)
+    term = NonlinearTerm(V, -u * u.diff(x), N=(M,))
+    uh = crand(rng, (6, N), 0.1)
+    got = term(dev(uh, cuda))
+    assert term.launches(dev(uh, cuda)) == 1
+    ref = np.stack([O.nonlinear_rhs(Vo, [0, 1], lambda a, ax: -(a * ax), r, N=M) for r in uh])
+    assert relerr(got, ref) < 1e-12
