@@ -99,20 +99,35 @@ fused_rows_kernel(const __grid_constant__ FusedRowArgs a) {
       __syncthreads();                                   // exchange buffer is reused by the next transform
     }
     // ---- pointwise program over the thread's own points, in place over the line of leaf 0 ------------
+    if (a.poly.n_terms > 0) {
+      // polynomial normal form, four points at a time (their scratch loads overlap)
+      static_assert(E % 4 == 0, "points per thread");
 #pragma unroll 1
-    for (int e = 0; e < E; ++e) {
-      const int m = j + e * TN;
-      auto leaf = [&](int l) -> C2<T> {
-        const Cpx<T> z = Lb[(size_t)l * N + m];
-        return C2<T>{z.x, z.y};
-      };
-      auto stat = [&](int s) -> C2<T> {
-        const Cpx<T> z = reinterpret_cast<const Cpx<T>*>(a.statics[s])[(size_t)row * N + m];
-        return C2<T>{z.x, z.y};
-      };
-      const C2<T> r = a.poly.n_terms > 0 ? poly_eval<T>(a.poly, leaf)
-                                         : pw_eval<T, true, DEPTH>(a.instr, a.n_instr, a.consts, leaf, stat);
-      Lb[m] = Cpx<T>{r.re, r.im};
+      for (int e0 = 0; e0 < E; e0 += 4) {
+        auto leaf4 = [&](int l, int c) -> C2<T> {
+          const Cpx<T> z = Lb[(size_t)l * N + j + (e0 + c) * TN];
+          return C2<T>{z.x, z.y};
+        };
+        C2<T> r4[4];
+        poly_eval_vec<T, 4>(a.poly, leaf4, r4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Lb[j + (e0 + c) * TN] = Cpx<T>{r4[c].re, r4[c].im};
+      }
+    } else {
+#pragma unroll 1
+      for (int e = 0; e < E; ++e) {
+        const int m = j + e * TN;
+        auto leaf = [&](int l) -> C2<T> {
+          const Cpx<T> z = Lb[(size_t)l * N + m];
+          return C2<T>{z.x, z.y};
+        };
+        auto stat = [&](int s) -> C2<T> {
+          const Cpx<T> z = reinterpret_cast<const Cpx<T>*>(a.statics[s])[(size_t)row * N + m];
+          return C2<T>{z.x, z.y};
+        };
+        const C2<T> r = pw_eval<T, true, DEPTH>(a.instr, a.n_instr, a.consts, leaf, stat);
+        Lb[m] = Cpx<T>{r.re, r.im};
+      }
     }
 #pragma unroll
     for (int bf = 0; bf < BPT0; ++bf)

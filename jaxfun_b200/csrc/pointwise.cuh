@@ -190,4 +190,34 @@ __device__ __forceinline__ C2<T> poly_eval(const PolyProgram& P, LeafFn leaf) {
   return acc;
 }
 
+// The same for C points at once: the C leaf loads of a factor are independent, so their latencies overlap
+// (the leaves of the row-fused kernel come from an L2-resident scratch).  leaf(l, c) = leaf l at point c.
+template <typename T, int C, typename LeafFn>
+__device__ __forceinline__ void poly_eval_vec(const PolyProgram& P, LeafFn leaf, C2<T>* out) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) out[c] = C2<T>{T(0), T(0)};
+  for (int t = 0; t < P.n_terms; ++t) {
+    const PolyTerm& tm = P.t[t];
+    C2<T> p[C], x[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { p[c] = C2<T>{T(tm.cre), T(tm.cim)}; x[c] = C2<T>{T(0), T(0)}; }
+    int prev = -1;
+    for (int f = 0; f < tm.nf; ++f) {
+      const int fc = tm.fac[f];
+      if (fc != prev) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          x[c] = leaf(fc & 0x7f, c);
+          if (fc & 0x80) x[c].im = -x[c].im;
+        }
+        prev = fc;
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) p[c] = cmul(p[c], x[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) { out[c].re += p[c].re; out[c].im += p[c].im; }
+  }
+}
+
 }  // namespace jfx
