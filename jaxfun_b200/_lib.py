@@ -113,7 +113,7 @@ def load() -> C.CDLL:
         return _lib
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m jaxfun_b200._build` "
+            f"{LIB_PATH} is missing: build it with `python jaxfun_b200/_build.py` "
             "(or __graft_entry__.build()). jaxfun_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():

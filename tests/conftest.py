@@ -13,12 +13,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
-@pytest.fixture(scope="session", autouse=True)
-def _built_library():
-    """The product path needs libjfx.so; build it once if the tree is fresh (nvcc cross-compiles)."""
-    from jaxfun_b200 import _build
-    _build.build_library()
-    yield
+def _ensure_library():
+    """The product path needs libjfx.so.  _build.py is loaded by path (importing the package needs the
+    library) and runs before collection, because the test modules import jaxfun_b200 at import time.
+    A missing library is always built; a stale one only where there is no GPU (the dev container), so
+    the GPU box never spends its time in nvcc on the prebuilt file that travelled with the snapshot."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_jfx_build", os.path.join(ROOT, "jaxfun_b200", "_build.py"))
+    _build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(_build)
+    if not os.path.exists(_build.LIB):
+        _build.build_library(force=True)
+    elif _build.needs_build():
+        import torch
+        if not torch.cuda.is_available():
+            _build.build_library()
+
+
+_ensure_library()
 
 
 @pytest.fixture(scope="session")
