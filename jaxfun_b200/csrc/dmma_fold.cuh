@@ -1,0 +1,447 @@
+// Parity-folded FP64 tensor-core contraction: index math shared by the CUDA kernel (kernels_dense_fold.cu)
+// and by the host emulator that checks it on a machine without a GPU (tests/emu/fold_emu.cpp).
+//
+// Why: every table the polynomial bases produce on symmetric nodes (Legendre, Jacobi alpha = beta, Chebyshev,
+// ChebyshevU, Ultraspherical, and their composite / derivative tables) obeys psi_k(-x) = (-1)^k psi_k(x) and
+// x_{n-1-j} = -x_j, i.e.
+//        backward  T[n-1-j, k] = sigma_k T[j, k]      ("OUT" fold: the mirror pair is a pair of OUTPUT rows)
+//        forward   T[k, n-1-j] = sigma_k T[k, j]      ("IN"  fold: the mirror pair is a pair of INPUT rows)
+// with sigma_k = +1 for k = par_plus (mod 2) and -1 otherwise.  (Reference: the Vandermonde of
+// galerkin/orthogonal.py:131-141 on the nodes of Legendre.py:125-137 / Jacobi.py:112-124.)  Then
+//        OUT:  u_j = P_j + Q_j,  u_{n-1-j} = P_j - Q_j,   P_j = sum_{k plus} T[j,k] c_k,  Q_j = sum_{k minus} T[j,k] c_k
+//        IN :  c_k = sum_{j < n/2} T[k,j] (u_j + sigma_k u_{n-1-j})
+// which is HALF the multiply-adds of the plain contraction.  The kernel keeps the 128 x 128 CTA tile and the
+// 64 x 32 warp tile of dgemm_dmma_tma, but every warp tile holds a "plus" half and a "minus" half for the
+// SAME output rows / columns, so the butterfly is done in registers:
+//   NN order (other axes,  C_o = T * X_o): m-tiles 0..3 = plus rows, 4..7 = minus rows of 32 outputs
+//   NT order (last axis,   C   = X * T^T): n-tiles 0..1 = plus cols, 2..3 = minus cols of 16 outputs
+// One pipeline stage = three 16 KB tiles:
+//   OUT_NN: R0 = folded table [128 r'][16 k'],  R1 = X rows of the plus parity [16][128],  R2 = minus parity
+//           (the parity split of the coefficient index is done by the TMA unit: 4-D tensor map (n, parity, k/2, batch))
+//   IN_NN : R0 = folded table,                  R1 = X rows j0..j0+15,   R2 = X rows n-16-j0..n-1-j0 (mirror, read reversed)
+//   OUT_NT: R0 = X[128 rows][k0..k0+15],        R1 = X[128 rows][k0+16..k0+31],  R2 = folded table [128 c'][16 k']
+//           (parity split in the fragment load: one LDS.128 fetches (even k, odd k) for the plus and the minus MMA)
+//   IN_NT : R0 = X[128 rows][j0..j0+15],        R1 = mirror columns,    R2 = folded table
+#pragma once
+#include <cstdint>
+#include <cmath>
+#include <vector>
+
+#if defined(__CUDACC__)
+#define JFX_HD __host__ __device__ __forceinline__
+#else
+#define JFX_HD inline
+#endif
+
+namespace jfx {
+namespace dmma {
+namespace fold {
+
+enum Variant { OUT_NN = 0, IN_NN = 1, OUT_NT = 2, IN_NT = 3 };
+enum FoldType { FOLD_NONE = 0, FOLD_OUT = 1, FOLD_IN = 2 };
+
+constexpr int BK = 16, BM = 128, BN = 128, WM = 64, WN = 32;
+constexpr int MMA_WARPS = 8, WARPS_N = BN / WN;
+constexpr int STAGES = 4;
+constexpr int TILE = 128 * 16;                       // doubles per 16 KB tile
+constexpr unsigned STAGE_BYTES = 3u * TILE * 8u;     // 48 KB
+constexpr int HALF_PER_TILE = 64;                    // mirror pairs covered by one CTA tile
+
+struct alignas(16) Double2 { double x, y; };
+
+// K-contiguous tile [128 rows][16 k], 128-byte swizzle (TMA SWIZZLE_128B on 128-byte rows): the 16-byte chunk
+// (k >> 1) of row r is stored at chunk (k >> 1) ^ (r & 7)
+JFX_HD int kc_off(int row, int k) { return row * 16 + ((((k >> 1) ^ (row & 7)) << 1) | (k & 1)); }
+// N-contiguous tile [16 k][128 n] stored as 16 sub-tiles [16 k][8 n] of 64-byte rows, 64-byte swizzle: chunk
+// ((n & 7) >> 1) of row k is stored at chunk ((n & 7) >> 1) ^ ((k >> 1) & 3)
+JFX_HD int nc_off(int k, int n) {
+  return (n >> 3) * 128 + k * 8 + (((((n & 7) >> 1) ^ ((k >> 1) & 3)) << 1) | (n & 1));
+}
+// row permutation of the OUT_NT variant: MMA row g of an m-tile is fed from tile row rho(g), so that the eight lanes
+// of one LDS.128 phase (two rows x four chunks) cover the eight 16-byte bank groups exactly once
+JFX_HD int rho(int g) { return ((g & 1) << 2) | (g >> 1); }
+
+struct Args {
+  // logical problem
+  int variant;
+  int par_plus;        // parity of the coefficient index whose sigma is +1
+  int n_fold;          // extent of the mirrored axis (nodes), even
+  int n_other;         // extent of the parity-split axis (modes)
+  int half;            // n_fold / 2
+  int kfold;           // reduction length of the folded problem: OUT: n_other / 2, IN: n_fold / 2
+  // GEMM geometry
+  int M, N;            // NN: M = folded table rows (padded), N = inner; NT: M = data rows, N = folded table rows (padded)
+  int tiles_m, tiles_n, batch;
+  double* C;
+  long long ldc, strideC;
+  int vec_ok;          // 16-byte aligned vector stores allowed
+};
+
+// ------------------------------------------------------------------------------------------------
+// one k-tile of the MMA warps (lane (g, t) of warp (wm, wn)); S = base of the stage (3 tiles)
+// mma(d0, d1, a, b) is the m8n8k4 step (device: mma.sync; emulator: a recorder)
+// ------------------------------------------------------------------------------------------------
+template <int V, class MMA>
+JFX_HD void ktile(const double* S, int wm, int wn, int g, int t, int par_plus, double (&acc)[8][4][2], MMA&& mma) {
+  const double* R0 = S;
+  const double* R1 = S + TILE;
+  const double* R2 = S + 2 * TILE;
+#pragma unroll
+  for (int kk = 0; kk < BK / 4; ++kk) {
+    const int kx = kk * 4 + t;
+    if constexpr (V == OUT_NN || V == IN_NN) {
+      // plus half (m-tiles 0..3) then minus half (m-tiles 4..7): 8 fragment registers live at a time
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = R0[kc_off(wm * WM + (h * 4 + i) * 8 + g, kx)];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = wn * WN + j * 8 + g;
+          if constexpr (V == OUT_NN) {
+            b[j] = (h ? R2 : R1)[nc_off(kx, n)];
+          } else {
+            const double u = R1[nc_off(kx, n)], v = R2[nc_off(15 - kx, n)];
+            b[j] = h ? u - v : u + v;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma(acc[h * 4 + i][j][0], acc[h * 4 + i][j][1], a[i], b[j]);
+      }
+    } else {
+      double b[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = R2[kc_off(wn * WN + j * 8 + g, kx)];
+      // four m-tiles at a time: plus / minus operand pairs of 4 rows live together
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        double ap[4], aq[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int i = h * 4 + ii;
+          if constexpr (V == OUT_NT) {
+            const int r = wm * WM + i * 8 + rho(g);
+            const int chunk = 4 * (kk & 1) + t;
+            const double* sub = (kk >> 1) ? R1 : R0;
+            const Double2 v = *reinterpret_cast<const Double2*>(sub + r * 16 + ((chunk ^ (r & 7)) << 1));
+            ap[ii] = par_plus ? v.y : v.x;
+            aq[ii] = par_plus ? v.x : v.y;
+          } else {
+            const int r = wm * WM + i * 8 + g;
+            const double u = R0[kc_off(r, kx)], v = R1[kc_off(r, 15 - kx)];
+            ap[ii] = u + v;
+            aq[ii] = u - v;
+          }
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            mma(acc[h * 4 + ii][j][0], acc[h * 4 + ii][j][1], j < 2 ? ap[ii] : aq[ii], b[j]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue of one CTA tile (tile_m, tile_n, z).  st.s2(idx, v0, v1): two consecutive elements at an even, 16-byte
+// aligned element index of C; st.s1(idx, v): one element.
+// ------------------------------------------------------------------------------------------------
+template <class ST>
+JFX_HD void put2(ST& st, bool vec, long long idx, double v0, double v1, bool ok0, bool ok1) {
+  if (vec && ok0 && ok1) {
+    st.s2(idx, v0, v1);
+  } else {
+    if (ok0) st.s1(idx, v0);
+    if (ok1) st.s1(idx + 1, v1);
+  }
+}
+
+template <int V, class ST>
+JFX_HD void epilogue(const Args& q, int tile_m, int tile_n, long long z, int wm, int wn, int g, int t,
+                     const double (&acc)[8][4][2], ST&& st) {
+  const bool vec = q.vec_ok != 0;
+  const int pp = q.par_plus, pq = 1 - q.par_plus;
+  if constexpr (V == OUT_NN) {
+    // rows: mirror pairs of the node index; cols: inner
+    const long long base = z * q.strideC;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int jidx = tile_m * HALF_PER_TILE + wm * 32 + i * 8 + g;
+      if (jidx >= q.half) continue;
+      const long long lo = base + (long long)jidx * q.ldc, hi = base + (long long)(q.n_fold - 1 - jidx) * q.ldc;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = tile_n * BN + wn * WN + j * 8 + 2 * t;
+        const bool ok0 = col < q.N, ok1 = col + 1 < q.N;
+        const double p0 = acc[i][j][0], p1 = acc[i][j][1], q0 = acc[i + 4][j][0], q1 = acc[i + 4][j][1];
+        put2(st, vec, lo + col, p0 + q0, p1 + q1, ok0, ok1);
+        put2(st, vec, hi + col, p0 - q0, p1 - q1, ok0, ok1);
+      }
+    }
+  } else if constexpr (V == IN_NN) {
+    // rows: mode index k = 2 * kidx + parity; cols: inner
+    const long long base = z * q.strideC;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int kidx = tile_m * HALF_PER_TILE + wm * 32 + (i & 3) * 8 + g;
+      const int k = 2 * kidx + ((i >> 2) ? pq : pp);
+      if (k >= q.n_other) continue;
+      const long long row = base + (long long)k * q.ldc;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = tile_n * BN + wn * WN + j * 8 + 2 * t;
+        put2(st, vec, row + col, acc[i][j][0], acc[i][j][1], col < q.N, col + 1 < q.N);
+      }
+    }
+  } else if constexpr (V == OUT_NT) {
+    // rows: data lines (permuted by rho inside an m-tile); cols: mirror pairs of the node index
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = tile_m * BM + wm * WM + i * 8 + rho(g);
+      if (row >= q.M) continue;
+      const long long rb = (long long)row * q.ldc;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = tile_n * HALF_PER_TILE + wn * 16 + j * 8 + 2 * t;
+        const bool ok0 = c < q.half, ok1 = c + 1 < q.half;
+        const double p0 = acc[i][j][0], p1 = acc[i][j][1], q0 = acc[i][j + 2][0], q1 = acc[i][j + 2][1];
+        put2(st, vec, rb + c, p0 + q0, p1 + q1, ok0, ok1);
+        // mirror columns n-1-c (value 0) and n-2-c (value 1): stored ascending as (n-2-c, n-1-c)
+        const long long m = rb + (q.n_fold - 2 - c);
+        put2(st, vec, m, p1 - q1, p0 - q0, ok1, ok0);
+      }
+    }
+  } else {
+    // rows: data lines; cols: mode index k = 2 * kidx + parity -> four consecutive columns 2c .. 2c+3
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = tile_m * BM + wm * WM + i * 8 + g;
+      if (row >= q.M) continue;
+      const long long rb = (long long)row * q.ldc;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = tile_n * HALF_PER_TILE + wn * 16 + j * 8 + 2 * t;
+        const double p0 = acc[i][j][0], p1 = acc[i][j][1], q0 = acc[i][j + 2][0], q1 = acc[i][j + 2][1];
+        const double e0 = pp ? q0 : p0, o0 = pp ? p0 : q0, e1 = pp ? q1 : p1, o1 = pp ? p1 : q1;
+        const int k0 = 2 * c;
+        put2(st, vec, rb + k0, e0, o0, k0 < q.n_other, k0 + 1 < q.n_other);
+        put2(st, vec, rb + k0 + 2, e1, o1, k0 + 2 < q.n_other, k0 + 3 < q.n_other);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA copies of one pipeline stage.  issue(map, dst_offset_in_doubles, rank, c0, c1, c2, c3); map 0 = "A" tensor map
+// (K-contiguous operand of the GEMM), 1 = "B" tensor map.  kt = k-tile of the folded problem.
+// ------------------------------------------------------------------------------------------------
+template <int V, class ISSUE>
+JFX_HD void stage_copies(const Args& q, int kt, int tile_m, int tile_n, int z, ISSUE&& issue) {
+  const int m0 = tile_m * BM, n0 = tile_n * BN, k0 = kt * BK;
+  if constexpr (V == OUT_NN) {
+    issue(0, 0, 2, k0, m0, 0, 0);
+#pragma unroll
+    for (int sub = 0; sub < BN / 8; ++sub) {
+      issue(1, TILE + sub * 128, 4, n0 + 8 * sub, q.par_plus, k0, z);
+      issue(1, 2 * TILE + sub * 128, 4, n0 + 8 * sub, 1 - q.par_plus, k0, z);
+    }
+  } else if constexpr (V == IN_NN) {
+    issue(0, 0, 2, k0, m0, 0, 0);
+#pragma unroll
+    for (int sub = 0; sub < BN / 8; ++sub) {
+      issue(1, TILE + sub * 128, 3, n0 + 8 * sub, k0, z, 0);
+      issue(1, 2 * TILE + sub * 128, 3, n0 + 8 * sub, q.n_fold - 16 - k0, z, 0);
+    }
+  } else if constexpr (V == OUT_NT) {
+    issue(0, 0, 2, 2 * k0, m0, 0, 0);
+    issue(0, TILE, 2, 2 * k0 + 16, m0, 0, 0);
+    issue(1, 2 * TILE, 2, k0, n0, 0, 0);
+  } else {
+    issue(0, 0, 2, k0, m0, 0, 0);
+    issue(0, TILE, 2, q.n_fold - 16 - k0, m0, 0, 0);
+    issue(1, 2 * TILE, 2, k0, n0, 0, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: symmetry analysis, folded tables, tensor-map descriptions
+// ------------------------------------------------------------------------------------------------
+struct MapDesc {
+  const void* base;
+  int rank;
+  unsigned long long dims[4];
+  unsigned long long strides_bytes[3];   // strides of dims 1..rank-1
+  unsigned box[4];
+  int swizzle_bytes;                     // 64 or 128
+};
+
+struct FoldInfo {
+  int type;       // FoldType
+  int par_plus;
+};
+
+// T: [rows][cols] row-major.  Detects the OUT fold (rows mirrored, both extents even) or the IN fold (columns mirrored,
+// column count even), with sigma_k strictly alternating.  tol is relative to max |T|.  The reference's nodes are mirror
+// images only up to an ulp (fastgl.py:512-544 takes cos(theta) and cos(pi - theta)), which shows in its Vandermonde as an
+// asymmetry of 1e-14 (n = 64) to 4e-13 (n = 1024) of max |T|; a table without the symmetry is off by O(1).  build() folds
+// the mean of the two mirror images, so the folded result differs from the plain contraction by at most half of that.
+inline FoldInfo analyze(const double* T, int rows, int cols, double tol = 1e-12) {
+  FoldInfo none{FOLD_NONE, 0};
+  if (rows < 2 || cols < 2) return none;
+  double tmax = 0;
+  for (long long i = 0; i < (long long)rows * cols; ++i) {
+    const double a = std::fabs(T[i]);
+    if (!(a <= 1.79e308)) return none;   // NaN / Inf
+    if (a > tmax) tmax = a;
+  }
+  if (tmax == 0) return none;
+  const double eps = tol * tmax;
+  // OUT: T[rows-1-j][k] = sigma_k T[j][k]
+  if (rows % 2 == 0 && cols % 2 == 0) {
+    for (int pp = 0; pp < 2; ++pp) {
+      bool ok = true;
+      for (int j = 0; j < rows / 2 && ok; ++j)
+        for (int k = 0; k < cols; ++k) {
+          const double s = ((k & 1) == pp) ? 1.0 : -1.0;
+          if (std::fabs(T[(long long)(rows - 1 - j) * cols + k] - s * T[(long long)j * cols + k]) > eps) { ok = false; break; }
+        }
+      if (ok) return FoldInfo{FOLD_OUT, pp};
+    }
+  }
+  // IN: T[k][cols-1-j] = sigma_k T[k][j]
+  if (cols % 2 == 0) {
+    for (int pp = 0; pp < 2; ++pp) {
+      bool ok = true;
+      for (int k = 0; k < rows && ok; ++k) {
+        const double s = ((k & 1) == pp) ? 1.0 : -1.0;
+        for (int j = 0; j < cols / 2; ++j)
+          if (std::fabs(T[(long long)k * cols + (cols - 1 - j)] - s * T[(long long)k * cols + j]) > eps) { ok = false; break; }
+      }
+      if (ok) return FoldInfo{FOLD_IN, pp};
+    }
+  }
+  return none;
+}
+
+struct FoldedTable {
+  int type = FOLD_NONE, par_plus = 0;
+  int n_fold = 0, n_other = 0, half = 0, kfold = 0;
+  int rows_nn = 0, rows_nt = 0, ld = 0;       // padded row counts of the two layouts, leading dimension (even)
+  std::vector<double> nn, nt;                  // folded tables for the NN and NT warp layouts, [rows][ld]
+};
+
+// row r' of the NN layout: tile = r' / 128, wm = (r' / 64) & 1, i = (r' / 8) & 7, g = r' & 7
+//   -> pair index = tile * 64 + wm * 32 + (i & 3) * 8 + g, group = i >> 2 (0 = plus, 1 = minus)
+JFX_HD void nn_row(int r, int* idx, int* grp) {
+  const int tile = r >> 7, wm = (r >> 6) & 1, i = (r >> 3) & 7, g = r & 7;
+  *idx = tile * HALF_PER_TILE + wm * 32 + (i & 3) * 8 + g;
+  *grp = i >> 2;
+}
+// row c' of the NT layout: tile = c' / 128, wn = (c' / 32) & 3, j = (c' / 8) & 3, g = c' & 7
+//   -> pair index = tile * 64 + wn * 16 + (j & 1) * 8 + g, group = j >> 1
+JFX_HD void nt_row(int c, int* idx, int* grp) {
+  const int tile = c >> 7, wn = (c >> 5) & 3, j = (c >> 3) & 3, g = c & 7;
+  *idx = tile * HALF_PER_TILE + wn * 16 + (j & 1) * 8 + g;
+  *grp = j >> 1;
+}
+
+// T: [rows][cols] as given to the plan (OUT: rows = nodes, cols = modes; IN: rows = modes, cols = nodes)
+inline FoldedTable build(const double* T, int rows, int cols, const FoldInfo& fi) {
+  FoldedTable f;
+  f.type = fi.type;
+  f.par_plus = fi.par_plus;
+  if (fi.type == FOLD_NONE) return f;
+  const bool out = fi.type == FOLD_OUT;
+  f.n_fold = out ? rows : cols;
+  f.n_other = out ? cols : rows;
+  f.half = f.n_fold / 2;
+  f.kfold = out ? f.n_other / 2 : f.half;
+  const int pairs = out ? f.half : (f.n_other + 1) / 2;     // mirror pairs (OUT) / mode pairs (IN) along the table rows
+  const int tiles = (pairs + HALF_PER_TILE - 1) / HALF_PER_TILE;
+  f.rows_nn = f.rows_nt = tiles * 128;
+  f.ld = (f.kfold + 1) & ~1;
+  if (f.ld < 2) f.ld = 2;
+  f.nn.assign((size_t)f.rows_nn * f.ld, 0.0);
+  f.nt.assign((size_t)f.rows_nt * f.ld, 0.0);
+  for (int layout = 0; layout < 2; ++layout) {
+    std::vector<double>& dst = layout == 0 ? f.nn : f.nt;
+    for (int r = 0; r < tiles * 128; ++r) {
+      int idx, grp;
+      if (layout == 0) nn_row(r, &idx, &grp); else nt_row(r, &idx, &grp);
+      const int par = grp ? 1 - fi.par_plus : fi.par_plus;
+      if (out) {
+        if (idx >= f.half) continue;
+        // sigma = +1 for the plus group, -1 for the minus group
+        const double sg = grp ? -1.0 : 1.0;
+        for (int kp = 0; kp < f.kfold; ++kp) {
+          const int k = 2 * kp + par;
+          dst[(size_t)r * f.ld + kp] = 0.5 * (T[(long long)idx * cols + k] + sg * T[(long long)(rows - 1 - idx) * cols + k]);
+        }
+      } else {
+        const int k = 2 * idx + par;
+        if (k >= f.n_other) continue;
+        const double sg = grp ? -1.0 : 1.0;
+        for (int j = 0; j < f.kfold; ++j)
+          dst[(size_t)r * f.ld + j] = 0.5 * (T[(long long)k * cols + j] + sg * T[(long long)k * cols + (cols - 1 - j)]);
+      }
+    }
+  }
+  return f;
+}
+
+// Geometry of one launch.  table = device (or emulated) pointer of the NN / NT folded table, X = input, C = output.
+// nn: the array is viewed as [outer][n_in][inner] (inner = real columns, even, > 1); !nn: [outer rows][n_in].
+inline bool make_launch(const FoldedTable& f, bool nn, long long outer, long long inner, const double* table,
+                        const double* X, double* C, Args* q, MapDesc* mA, MapDesc* mB) {
+  if (f.type == FOLD_NONE) return false;
+  const bool out = f.type == FOLD_OUT;
+  const int n_in = out ? f.n_other : f.n_fold, n_out = out ? f.n_fold : f.n_other;
+  Args a{};
+  a.variant = nn ? (out ? OUT_NN : IN_NN) : (out ? OUT_NT : IN_NT);
+  a.par_plus = f.par_plus;
+  a.n_fold = f.n_fold; a.n_other = f.n_other; a.half = f.half; a.kfold = f.kfold;
+  a.C = C;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(table) || !al16(X)) return false;
+  if (n_in % 2) return false;                       // TMA row strides must be multiples of 16 bytes
+  if (outer <= 0 || outer >= (1ll << 31) || inner >= (1ll << 31)) return false;
+  if (nn) {
+    if (inner < 2 || (inner & 1)) return false;
+    a.M = f.rows_nn; a.N = (int)inner;
+    a.tiles_m = f.rows_nn / BM; a.tiles_n = (int)((inner + BN - 1) / BN); a.batch = (int)outer;
+    a.ldc = inner; a.strideC = (long long)n_out * inner;
+    a.vec_ok = al16(C) ? 1 : 0;                     // inner even -> every row / batch offset is even
+    *mA = MapDesc{table, 2, {(unsigned long long)f.kfold, (unsigned long long)f.rows_nn, 1, 1},
+                  {(unsigned long long)f.ld * 8, 0, 0}, {BK, BM, 1, 1}, 128};
+    if (out) {
+      // X_o[k][n] with k = 2 kk + parity: dims (n, parity, kk, batch)
+      *mB = MapDesc{X, 4, {(unsigned long long)inner, 2, (unsigned long long)(n_in / 2), (unsigned long long)outer},
+                    {(unsigned long long)inner * 8, (unsigned long long)inner * 16, (unsigned long long)n_in * inner * 8},
+                    {8, 1, BK, 1}, 64};
+    } else {
+      *mB = MapDesc{X, 3, {(unsigned long long)inner, (unsigned long long)n_in, (unsigned long long)outer, 1},
+                    {(unsigned long long)inner * 8, (unsigned long long)n_in * inner * 8, 0}, {8, BK, 1, 1}, 64};
+    }
+  } else {
+    a.M = (int)outer; a.N = f.rows_nt;
+    a.tiles_m = (int)((outer + BM - 1) / BM); a.tiles_n = f.rows_nt / BN; a.batch = 1;
+    a.ldc = n_out; a.strideC = 0;
+    a.vec_ok = (al16(C) && n_out % 2 == 0) ? 1 : 0;
+    *mA = MapDesc{X, 2, {(unsigned long long)n_in, (unsigned long long)outer, 1, 1},
+                  {(unsigned long long)n_in * 8, 0, 0}, {BK, BM, 1, 1}, 128};
+    *mB = MapDesc{table, 2, {(unsigned long long)f.kfold, (unsigned long long)f.rows_nt, 1, 1},
+                  {(unsigned long long)f.ld * 8, 0, 0}, {BK, BN, 1, 1}, 128};
+  }
+  *q = a;
+  return true;
+}
+
+inline int ktiles(const Args& q) { return (q.kfold + BK - 1) / BK; }
+
+}  // namespace fold
+}  // namespace dmma
+}  // namespace jfx

@@ -1,0 +1,22 @@
+// Plan-time / launch-time interface of the parity-folded contraction (kernels_dense_fold.cu).  Internal header.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace jfx {
+namespace dmma {
+
+struct FoldPlan;
+
+// JFX_DMMA_FOLD=1 (read once) turns the folded kernel on for eligible table passes.
+bool fold_enabled();
+// Analyses the host table [rows][cols]; *out stays null when it has no mirror symmetry (not an error).
+int fold_plan_create(const double* table, int rows, int cols, FoldPlan** out);
+void fold_plan_destroy(FoldPlan* fp);
+int fold_plan_type(const FoldPlan* fp);   // 0 none, 1 OUT (backward-like), 2 IN (forward-like)
+// The array is [outer][n_in][inner_real] doubles (complex data: inner_real = 2 * inner).
+// 1 = launched, 0 = outside the envelope (use the plain kernel), < 0 = error.
+int launch_dmma_fold(cudaStream_t s, const FoldPlan* fp, long long outer, long long inner_real, const double* in,
+                     double* out);
+
+}  // namespace dmma
+}  // namespace jfx

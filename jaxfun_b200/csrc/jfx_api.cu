@@ -9,6 +9,7 @@
 
 #include "jfx_common.h"
 #include "fft_common.cuh"
+#include "dmma_fold_api.h"
 
 namespace jfx {
 
@@ -28,6 +29,7 @@ struct Pass {
   void* d_table = nullptr;  // owned
   bool table_complex = false;
   bool dmma = false;
+  dmma::FoldPlan* fold = nullptr;  // owned; parity-folded tables when the table has the mirror symmetry (JFX_DMMA_FOLD=1)
   FastParams fp{};
   FastTables* ft = nullptr;  // owned
 };
@@ -54,6 +56,7 @@ struct jfx_plan {
   ~jfx_plan() {
     for (auto& p : passes) {
       if (p.d_table) cudaFree(p.d_table);
+      if (p.fold) jfx::dmma::fold_plan_destroy(p.fold);
       if (p.ft) jfx::fast_tables_destroy(p.ft);
     }
     if (h_in) cudaFree(h_in);
@@ -165,6 +168,10 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
                   (long long)p.geom.inner);
     if (!p.fast) {
       p.dmma = table_apply_uses_dmma(p.geom, d->dtype, p.table_complex);
+      if (p.dmma && dmma::fold_enabled() && a.table != nullptr) {
+        int rc = dmma::fold_plan_create((const double*)a.table, n_out, n_in, &p.fold);
+        if (rc != JFX_OK) return rc;
+      }
       const double cm = dtype_is_complex(d->dtype) ? (p.table_complex ? 4.0 : 2.0) : 1.0;
       pl->flops += 2.0 * cm * (double)p.geom.outer * p.geom.inner * (double)n_in * n_out;
     }
@@ -228,6 +235,12 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
 
 static int run_pass_geom(cudaStream_t s, const Pass& p, const AxisGeom& g, int dtype, const void* src, void* dst) {
   if (p.fast) return launch_fast_axis(s, g, dtype, p.fp, p.ft, src, dst);
+  if (p.fold && g.outer * g.inner * g.n_out != 0) {
+    const int rc = dmma::launch_dmma_fold(s, p.fold, g.outer, g.inner * (dtype == JFX_C128 ? 2 : 1), (const double*)src,
+                                          (double*)dst);
+    if (rc < 0) return rc;
+    if (rc == 1) return JFX_OK;
+  }
   return launch_table_apply(s, g, dtype, p.d_table, p.table_complex, src, dst, nullptr);
 }
 static int run_pass(cudaStream_t s, const Pass& p, int dtype, const void* src, void* dst) {

@@ -1,0 +1,281 @@
+// Parity-folded FP64 tensor-core contraction (half the DMMA work of dgemm_dmma_tma for tables with the mirror
+// symmetry of polynomial bases on symmetric nodes).  The math, tile roles and every index formula live in
+// dmma_fold.cuh, which tests/emu/fold_emu.cpp executes on the host; this file adds the hardware pipeline:
+// a producer warp issuing cp.async.bulk.tensor box copies into a 4-stage ring of 48 KB stages (three 16 KB tiles),
+// "full" mbarriers carrying the transaction bytes, "empty" mbarriers with one arrival per MMA warp, a persistent
+// grid (one CTA per SM), spin waits bounded by __trap.
+//
+// Reference semantics: the same contraction as kernels_dense.cu (orthogonal.py:214-277 with the Vandermonde of
+// orthogonal.py:131-141); results differ from the unfolded kernel only by summation order.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include "jfx_common.h"
+#include "dmma_fold.cuh"
+#include "dmma_fold_api.h"
+
+namespace jfx {
+namespace dmma {
+namespace fold {
+
+// 8 MMA warps (two warpgroups) + one producer warpgroup of which only warp 8 / lane 0 works.  The third warpgroup exists
+// so that setmaxnreg can move registers: the kernel starts with 168 registers per thread (65536 / 384), the producer
+// warpgroup drops to 40 and the MMA warpgroups rise to 232 (2 * 128 * 232 + 128 * 40 = 64512 = 384 * 168).
+constexpr int THREADS = MMA_WARPS * 32 + 128;
+constexpr int REGS_PRODUCER = 40, REGS_MMA = 232;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8;
+constexpr unsigned SPIN_LIMIT = 1u << 27;
+
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > SPIN_LIMIT) __trap();   // a lost signal becomes a launch failure, never a hang
+  }
+}
+__device__ __forceinline__ void tma_2d(unsigned dst, const CUtensorMap* tm, int c0, int c1, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_3d(unsigned dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_4d(unsigned dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+
+struct MmaOp {
+  __device__ __forceinline__ void operator()(double& d0, double& d1, double a, double b) const {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+  }
+};
+
+struct GlobalStore {
+  double* C;
+  __device__ __forceinline__ void s2(long long idx, double v0, double v1) const {
+    *reinterpret_cast<double2*>(C + idx) = make_double2(v0, v1);
+  }
+  __device__ __forceinline__ void s1(long long idx, double v) const { C[idx] = v; }
+};
+
+template <int V>
+__global__ void __launch_bounds__(THREADS, 1)
+dgemm_dmma_fold(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args q) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte aligned tile ring (the swizzles are functions of the shared-memory address bits 4..9)
+  const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* gbase = smem_raw + (base - s32(smem_raw));
+  const unsigned bar_full = base + STAGES * STAGE_BYTES;
+  const unsigned bar_empty = bar_full + STAGES * 8;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, MMA_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int kts = (q.kfold + BK - 1) / BK;
+  const long long total_tiles = (long long)q.tiles_n * q.tiles_m * q.batch;
+
+  if (warp >= MMA_WARPS) {
+    // ================================ producer warpgroup ================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+    if (warp != MMA_WARPS || lane != 0) return;
+    long long it = 0;
+    for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
+      const int tn = (int)(tl % q.tiles_n);
+      const long long r = tl / q.tiles_n;
+      const int tm = (int)(r % q.tiles_m);
+      const int z = (int)(r / q.tiles_m);
+      for (int kt = 0; kt < kts; ++kt, ++it) {
+        const int s = (int)(it % STAGES);
+        const unsigned ph = (unsigned)((it / STAGES) & 1);
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        const unsigned full = bar_full + 8 * s;
+        mbar_expect_tx(full, STAGE_BYTES);
+        const unsigned dst0 = base + s * STAGE_BYTES;
+        stage_copies<V>(q, kt, tm, tn, z, [&](int map, int dst, int rank, int c0, int c1, int c2, int c3) {
+          const CUtensorMap* tmap = map == 0 ? &tmA : &tmB;
+          const unsigned d = dst0 + (unsigned)dst * 8u;
+          if (rank == 2) tma_2d(d, tmap, c0, c1, full);
+          else if (rank == 3) tma_3d(d, tmap, c0, c1, c2, full);
+          else tma_4d(d, tmap, c0, c1, c2, c3, full);
+        });
+      }
+    }
+    return;
+  }
+
+  // ================================ MMA warps ================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_MMA));
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  long long it = 0;
+  for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
+    for (int kt = 0; kt < kts; ++kt, ++it) {
+      const int s = (int)(it % STAGES);
+      const unsigned ph = (unsigned)((it / STAGES) & 1);
+      mbar_wait(bar_full + 8 * s, ph);
+      const double* S = reinterpret_cast<const double*>(gbase + (size_t)s * STAGE_BYTES);
+      ktile<V>(S, wm, wn, g, t, q.par_plus, acc, MmaOp{});
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+    }
+    const int tn = (int)(tl % q.tiles_n);
+    const long long r = tl / q.tiles_n;
+    const int tm = (int)(r % q.tiles_m);
+    const long long z = r / q.tiles_m;
+    epilogue<V>(q, tm, tn, z, wm, wn, g, t, acc, GlobalStore{q.C});
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  }
+}
+
+// ---- host ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn encode_fn() {
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeFn)p;
+  }();
+  return fn;
+}
+
+static bool encode(CUtensorMap* tm, const MapDesc& m) {
+  EncodeFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4], strides[3];
+  cuuint32_t box[4];
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int d = 0; d < m.rank; ++d) { dims[d] = m.dims[d]; box[d] = m.box[d]; }
+  for (int d = 0; d + 1 < m.rank; ++d) strides[d] = m.strides_bytes[d];
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)m.rank, const_cast<void*>(m.base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, m.swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int V>
+static int launch_variant(cudaStream_t s, const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& q, int sms) {
+  static bool attr = false;
+  if (!attr) {
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_fold<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr = true;
+  }
+  const long long tiles = (long long)q.tiles_n * q.tiles_m * q.batch;
+  const unsigned ctas = (unsigned)(tiles < sms ? tiles : sms);
+  dgemm_dmma_fold<V><<<ctas, THREADS, SMEM_BYTES, s>>>(tmA, tmB, q);
+  JFX_CUDA_OK(cudaGetLastError());
+  return 1;
+}
+
+}  // namespace fold
+
+// ---- plan-time object ------------------------------------------------------------------------------
+struct FoldPlan {
+  fold::FoldedTable host;     // geometry (the host copies of the tables are released after the upload)
+  double* d_nn = nullptr;     // device copies of the two layouts
+  double* d_nt = nullptr;
+};
+
+// Read at every plan creation (not cached), so one process can hold folded and plain plans side by side.
+bool fold_enabled() {
+  const char* e = getenv("JFX_DMMA_FOLD");
+  return e && e[0] == '1';
+}
+
+int fold_plan_create(const double* table, int rows, int cols, FoldPlan** out) {
+  *out = nullptr;
+  if (rows < 16 || cols < 16) return JFX_OK;   // tiny tables: the plain kernel's tile is already mostly padding
+  const fold::FoldInfo fi = fold::analyze(table, rows, cols);
+  if (fi.type == fold::FOLD_NONE) return JFX_OK;
+  FoldPlan* fp = new FoldPlan;
+  fp->host = fold::build(table, rows, cols, fi);
+  const size_t bn = fp->host.nn.size() * sizeof(double), bt = fp->host.nt.size() * sizeof(double);
+  if (cudaMalloc(&fp->d_nn, bn) != cudaSuccess || cudaMalloc(&fp->d_nt, bt) != cudaSuccess ||
+      cudaMemcpy(fp->d_nn, fp->host.nn.data(), bn, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(fp->d_nt, fp->host.nt.data(), bt, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    fold_plan_destroy(fp);
+    set_error("fold_plan_create: device allocation / upload of the folded tables failed");
+    return JFX_ERR_CUDA;
+  }
+  std::vector<double>().swap(fp->host.nn);
+  std::vector<double>().swap(fp->host.nt);
+  *out = fp;
+  return JFX_OK;
+}
+
+void fold_plan_destroy(FoldPlan* fp) {
+  if (!fp) return;
+  if (fp->d_nn) cudaFree(fp->d_nn);
+  if (fp->d_nt) cudaFree(fp->d_nt);
+  delete fp;
+}
+
+int fold_plan_type(const FoldPlan* fp) { return fp ? fp->host.type : 0; }
+
+// 1 = launched, 0 = outside the envelope (caller uses the plain kernel), < 0 = error
+int launch_dmma_fold(cudaStream_t s, const FoldPlan* fp, long long outer, long long inner_real, const double* in,
+                     double* out) {
+  using namespace fold;
+  if (!fp) return 0;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    JFX_CUDA_OK(cudaGetDevice(&dev));
+    JFX_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const bool nn = inner_real != 1;
+  Args q;
+  MapDesc mA, mB;
+  if (!make_launch(fp->host, nn, outer, inner_real, nn ? fp->d_nn : fp->d_nt, in, out, &q, &mA, &mB)) return 0;
+  CUtensorMap tmA, tmB;
+  if (!encode(&tmA, mA) || !encode(&tmB, mB)) return 0;
+  switch (q.variant) {
+    case OUT_NN: return launch_variant<OUT_NN>(s, tmA, tmB, q, sms);
+    case IN_NN: return launch_variant<IN_NN>(s, tmA, tmB, q, sms);
+    case OUT_NT: return launch_variant<OUT_NT>(s, tmA, tmB, q, sms);
+    default: return launch_variant<IN_NT>(s, tmA, tmB, q, sms);
+  }
+}
+
+}  // namespace dmma
+}  // namespace jfx

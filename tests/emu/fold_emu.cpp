@@ -1,0 +1,249 @@
+// Host emulator of the parity-folded tensor-core contraction (jaxfun_b200/csrc/dmma_fold.cuh).
+//
+// Test infrastructure (not product code).  The CUDA kernel in kernels_dense_fold.cu takes ALL of its index math —
+// fragment addresses, the P/Q operand selection, the epilogue butterfly and store addresses, the list of TMA box
+// copies per pipeline stage, the tensor-map geometry and the folded tables — from dmma_fold.cuh.  This program
+// compiles the same header for the host and executes it with a model of the hardware pieces:
+//   * TMA tiled copy: box elements in row-major box order, out-of-bounds (also negative) coordinates zero-filled,
+//     128 B / 64 B swizzle = XOR of shared-memory byte-address bits [4:6] with [7:9] / [4:5] with [7:8]
+//     (the model reproduces the two layouts the GPU-proven dgemm_dmma_tma kernel relies on);
+//   * mma.sync.m8n8k4.f64: A lane (g, t) = A[g][t], B lane (g, t) = B[t][g], D lane (g, t) = D[g][2t], D[g][2t+1].
+// It checks every output element against the plain contraction and that each is written exactly once.
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../../jaxfun_b200/csrc/dmma_fold.cuh"
+
+using namespace jfx::dmma::fold;
+
+static void tma_copy(const MapDesc& m, std::vector<double>& stage, int dst_off, int rank, const int c[4]) {
+  assert(rank == m.rank);
+  assert((dst_off * 8) % (m.swizzle_bytes == 128 ? 1024 : 512) == 0);
+  const unsigned b0n = m.box[0], b1n = m.box[1], b2n = rank > 2 ? m.box[2] : 1, b3n = rank > 3 ? m.box[3] : 1;
+  assert(b0n * 8 <= (unsigned)m.swizzle_bytes);   // inner box extent must fit the swizzle span
+  for (unsigned b3 = 0; b3 < b3n; ++b3)
+    for (unsigned b2 = 0; b2 < b2n; ++b2)
+      for (unsigned b1 = 0; b1 < b1n; ++b1)
+        for (unsigned b0 = 0; b0 < b0n; ++b0) {
+          const long long x[4] = {(long long)c[0] + b0, (long long)c[1] + b1, (long long)c[2] + b2, (long long)c[3] + b3};
+          bool inb = true;
+          for (int d = 0; d < rank; ++d) inb = inb && x[d] >= 0 && x[d] < (long long)m.dims[d];
+          double v = 0.0;
+          if (inb) {
+            long long off = x[0] * 8;
+            for (int d = 1; d < rank; ++d) off += x[d] * (long long)m.strides_bytes[d - 1];
+            memcpy(&v, (const char*)m.base + off, 8);
+          }
+          const unsigned lin = ((b3 * b2n + b2) * b1n + b1) * b0n + b0;
+          unsigned addr = (unsigned)(dst_off + (int)lin) * 8u;
+          if (m.swizzle_bytes == 128) addr ^= ((addr >> 7) & 7u) << 4;
+          else addr ^= ((addr >> 7) & 3u) << 4;
+          stage[addr / 8] = v;
+        }
+}
+
+struct Rec { int slot; double a, b; };
+
+struct Store {
+  std::vector<double>& out;
+  std::vector<int>& cnt;
+  bool vec_allowed;
+  void s2(long long idx, double v0, double v1) {
+    assert(vec_allowed);
+    assert(idx % 2 == 0);
+    s1(idx, v0);
+    s1(idx + 1, v1);
+  }
+  void s1(long long idx, double v) {
+    assert(idx >= 0 && idx < (long long)out.size());
+    out[idx] = v;
+    cnt[idx]++;
+  }
+};
+
+template <int V>
+static void run_tiles(const Args& q, const MapDesc& mA, const MapDesc& mB, std::vector<double>& out, std::vector<int>& cnt) {
+  const int kts = ktiles(q);
+  std::vector<double> stage(3 * TILE);
+  for (int z = 0; z < q.batch; ++z)
+    for (int tm = 0; tm < q.tiles_m; ++tm)
+      for (int tn = 0; tn < q.tiles_n; ++tn) {
+        static double acc[MMA_WARPS][32][8][4][2];
+        memset(acc, 0, sizeof(acc));
+        for (int kt = 0; kt < kts; ++kt) {
+          // poison the stage so that a fragment read of a location no copy wrote is caught
+          for (auto& v : stage) v = 1e300;
+          unsigned bytes = 0;
+          stage_copies<V>(q, kt, tm, tn, z, [&](int map, int dst, int rank, int c0, int c1, int c2, int c3) {
+            const int c[4] = {c0, c1, c2, c3};
+            const MapDesc& m = map == 0 ? mA : mB;
+            tma_copy(m, stage, dst, rank, c);
+            unsigned n = 8;
+            for (int d = 0; d < rank; ++d) n *= m.box[d];
+            bytes += n;
+          });
+          assert(bytes == STAGE_BYTES);   // what the producer announces with expect_tx
+          for (int w = 0; w < MMA_WARPS; ++w) {
+            const int wm = w / WARPS_N, wn = w % WARPS_N;
+            std::vector<Rec> rec[32];
+            for (int lane = 0; lane < 32; ++lane) {
+              double dummy[8][4][2];
+              double* d0base = &dummy[0][0][0];
+              ktile<V>(stage.data(), wm, wn, lane >> 2, lane & 3, q.par_plus, dummy,
+                       [&](double& d0, double& d1, double a, double b) {
+                         assert(&d1 == &d0 + 1);
+                         rec[lane].push_back(Rec{(int)((&d0 - d0base) / 2), a, b});
+                       });
+            }
+            const size_t nrec = rec[0].size();
+            for (size_t r = 0; r < nrec; ++r) {
+              const int slot = rec[0][r].slot;
+              for (int lane = 0; lane < 32; ++lane) {
+                assert(rec[lane].size() == nrec && rec[lane][r].slot == slot);
+                const int g = lane >> 2, t = lane & 3;
+                double d0 = 0, d1 = 0;
+                for (int k = 0; k < 4; ++k) {
+                  const double a = rec[g * 4 + k][r].a;
+                  d0 += a * rec[(2 * t) * 4 + k][r].b;
+                  d1 += a * rec[(2 * t + 1) * 4 + k][r].b;
+                }
+                (&acc[w][lane][0][0][0])[2 * slot] += d0;
+                (&acc[w][lane][0][0][0])[2 * slot + 1] += d1;
+              }
+            }
+          }
+        }
+        Store st{out, cnt, q.vec_ok != 0};
+        for (int w = 0; w < MMA_WARPS; ++w)
+          for (int lane = 0; lane < 32; ++lane)
+            epilogue<V>(q, tm, tn, z, w / WARPS_N, w % WARPS_N, lane >> 2, lane & 3, acc[w][lane], st);
+      }
+}
+
+static int g_fail = 0;
+
+// the check proper: table [rows][cols] (type / par_plus < 0: whatever analyze() finds), array [outer][cols][inner]
+static void check_table(const std::vector<double>& T, int rows, int cols, int type, int par_plus, long long outer,
+                        long long inner, unsigned seed, double tol) {
+  std::mt19937_64 rng(seed ^ 0x9e3779b97f4a7c15ull);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  const FoldInfo fi = analyze(T.data(), rows, cols);
+  if ((type >= 0 && fi.type != type) || (par_plus >= 0 && fi.par_plus != par_plus) || fi.type == FOLD_NONE) {
+    printf("FAIL analyze: type %d par %d -> got %d %d (rows %d cols %d)\n", type, par_plus, fi.type, fi.par_plus, rows, cols);
+    ++g_fail;
+    return;
+  }
+  type = fi.type;
+  par_plus = fi.par_plus;
+  const bool outf = type == FOLD_OUT;
+  const int n_fold = outf ? rows : cols, n_other = outf ? cols : rows;
+  const FoldedTable f = build(T.data(), rows, cols, fi);
+  const int n_in = cols, n_out = rows;
+  std::vector<double> X((size_t)outer * n_in * inner + 2), ref((size_t)outer * n_out * inner);
+  for (auto& v : X) v = U(rng);
+  for (long long o = 0; o < outer; ++o)
+    for (int r = 0; r < n_out; ++r)
+      for (long long i = 0; i < inner; ++i) {
+        long double s = 0;
+        for (int c = 0; c < n_in; ++c) s += (long double)T[(size_t)r * n_in + c] * X[((size_t)o * n_in + c) * inner + i];
+        ref[((size_t)o * n_out + r) * inner + i] = (double)s;
+      }
+  const bool nn = inner > 1;
+  std::vector<double> out(ref.size(), 7e299);
+  std::vector<int> cnt(ref.size(), 0);
+  // 16-byte aligned stand-ins for the device buffers
+  std::vector<double> tbl_buf((nn ? f.nn : f.nt).size() + 2), xbuf(X.size() + 2);
+  double* tbl = tbl_buf.data() + ((reinterpret_cast<uintptr_t>(tbl_buf.data()) & 15) ? 1 : 0);
+  double* xin = xbuf.data() + ((reinterpret_cast<uintptr_t>(xbuf.data()) & 15) ? 1 : 0);
+  memcpy(tbl, (nn ? f.nn : f.nt).data(), (nn ? f.nn : f.nt).size() * 8);
+  memcpy(xin, X.data(), (X.size() - 2) * 8);
+  std::vector<double> cbuf(out.size() + 2);
+  double* cptr = cbuf.data() + ((reinterpret_cast<uintptr_t>(cbuf.data()) & 15) ? 1 : 0);
+  Args q;
+  MapDesc mA, mB;
+  if (!make_launch(f, nn, outer, nn ? inner : 1, tbl, xin, cptr, &q, &mA, &mB)) {
+    printf("FAIL make_launch refused type %d n_fold %d n_other %d outer %lld inner %lld\n", type, n_fold, n_other, outer, inner);
+    ++g_fail;
+    return;
+  }
+  switch (q.variant) {
+    case OUT_NN: run_tiles<OUT_NN>(q, mA, mB, out, cnt); break;
+    case IN_NN: run_tiles<IN_NN>(q, mA, mB, out, cnt); break;
+    case OUT_NT: run_tiles<OUT_NT>(q, mA, mB, out, cnt); break;
+    default: run_tiles<IN_NT>(q, mA, mB, out, cnt); break;
+  }
+  double err = 0, nrm = 0;
+  long long bad_cnt = 0;
+  for (size_t i = 0; i < ref.size(); ++i) {
+    err = std::fmax(err, std::fabs(out[i] - ref[i]));
+    nrm = std::fmax(nrm, std::fabs(ref[i]));
+    if (cnt[i] != 1) ++bad_cnt;
+  }
+  const bool ok = err <= tol * std::fmax(nrm, 1e-300) && bad_cnt == 0;
+  printf("%s variant %d par %d n_fold %3d n_other %3d outer %4lld inner %4lld  err %.2e  miswritten %lld\n", ok ? "ok  " : "FAIL",
+         q.variant, par_plus, n_fold, n_other, outer, inner, err, bad_cnt);
+  if (!ok) ++g_fail;
+}
+
+// synthetic table with the exact symmetry
+static void run_case(int type, int par_plus, int n_fold, int n_other, long long outer, long long inner, unsigned seed) {
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  const bool outf = type == FOLD_OUT;
+  const int rows = outf ? n_fold : n_other, cols = outf ? n_other : n_fold;
+  std::vector<double> T((size_t)rows * cols);
+  for (int k = 0; k < n_other; ++k) {
+    const double s = ((k & 1) == par_plus) ? 1.0 : -1.0;
+    for (int j = 0; j < n_fold / 2; ++j) {
+      const double v = U(rng);
+      if (outf) { T[(size_t)j * cols + k] = v; T[(size_t)(n_fold - 1 - j) * cols + k] = s * v; }
+      else { T[(size_t)k * cols + j] = v; T[(size_t)k * cols + (n_fold - 1 - j)] = s * v; }
+    }
+  }
+  check_table(T, rows, cols, type, par_plus, outer, inner, seed, 1e-13);
+}
+
+int main(int argc, char** argv) {
+  // fold_emu --table file rows cols : a real host table (raw float64, row-major) through the NN and NT variants;
+  // the reference result uses the table as given (slightly asymmetric nodes), tolerance 1e-12 of the result's max norm
+  if (argc == 5 && !strcmp(argv[1], "--table")) {
+    const int rows = atoi(argv[3]), cols = atoi(argv[4]);
+    std::vector<double> T((size_t)rows * cols);
+    FILE* f = fopen(argv[2], "rb");
+    if (!f || fread(T.data(), 8, T.size(), f) != T.size()) { printf("FAIL: cannot read %s\n", argv[2]); return 2; }
+    fclose(f);
+    check_table(T, rows, cols, -1, -1, 2, 34, 11, 1e-12);
+    check_table(T, rows, cols, -1, -1, 37, 1, 12, 1e-12);
+    printf(g_fail ? "FOLD EMU: %d FAILURES\n" : "FOLD EMU: ALL OK\n", g_fail);
+    return g_fail ? 1 : 0;
+  }
+  unsigned seed = 1;
+  const int sizes[][2] = {{8, 8}, {16, 16}, {34, 30}, {64, 64}, {96, 64}, {130, 128}, {256, 256}, {48, 32}, {66, 66}, {192, 192}};
+  for (auto& s : sizes)
+    for (int pp = 0; pp < 2; ++pp) {
+      // NN (inner > 1): OUT needs both extents even; IN allows an odd number of modes
+      run_case(FOLD_OUT, pp, s[0], s[1], 1, 130, seed++);
+      run_case(FOLD_OUT, pp, s[0], s[1], 3, 6, seed++);
+      run_case(FOLD_IN, pp, s[0], s[1], 2, 258, seed++);
+      run_case(FOLD_IN, pp, s[0], s[1] - 1, 1, 2, seed++);
+      // NT (inner == 1)
+      run_case(FOLD_OUT, pp, s[0], s[1], 129, 1, seed++);
+      run_case(FOLD_OUT, pp, s[0], s[1], 5, 1, seed++);
+      run_case(FOLD_IN, pp, s[0], s[1], 260, 1, seed++);
+      run_case(FOLD_IN, pp, s[0], s[1] - 1, 7, 1, seed++);
+    }
+  // tables without the symmetry must be refused
+  {
+    std::vector<double> T(64 * 64);
+    std::mt19937_64 rng(99);
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    for (auto& v : T) v = U(rng);
+    if (analyze(T.data(), 64, 64).type != FOLD_NONE) { printf("FAIL: random table accepted\n"); ++g_fail; }
+  }
+  printf(g_fail ? "FOLD EMU: %d FAILURES\n" : "FOLD EMU: ALL OK\n", g_fail);
+  return g_fail ? 1 : 0;
+}
