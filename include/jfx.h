@@ -162,6 +162,10 @@ int jfx_plan_workspace_bytes(const jfx_plan* plan, size_t* bytes);
 /* Algorithmic work of one execution: flops of dense contractions and the compulsory
    bytes (input read once + output written once). */
 int jfx_plan_work(const jfx_plan* plan, double* flops, double* bytes);
+/* Flops the plan actually issues: table passes whose table has the mirror symmetry of a polynomial basis on
+   symmetric nodes (T[n-1-j, k] = +-(-1)^k T[j, k]) run parity-folded at half the multiply-adds of
+   jfx_plan_work's algorithmic count (set JFX_DMMA_FOLD=0 before plan creation to disable the folding). */
+int jfx_plan_executed_flops(const jfx_plan* plan, double* flops);
 /* Number of kernel launches one jfx_execute enqueues. */
 int jfx_plan_launches(const jfx_plan* plan);
 

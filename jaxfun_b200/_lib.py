@@ -79,6 +79,7 @@ _SIGNATURES = {
     "jfx_plan_shape_out": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "jfx_plan_workspace_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
     "jfx_plan_work": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "jfx_plan_executed_flops": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "jfx_plan_launches": (C.c_int, [C.c_void_p]),
     "jfx_execute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jfx_execute_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

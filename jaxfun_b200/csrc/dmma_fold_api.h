@@ -7,7 +7,7 @@ namespace dmma {
 
 struct FoldPlan;
 
-// JFX_DMMA_FOLD=1 (read once) turns the folded kernel on for eligible table passes.
+// On by default for eligible table passes; JFX_DMMA_FOLD=0 (read at every plan creation) turns it off.
 bool fold_enabled();
 // Analyses the host table [rows][cols]; *out stays null when it has no mirror symmetry (not an error).
 int fold_plan_create(const double* table, int rows, int cols, FoldPlan** out);

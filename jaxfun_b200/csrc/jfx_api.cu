@@ -29,7 +29,7 @@ struct Pass {
   void* d_table = nullptr;  // owned
   bool table_complex = false;
   bool dmma = false;
-  dmma::FoldPlan* fold = nullptr;  // owned; parity-folded tables when the table has the mirror symmetry (JFX_DMMA_FOLD=1)
+  dmma::FoldPlan* fold = nullptr;  // owned; parity-folded tables when the table has the mirror symmetry (default; JFX_DMMA_FOLD=0 disables)
   FastParams fp{};
   FastTables* ft = nullptr;  // owned
 };
@@ -48,6 +48,7 @@ struct jfx_plan {
   bool pair = false;     // the last two passes run as ONE plane-fused launch (kernels_fft2_pair.cu)
   size_t pair_counter_off = 0, pair_ring_off = 0, pair_ring_bytes = 0;
   double flops = 0, bytes = 0;
+  double flops_executed = 0;   // multiply-adds actually issued: folded passes count half
   // host-pointer path (lazy, guarded)
   std::mutex host_mu;
   void* h_in = nullptr;
@@ -173,7 +174,9 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
         if (rc != JFX_OK) return rc;
       }
       const double cm = dtype_is_complex(d->dtype) ? (p.table_complex ? 4.0 : 2.0) : 1.0;
-      pl->flops += 2.0 * cm * (double)p.geom.outer * p.geom.inner * (double)n_in * n_out;
+      const double fl = 2.0 * cm * (double)p.geom.outer * p.geom.inner * (double)n_in * n_out;
+      pl->flops += fl;
+      pl->flops_executed += p.fold ? 0.5 * fl : fl;
     }
     cur[ax] = n_out;
     max_inter = std::max(max_inter, (size_t)prod(cur, 0, d->ndim) * es);
@@ -536,6 +539,13 @@ int jfx_plan_work(const jfx_plan* plan, double* flops, double* bytes) {
   JFX_REQUIRE(plan, JFX_ERR_INVALID, "null argument");
   if (flops) *flops = plan->flops;
   if (bytes) *bytes = plan->bytes;
+  return JFX_OK;
+}
+
+int jfx_plan_executed_flops(const jfx_plan* plan, double* flops) {
+  using namespace jfx;
+  JFX_REQUIRE(plan && flops, JFX_ERR_INVALID, "null argument");
+  *flops = plan->flops_executed;
   return JFX_OK;
 }
 

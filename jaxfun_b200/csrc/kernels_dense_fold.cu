@@ -217,8 +217,8 @@ struct FoldPlan {
 
 // Read at every plan creation (not cached), so one process can hold folded and plain plans side by side.
 bool fold_enabled() {
-  const char* e = getenv("JFX_DMMA_FOLD");
-  return e && e[0] == '1';
+  const char* e = getenv("JFX_DMMA_FOLD");   // default on; JFX_DMMA_FOLD=0 keeps every table pass on dgemm_dmma_tma
+  return !(e && e[0] == '0');
 }
 
 int fold_plan_create(const double* table, int rows, int cols, FoldPlan** out) {

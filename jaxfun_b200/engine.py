@@ -137,6 +137,8 @@ class Plan:
         fl, by = C.c_double(), C.c_double()
         L.check(self._lib.jfx_plan_work(self._h, C.byref(fl), C.byref(by)))
         self.flops, self.bytes = float(fl.value), float(by.value)
+        L.check(self._lib.jfx_plan_executed_flops(self._h, C.byref(fl)))
+        self.flops_executed = float(fl.value)   # parity-folded table passes issue half the algorithmic flops
         self.launches = int(self._lib.jfx_plan_launches(self._h))
         self._ws = {}
 

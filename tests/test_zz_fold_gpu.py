@@ -1,0 +1,77 @@
+"""GPU checks of the parity-folded contraction (`dgemm_dmma_fold`, JFX_DMMA_FOLD=1), each in its own process so that a
+device fault cannot poison the CUDA context of the rest of the suite (the file name sorts last for the same reason).
+
+1. `tools/fold_check` (C, through the C ABI): the same JFX_OP_APPLY plan folded and plain over a matrix of shapes.
+2. The Python API with the fold on, against the NumPy oracle at the 1e-12 bar of BASELINE.json.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/oracle")
+import jaxfun_b200 as jf, jaxfun_oracle as O
+from jaxfun_b200.galerkin.composite import FunctionSpace
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(7)
+def rel(a, b): return np.abs(a - b).max() / np.abs(b).max()
+worst = 0.0
+def check(T, To, c, tag):
+    global worst
+    u = T.backward(torch.from_numpy(c).to(dev)); torch.cuda.synchronize()
+    ur = To.backward(c)
+    e1 = rel(u.cpu().numpy(), ur)
+    ch = T.forward(torch.from_numpy(ur).to(dev)); sp = T.scalar_product(torch.from_numpy(ur).to(dev)); torch.cuda.synchronize()
+    e2 = rel(ch.cpu().numpy(), To.forward(ur)); e3 = rel(sp.cpu().numpy(), To.scalar_product(ur))
+    print(tag, e1, e2, e3); worst = max(worst, e1, e2, e3)
+    assert max(e1, e2, e3) < 1e-12, (tag, e1, e2, e3)
+for n in (16, 32, 64, 96):
+    check(jf.TensorProduct(*[jf.Legendre(n)] * 3), O.TensorProductSpace(*[O.Legendre(n)] * 3), rng.standard_normal((n,) * 3), f"Leg^3 {n}")
+check(jf.TensorProduct(jf.Legendre(128), jf.Legendre(128)), O.TensorProductSpace(O.Legendre(128), O.Legendre(128)),
+      rng.standard_normal((128, 128)), "Leg^2 128")
+check(jf.TensorProduct(jf.Fourier(32), jf.Legendre(48), jf.Chebyshev(40)), O.TensorProductSpace(O.Fourier(32), O.Legendre(48), O.Chebyshev(40)),
+      rng.standard_normal((32, 48, 40)) + 1j * rng.standard_normal((32, 48, 40)), "F x Leg x Cheb(dense 40)")
+check(jf.TensorProduct(jf.Jacobi(32, alpha=1, beta=1), jf.ChebyshevU(64)), O.TensorProductSpace(O.Jacobi(32, alpha=1, beta=1), O.ChebyshevU(64)),
+      rng.standard_normal((32, 64)), "Jacobi(1,1) x ChebU")
+V, Vo = jf.Legendre(64), O.Legendre(64)
+c = rng.standard_normal((300, 64))
+for k in (1, 2):
+    got = V.backward_primitive(torch.from_numpy(c).to(dev), k=k).cpu().numpy()
+    ref = np.stack([Vo.backward_primitive(r, k=k) for r in c])
+    e = rel(got, ref); print("Leg bp", k, e); assert e < 1e-11
+got = V.backward(torch.from_numpy(c).to(dev), N=96).cpu().numpy()
+ref = np.stack([Vo.backward(r, N=96) for r in c])
+e = rel(got, ref); print("Leg padded", e); assert e < 1e-12
+print("FOLD PY OK worst", worst)
+"""
+
+
+def _env(fold):
+    e = dict(os.environ)
+    e["JFX_DMMA_FOLD"] = "1" if fold else "0"
+    return e
+
+
+def test_fold_check_c_abi(cuda):
+    tool = os.path.join(ROOT, "tools", "fold_check")
+    if not os.path.exists(tool):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", tool, tool + ".cu",
+                               "-L" + os.path.join(ROOT, "jaxfun_b200"), "-ljfx", "-Xlinker", "-rpath", "-Xlinker",
+                               "$ORIGIN/../jaxfun_b200"])
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    r = subprocess.run([tool, "--quick"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0 and "FOLD CHECK: ALL OK" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+def test_fold_python_api_vs_oracle(cuda):
+    r = subprocess.run([sys.executable, "-c", _SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600,
+                       env=_env(True), cwd=ROOT)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0 and "FOLD PY OK" in r.stdout, r.stdout[-4000:] + r.stderr[-3000:]

@@ -141,7 +141,7 @@ static double run_case(const Case& c, int time_iters) {
 
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "--quick");
-  g_log = fopen("gpurun_out/fold_check.txt", "w");
+  g_log = fopen(quick ? "gpurun_out/fold_check_quick.txt" : "gpurun_out/fold_check.txt", "w");
   if (jfx_device_count() < 1) { LOG("no CUDA device\n"); return 3; }
   // timing first (the numbers matter most if the box time runs out): 256^3 backward / forward, f64
   for (int fwd = 0; fwd < 2; ++fwd) {
