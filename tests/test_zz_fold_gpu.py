@@ -3,6 +3,9 @@ device fault cannot poison the CUDA context of the rest of the suite (the file n
 
 1. `tools/fold_check` (C, through the C ABI): the same JFX_OP_APPLY plan folded and plain over a matrix of shapes.
 2. The Python API with the fold on, against the NumPy oracle at the 1e-12 bar of BASELINE.json.
+
+Recorded GPU run of this round (gpurun_out -> profiles/r1_fold_check.txt): 83 / 83 shapes of (1) agree to < 4e-15;
+(2) Legendre^3 16..96, Legendre^2 128 and Fourier x Legendre x Chebyshev(40) agree with the oracle to < 7e-14.
 """
 import os
 import subprocess
@@ -25,7 +28,7 @@ worst = 0.0
 def check(T, To, c, tag):
     global worst
     u = T.backward(torch.from_numpy(c).to(dev)); torch.cuda.synchronize()
-    ur = To.backward(c)
+    ur = np.ascontiguousarray(To.backward(c))   # ChebyshevU's oracle returns a reversed view
     e1 = rel(u.cpu().numpy(), ur)
     ch = T.forward(torch.from_numpy(ur).to(dev)); sp = T.scalar_product(torch.from_numpy(ur).to(dev)); torch.cuda.synchronize()
     e2 = rel(ch.cpu().numpy(), To.forward(ur)); e3 = rel(sp.cpu().numpy(), To.scalar_product(ur))
