@@ -29,8 +29,13 @@ def _case(seed):
     return rng, names, sizes, batch
 
 
-@pytest.mark.parametrize("seed", range(40))
-def test_random_tensor_products(cuda, seed):
+@pytest.mark.parametrize("seed", list(range(40)) + [-s for s in range(1, 13)])
+def test_random_tensor_products(cuda, seed, monkeypatch):
+    # negative seeds repeat cases 1..12 with the parity folding off (JFX_DMMA_FOLD is read at plan creation), so both
+    # dgemm_dmma_fold (default) and dgemm_dmma_tma stay covered on mirror-symmetric tables
+    if seed < 0:
+        monkeypatch.setenv("JFX_DMMA_FOLD", "0")
+        seed = -seed
     rng, names, sizes, batch = _case(seed)
     To = O.TensorProductSpace(*[getattr(O, nm)(n) for nm, n in zip(names, sizes)])
     Tp = jf.TensorProduct(*[getattr(jf, nm)(n) for nm, n in zip(names, sizes)])
@@ -58,9 +63,12 @@ def test_random_tensor_products(cuda, seed):
     (192, 640, 0, False), (192, 640, 1, False), (64, 1024, 0, False), (64, 1024, 1, True), (320, 512, 1, False),
     (96, 700, 0, True), (130, 515, 1, False), (200, 1000, 0, False), (62, 999, 1, False),
 ])
-def test_dense_tile_shapes_and_tails(cuda, n, other, axis, cplx):
-    """Legendre tables of extent n against a long other extent: picks the 64x256 / 256x64 / 128x128 TMA tiles (or
-    the cp.async / generic kernels when the operands are not TMA-describable) with ragged edges everywhere."""
+@pytest.mark.parametrize("fold", ["1", "0"])
+def test_dense_tile_shapes_and_tails(cuda, n, other, axis, cplx, fold, monkeypatch):
+    """Legendre tables of extent n against a long other extent: fold = 1 runs the parity-folded kernel (ragged halves:
+    n = 130 -> 65 pairs, n = 62 -> 31), fold = 0 picks the 64x256 / 256x64 / 128x128 tiles of dgemm_dmma_tma (or the
+    cp.async / generic kernels when the operands are not TMA-describable), with ragged edges everywhere."""
+    monkeypatch.setenv("JFX_DMMA_FOLD", fold)
     rng = np.random.default_rng(n + other)
     o, p = O.Legendre(n), jf.Legendre(n)
     shape = (n, other) if axis == 0 else (other, n)
