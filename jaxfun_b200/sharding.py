@@ -72,11 +72,87 @@ class SlabBackend:
         dist.all_to_all_single(out, send)
         return out
 
+    def all_to_all_async(self, send):
+        """Same exchange, not waited for: returns (out, work).  `work.wait()` orders the current stream after the
+        exchange (NCCL runs it on its own stream, so kernels issued in between overlap it); `send` must stay
+        referenced until then."""
+        out = torch.empty_like(send)
+        work = dist.all_to_all_single(out, send, async_op=True)
+        return out, work
 
-def apply_separable_slab(x, sharding: str, backend: SlabBackend, world_size: int):
+
+def slab_chunks() -> int:
+    """Number of chunks of the overlapped exchange (JFX_SLAB_CHUNKS, default 1 = one blocking all-to-all)."""
+    import os
+    try:
+        return max(1, int(os.environ.get("JFX_SLAB_CHUNKS", "1")))
+    except ValueError:
+        return 1
+
+
+def _chunk_bounds(n: int, chunks: int):
+    per = -(-n // max(1, min(chunks, n)))
+    return [(a, min(n, a + per)) for a in range(0, n, per)]
+
+
+def _apply_separable_slab_chunked(x, sharding: str, backend: SlabBackend, world_size: int, chunks: int):
+    """Same result as apply_separable_slab, with the all-to-all cut into chunks that overlap the local passes.
+
+    spectral -> physical (split axis 1, concat axis 0): the phase-1 passes act on axes >= 1, so the local planes of axis 0
+    are independent: chunk c of planes is transformed, packed and sent while chunk c + 1 is being transformed; phase 2
+    (axis 0) starts when every chunk has arrived.
+    physical -> spectral (split axis 0, concat axis 1): phase 1 runs on the whole block; the rows each peer receives are
+    sent in chunks, and chunk c is unpacked and taken through phase 2 (axis 1) while chunk c + 1 is in flight."""
+    P = world_size
+    sh = sharded_axis(sharding)
+    unsharded = [ax for ax in range(x.ndim) if ax != sh]
+    if sh == 0:
+        L = x.shape[0]
+        pending = []
+        y_full = None
+        for a, b in _chunk_bounds(L, chunks):
+            y = backend.apply_axes(x[a:b].contiguous(), unsharded)
+            if y.shape[1] % P != 0:
+                raise ValueError(f"split axis 1 has extent {y.shape[1]}, not divisible by {P} devices")
+            send = backend.pack(y, 1, P)                              # [P, b-a, m1/P, ...]
+            recv, work = backend.all_to_all_async(send)
+            if y_full is None:
+                y_full = recv.new_empty((P, L) + tuple(recv.shape[2:]))
+            pending.append((a, b, send, recv, work))
+        for a, b, send, recv, work in pending:
+            work.wait()
+            y_full[:, a:b] = recv                                     # block p of chunk c = planes a..b of rank p
+        y = y_full.reshape((P * L,) + tuple(y_full.shape[2:]))
+        return backend.apply_axes(y, [0])
+    y = backend.apply_axes(x, unsharded)
+    if y.shape[0] % P != 0:
+        raise ValueError(f"split axis 0 has extent {y.shape[0]}, not divisible by {P} devices")
+    rows = y.shape[0] // P
+    blocks = y.reshape((P, rows) + tuple(y.shape[1:]))
+    bounds = _chunk_bounds(rows, chunks)
+    pending = []
+    for a, b in bounds:
+        send = blocks[:, a:b].contiguous()                            # [P, b-a, n1/P, ...]
+        recv, work = backend.all_to_all_async(send)
+        pending.append((send, recv, work))
+    out = None
+    for (a, b), (send, recv, work) in zip(bounds, pending):
+        work.wait()
+        z = backend.apply_axes(backend.unpack(recv, 1, P), [1])       # [b-a, n1, ...] -> phase 2 along axis 1
+        if out is None:
+            out = z.new_empty((rows,) + tuple(z.shape[1:]))
+        out[a:b] = z
+    return out
+
+
+def apply_separable_slab(x, sharding: str, backend: SlabBackend, world_size: int, chunks: int | None = None):
     """`_apply_separable_spmd_shard_map` (sharding.py:43-105) for one rank's local block `x`.
 
-    Returns the local block of the result, which carries the transposed sharding."""
+    Returns the local block of the result, which carries the transposed sharding.  chunks > 1 (default: JFX_SLAB_CHUNKS)
+    selects the overlapped exchange."""
+    chunks = slab_chunks() if chunks is None else chunks
+    if chunks > 1 and world_size > 1:
+        return _apply_separable_slab_chunked(x, sharding, backend, world_size, chunks)
     dim = x.ndim
     sh = sharded_axis(sharding)
     unsharded = [ax for ax in range(dim) if ax != sh]

@@ -50,7 +50,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, names, N, seed, q):
+def _worker(rank, world, port, names, N, seed, q, chunks=1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -62,27 +62,32 @@ def _worker(rank, world, port, names, N, seed, q):
         c = rng.standard_normal(N) + (1j * rng.standard_normal(N) if "F" in names else 0)
         u_ref = T.backward(c)
         c_loc = torch.from_numpy(np.ascontiguousarray(S.local_block(c, S.SPECTRAL, rank, world)))
-        u_loc = S.apply_separable_slab(c_loc, S.SPECTRAL, OracleBackend(spaces, "backward"), world)
+        u_loc = S.apply_separable_slab(c_loc, S.SPECTRAL, OracleBackend(spaces, "backward"), world, chunks)
         e1 = np.abs(u_loc.numpy() - S.local_block(u_ref, S.PHYSICAL, rank, world)).max()
-        c_back = S.apply_separable_slab(u_loc, S.PHYSICAL, OracleBackend(spaces, "forward"), world)
+        c_back = S.apply_separable_slab(u_loc, S.PHYSICAL, OracleBackend(spaces, "forward"), world, chunks)
         e2 = np.abs(c_back.numpy() - S.local_block(c, S.SPECTRAL, rank, world)).max()
-        sp_loc = S.apply_separable_slab(u_loc, S.PHYSICAL, OracleBackend(spaces, "scalar_product"), world)
+        sp_loc = S.apply_separable_slab(u_loc, S.PHYSICAL, OracleBackend(spaces, "scalar_product"), world, chunks)
         e3 = np.abs(sp_loc.numpy() - S.local_block(T.scalar_product(u_ref), S.SPECTRAL, rank, world)).max()
         q.put((rank, float(e1), float(e2), float(e3), tuple(u_loc.shape), tuple(c_back.shape)))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("names,N", [("CC", (8, 12)), ("FL", (8, 8)), ("CCC", (8, 8, 6)), ("FCL", (8, 12, 5)),
-                                      ("FFL", (8, 4, 7))])
-def test_slab_roundtrip_gloo(world, names, N):
+_CASES = [("CC", (8, 12)), ("FL", (8, 8)), ("CCC", (8, 8, 6)), ("FCL", (8, 12, 5)), ("FFL", (8, 4, 7))]
+
+
+@pytest.mark.parametrize("world,chunks,names,N",
+                         [(w, 1, nm, N) for w in (2, 4) for nm, N in _CASES] +
+                         [(2, 2, "CC", (8, 12)), (2, 3, "FCL", (8, 12, 5)), (4, 2, "CCC", (8, 8, 6)), (2, 3, "FFL", (8, 4, 7))])
+def test_slab_roundtrip_gloo(world, chunks, names, N):
+    """chunks > 1: the overlapped exchange (chunked all-to-all interleaved with the local passes; ragged last chunk when
+    the chunk count does not divide the local extent) must give the same blocks as the single all-to-all."""
     if any(n % world for n in N[:2]):
         pytest.skip("extent not divisible")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, names, N, 11, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, names, N, 11, q, chunks)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
