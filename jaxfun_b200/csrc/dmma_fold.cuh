@@ -37,7 +37,11 @@ namespace jfx {
 namespace dmma {
 namespace fold {
 
-enum Variant { OUT_NN = 0, IN_NN = 1, OUT_NT = 2, IN_NT = 3 };
+// CPLX_NT is not a fold: complex interleaved data on a LAST table axis, any real table.  It reuses the OUT_NT main loop —
+// the LDS.128 that fetches (even, odd) there fetches (re, im) of one complex coefficient here, the "plus" accumulators
+// collect the real part and the "minus" accumulators the imaginary part against the SAME table rows — and the IN_NT
+// epilogue, which interleaves the two accumulator groups into consecutive columns.
+enum Variant { OUT_NN = 0, IN_NN = 1, OUT_NT = 2, IN_NT = 3, CPLX_NT = 4 };
 enum FoldType { FOLD_NONE = 0, FOLD_OUT = 1, FOLD_IN = 2 };
 
 constexpr int BK = 16, BM = 128, BN = 128, WM = 64, WN = 32;
@@ -83,6 +87,10 @@ struct Args {
 // ------------------------------------------------------------------------------------------------
 template <int V, class MMA>
 JFX_HD void ktile(const double* S, int wm, int wn, int g, int t, int par_plus, double (&acc)[8][4][2], MMA&& mma) {
+  if constexpr (V == CPLX_NT) {
+    ktile<OUT_NT>(S, wm, wn, g, t, 0, acc, mma);
+    return;
+  }
   const double* R0 = S;
   const double* R1 = S + TILE;
   const double* R2 = S + 2 * TILE;
@@ -163,6 +171,23 @@ JFX_HD void put2(ST& st, bool vec, long long idx, double v0, double v1, bool ok0
 template <int V, class ST>
 JFX_HD void epilogue(const Args& q, int tile_m, int tile_n, long long z, int wm, int wn, int g, int t,
                      const double (&acc)[8][4][2], ST&& st) {
+  if constexpr (V == CPLX_NT) {
+    // rows follow the OUT_NT main loop (permuted by rho); columns: (re, im) pairs = the IN_NT interleave with par_plus = 0
+    const bool vec = q.vec_ok != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = tile_m * BM + wm * WM + i * 8 + rho(g);
+      if (row >= q.M) continue;
+      const long long rb = (long long)row * q.ldc;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k0 = 2 * (tile_n * HALF_PER_TILE + wn * 16 + j * 8 + 2 * t);
+        put2(st, vec, rb + k0, acc[i][j][0], acc[i][j + 2][0], k0 < q.n_other, k0 + 1 < q.n_other);
+        put2(st, vec, rb + k0 + 2, acc[i][j][1], acc[i][j + 2][1], k0 + 2 < q.n_other, k0 + 3 < q.n_other);
+      }
+    }
+    return;
+  }
   const bool vec = q.vec_ok != 0;
   const int pp = q.par_plus, pq = 1 - q.par_plus;
   if constexpr (V == OUT_NN) {
@@ -256,7 +281,7 @@ JFX_HD void stage_copies(const Args& q, int kt, int tile_m, int tile_n, int z, I
       issue(1, TILE + sub * 128, 3, n0 + 8 * sub, k0, z, 0);
       issue(1, 2 * TILE + sub * 128, 3, n0 + 8 * sub, q.n_fold - 16 - k0, z, 0);
     }
-  } else if constexpr (V == OUT_NT) {
+  } else if constexpr (V == OUT_NT || V == CPLX_NT) {
     issue(0, 0, 2, 2 * k0, m0, 0, 0);
     issue(0, TILE, 2, 2 * k0 + 16, m0, 0, 0);
     issue(1, 2 * TILE, 2, k0, n0, 0, 0);
@@ -441,6 +466,52 @@ inline bool make_launch(const FoldedTable& f, bool nn, long long outer, long lon
 }
 
 inline int ktiles(const Args& q) { return (q.kfold + BK - 1) / BK; }
+
+// ---- CPLX_NT: complex interleaved rows [outer][n_in] (as 2 n_in doubles) times a real table [n_out][n_in] ------------
+struct CplxTable {
+  int n_in = 0, n_out = 0, rows_nt = 0, ld = 0;
+  std::vector<double> nt;   // [rows_nt][ld]: row c' holds T[idx(c')][:] for both accumulator groups
+};
+
+inline CplxTable build_cplx(const double* T, int n_out, int n_in) {
+  CplxTable c;
+  c.n_in = n_in; c.n_out = n_out;
+  c.rows_nt = (n_out + HALF_PER_TILE - 1) / HALF_PER_TILE * 128;
+  c.ld = (n_in + 1) & ~1;
+  if (c.ld < 2) c.ld = 2;
+  c.nt.assign((size_t)c.rows_nt * c.ld, 0.0);
+  for (int r = 0; r < c.rows_nt; ++r) {
+    int idx, grp;
+    nt_row(r, &idx, &grp);
+    if (idx >= n_out) continue;
+    for (int k = 0; k < n_in; ++k) c.nt[(size_t)r * c.ld + k] = T[(long long)idx * n_in + k];
+  }
+  return c;
+}
+
+inline bool make_launch_cplx(const CplxTable& c, long long outer, const double* table, const double* X, double* C, Args* q,
+                             MapDesc* mA, MapDesc* mB) {
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(table) || !al16(X) || !al16(C)) return false;
+  if (outer <= 0 || outer >= (1ll << 31) || c.n_in < 1 || c.n_out < 1) return false;
+  Args a{};
+  a.variant = CPLX_NT;
+  a.par_plus = 0;
+  a.n_fold = 0; a.half = 0;
+  a.n_other = 2 * c.n_out;            // output columns (doubles) per row
+  a.kfold = c.n_in;                   // complex coefficients per row = reduction length per accumulator group
+  a.C = C;
+  a.M = (int)outer; a.N = c.rows_nt;
+  a.tiles_m = (int)((outer + BM - 1) / BM); a.tiles_n = c.rows_nt / BN; a.batch = 1;
+  a.ldc = 2ll * c.n_out; a.strideC = 0;
+  a.vec_ok = 1;                       // complex elements are 16 bytes: every (re, im) pair is an aligned double2
+  *mA = MapDesc{X, 2, {(unsigned long long)(2 * c.n_in), (unsigned long long)outer, 1, 1},
+                {(unsigned long long)c.n_in * 16, 0, 0}, {BK, BM, 1, 1}, 128};
+  *mB = MapDesc{table, 2, {(unsigned long long)c.n_in, (unsigned long long)c.rows_nt, 1, 1},
+                {(unsigned long long)c.ld * 8, 0, 0}, {BK, BN, 1, 1}, 128};
+  *q = a;
+  return true;
+}
 
 }  // namespace fold
 }  // namespace dmma

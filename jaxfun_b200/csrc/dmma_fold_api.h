@@ -18,5 +18,13 @@ int fold_plan_type(const FoldPlan* fp);   // 0 none, 1 OUT (backward-like), 2 IN
 int launch_dmma_fold(cudaStream_t s, const FoldPlan* fp, long long outer, long long inner_real, const double* in,
                      double* out);
 
+// Complex interleaved data on a LAST table axis (any real table): one NT launch with (re, im) accumulator groups
+// instead of the NN order with two real columns per batch.  Opt-in: JFX_CPLX_NT=1 at plan creation.
+struct CplxPlan;
+bool cplx_nt_enabled();
+int cplx_plan_create(const double* table, int n_out, int n_in, CplxPlan** out);
+void cplx_plan_destroy(CplxPlan* cp);
+int launch_dmma_cplx_nt(cudaStream_t s, const CplxPlan* cp, long long outer, const double* in, double* out);
+
 }  // namespace dmma
 }  // namespace jfx

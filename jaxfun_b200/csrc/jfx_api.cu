@@ -29,6 +29,7 @@ struct Pass {
   void* d_table = nullptr;  // owned
   bool table_complex = false;
   bool dmma = false;
+  dmma::CplxPlan* cplx = nullptr;  // owned; complex data on a last table axis as one NT launch (JFX_CPLX_NT=1)
   dmma::FoldPlan* fold = nullptr;  // owned; parity-folded tables when the table has the mirror symmetry (default; JFX_DMMA_FOLD=0 disables)
   FastParams fp{};
   FastTables* ft = nullptr;  // owned
@@ -58,6 +59,7 @@ struct jfx_plan {
     for (auto& p : passes) {
       if (p.d_table) cudaFree(p.d_table);
       if (p.fold) jfx::dmma::fold_plan_destroy(p.fold);
+      if (p.cplx) jfx::dmma::cplx_plan_destroy(p.cplx);
       if (p.ft) jfx::fast_tables_destroy(p.ft);
     }
     if (h_in) cudaFree(h_in);
@@ -169,7 +171,11 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
                   (long long)p.geom.inner);
     if (!p.fast) {
       p.dmma = table_apply_uses_dmma(p.geom, d->dtype, p.table_complex);
-      if (p.dmma && dmma::fold_enabled() && a.table != nullptr) {
+      if (p.dmma && d->dtype == JFX_C128 && p.geom.inner == 1 && a.table != nullptr && dmma::cplx_nt_enabled()) {
+        int rc = dmma::cplx_plan_create((const double*)a.table, n_out, n_in, &p.cplx);
+        if (rc != JFX_OK) return rc;
+      }
+      if (p.dmma && !p.cplx && dmma::fold_enabled() && a.table != nullptr) {
         int rc = dmma::fold_plan_create((const double*)a.table, n_out, n_in, &p.fold);
         if (rc != JFX_OK) return rc;
       }
@@ -238,6 +244,11 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
 
 static int run_pass_geom(cudaStream_t s, const Pass& p, const AxisGeom& g, int dtype, const void* src, void* dst) {
   if (p.fast) return launch_fast_axis(s, g, dtype, p.fp, p.ft, src, dst);
+  if (p.cplx && g.outer * g.n_out != 0) {
+    const int rc = dmma::launch_dmma_cplx_nt(s, p.cplx, g.outer, (const double*)src, (double*)dst);
+    if (rc < 0) return rc;
+    if (rc == 1) return JFX_OK;
+  }
   if (p.fold && g.outer * g.inner * g.n_out != 0) {
     const int rc = dmma::launch_dmma_fold(s, p.fold, g.outer, g.inner * (dtype == JFX_C128 ? 2 : 1), (const double*)src,
                                           (double*)dst);

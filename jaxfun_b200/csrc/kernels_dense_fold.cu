@@ -277,5 +277,60 @@ int launch_dmma_fold(cudaStream_t s, const FoldPlan* fp, long long outer, long l
   }
 }
 
+// ---- complex data on a last table axis (CPLX_NT) ---------------------------------------------------
+struct CplxPlan {
+  fold::CplxTable host;   // geometry (host copy of the table released after the upload)
+  double* d_nt = nullptr;
+};
+
+// opt-in until it has run on a GPU (JFX_CPLX_NT=1, read at plan creation); without it such passes run the NN order
+// with two real columns per batch, which is correct but wastes 63 / 64 of every tile
+bool cplx_nt_enabled() {
+  const char* e = getenv("JFX_CPLX_NT");
+  return e && e[0] == '1';
+}
+
+int cplx_plan_create(const double* table, int n_out, int n_in, CplxPlan** out) {
+  *out = nullptr;
+  if (n_out < 1 || n_in < 1) return JFX_OK;
+  CplxPlan* cp = new CplxPlan;
+  cp->host = fold::build_cplx(table, n_out, n_in);
+  const size_t b = cp->host.nt.size() * sizeof(double);
+  if (cudaMalloc(&cp->d_nt, b) != cudaSuccess ||
+      cudaMemcpy(cp->d_nt, cp->host.nt.data(), b, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    cplx_plan_destroy(cp);
+    set_error("cplx_plan_create: device allocation / upload of the table failed");
+    return JFX_ERR_CUDA;
+  }
+  std::vector<double>().swap(cp->host.nt);
+  *out = cp;
+  return JFX_OK;
+}
+
+void cplx_plan_destroy(CplxPlan* cp) {
+  if (!cp) return;
+  if (cp->d_nt) cudaFree(cp->d_nt);
+  delete cp;
+}
+
+// rows = complex lines [outer][n_in]; 1 = launched, 0 = outside the envelope, < 0 = error
+int launch_dmma_cplx_nt(cudaStream_t s, const CplxPlan* cp, long long outer, const double* in, double* out) {
+  using namespace fold;
+  if (!cp) return 0;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    JFX_CUDA_OK(cudaGetDevice(&dev));
+    JFX_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  Args q;
+  MapDesc mA, mB;
+  if (!make_launch_cplx(cp->host, outer, cp->d_nt, in, out, &q, &mA, &mB)) return 0;
+  CUtensorMap tmA, tmB;
+  if (!encode(&tmA, mA) || !encode(&tmB, mB)) return 0;
+  return launch_variant<CPLX_NT>(s, tmA, tmB, q, sms);
+}
+
 }  // namespace dmma
 }  // namespace jfx

@@ -207,6 +207,46 @@ static void run_case(int type, int par_plus, int n_fold, int n_other, long long 
   check_table(T, rows, cols, type, par_plus, outer, inner, seed, 1e-13);
 }
 
+// CPLX_NT: complex interleaved rows times an arbitrary real table
+static void run_cplx_case(int n_out, int n_in, long long outer, unsigned seed) {
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  std::vector<double> T((size_t)n_out * n_in), X((size_t)outer * n_in * 2), ref((size_t)outer * n_out * 2);
+  for (auto& v : T) v = U(rng);
+  for (auto& v : X) v = U(rng);
+  for (long long o = 0; o < outer; ++o)
+    for (int r = 0; r < n_out; ++r)
+      for (int c = 0; c < 2; ++c) {
+        long double s = 0;
+        for (int k = 0; k < n_in; ++k) s += (long double)T[(size_t)r * n_in + k] * X[((size_t)o * n_in + k) * 2 + c];
+        ref[((size_t)o * n_out + r) * 2 + c] = (double)s;
+      }
+  const CplxTable ct = build_cplx(T.data(), n_out, n_in);
+  std::vector<double> out(ref.size(), 7e299);
+  std::vector<int> cnt(ref.size(), 0);
+  std::vector<double> tb(ct.nt.size() + 2), xb(X.size() + 2), cb(out.size() + 2);
+  double* tbl = tb.data() + ((reinterpret_cast<uintptr_t>(tb.data()) & 15) ? 1 : 0);
+  double* xin = xb.data() + ((reinterpret_cast<uintptr_t>(xb.data()) & 15) ? 1 : 0);
+  double* cptr = cb.data() + ((reinterpret_cast<uintptr_t>(cb.data()) & 15) ? 1 : 0);
+  memcpy(tbl, ct.nt.data(), ct.nt.size() * 8);
+  memcpy(xin, X.data(), X.size() * 8);
+  Args q;
+  MapDesc mA, mB;
+  if (!make_launch_cplx(ct, outer, tbl, xin, cptr, &q, &mA, &mB)) { printf("FAIL make_launch_cplx\n"); ++g_fail; return; }
+  run_tiles<CPLX_NT>(q, mA, mB, out, cnt);
+  double err = 0, nrm = 0;
+  long long bad = 0;
+  for (size_t i = 0; i < ref.size(); ++i) {
+    err = std::fmax(err, std::fabs(out[i] - ref[i]));
+    nrm = std::fmax(nrm, std::fabs(ref[i]));
+    if (cnt[i] != 1) ++bad;
+  }
+  const bool ok = err <= 1e-13 * std::fmax(nrm, 1e-300) && bad == 0;
+  printf("%s variant 4 (complex last axis) n_out %3d n_in %3d rows %4lld  err %.2e  miswritten %lld\n", ok ? "ok  " : "FAIL", n_out,
+         n_in, outer, err, bad);
+  if (!ok) ++g_fail;
+}
+
 int main(int argc, char** argv) {
   // fold_emu --table file rows cols : a real host table (raw float64, row-major) through the NN and NT variants;
   // the reference result uses the table as given (slightly asymmetric nodes), tolerance 1e-12 of the result's max norm
@@ -236,6 +276,13 @@ int main(int argc, char** argv) {
       run_case(FOLD_IN, pp, s[0], s[1], 260, 1, seed++);
       run_case(FOLD_IN, pp, s[0], s[1] - 1, 7, 1, seed++);
     }
+  {
+    const int cs[][2] = {{8, 8}, {16, 16}, {30, 34}, {63, 64}, {64, 48}, {96, 96}, {130, 128}, {256, 256}, {65, 7}};
+    for (auto& c : cs) {
+      run_cplx_case(c[0], c[1], 1, seed++);
+      run_cplx_case(c[0], c[1], 131, seed++);
+    }
+  }
   // tables without the symmetry must be refused
   {
     std::vector<double> T(64 * 64);

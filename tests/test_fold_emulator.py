@@ -25,11 +25,13 @@ def emu(tmp_path_factory):
 
 
 def test_synthetic_tables_all_variants(emu):
-    """160 cases: OUT/IN fold x NN/NT order x both parities x sizes with ragged tiles, odd mode counts, padding."""
+    """160 fold cases (OUT/IN fold x NN/NT order x both parities x sizes with ragged tiles, odd mode counts, padding) and
+    18 cases of the complex-last-axis variant CPLX_NT (arbitrary real table, odd extents)."""
     r = subprocess.run([emu], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "FOLD EMU: ALL OK" in r.stdout
-    assert r.stdout.count("\nok  ") + r.stdout.startswith("ok  ") >= 160
+    assert r.stdout.count("\nok  ") + r.stdout.startswith("ok  ") >= 178
+    assert r.stdout.count("variant 4 (complex last axis)") == 18
 
 
 @pytest.mark.parametrize("space,n", [("Legendre", 64), ("Legendre", 128), ("ChebyshevU", 64), ("Ultraspherical", 32),

@@ -78,3 +78,41 @@ def test_fold_python_api_vs_oracle(cuda):
                        env=_env(True), cwd=ROOT)
     print(r.stdout[-4000:])
     assert r.returncode == 0 and "FOLD PY OK" in r.stdout, r.stdout[-4000:] + r.stderr[-3000:]
+
+
+_CPLX_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/oracle")
+import jaxfun_b200 as jf, jaxfun_oracle as O
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(11)
+def rel(a, b): return np.abs(a - b).max() / np.abs(b).max()
+def cplx(shape): return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+cases = [((jf.Fourier(32), jf.Legendre(48)), (O.Fourier(32), O.Legendre(48)), (32, 48)),
+         ((jf.Fourier(16), jf.Fourier(32), jf.Legendre(64)), (O.Fourier(16), O.Fourier(32), O.Legendre(64)), (16, 32, 64)),
+         ((jf.Fourier(64), jf.Jacobi(40, alpha=0.5, beta=-0.5)), (O.Fourier(64), O.Jacobi(40, alpha=0.5, beta=-0.5)), (64, 40)),
+         ((jf.Fourier(8), jf.Chebyshev(36)), (O.Fourier(8), O.Chebyshev(36)), (8, 36))]
+for sp, so, shape in cases:
+    T, To = jf.TensorProduct(*sp), O.TensorProductSpace(*so)
+    c = cplx(shape)
+    ur = np.ascontiguousarray(To.backward(c))
+    e1 = rel(T.backward(torch.from_numpy(c).to(dev)).cpu().numpy(), ur)
+    e2 = rel(T.forward(torch.from_numpy(ur).to(dev)).cpu().numpy(), To.forward(ur))
+    e3 = rel(T.scalar_product(torch.from_numpy(ur).to(dev)).cpu().numpy(), To.scalar_product(ur))
+    print(shape, e1, e2, e3); assert max(e1, e2, e3) < 1e-12
+V, Vo = jf.Legendre(128), O.Legendre(128)
+c = cplx((777, 128))
+e = rel(V.backward(torch.from_numpy(c).to(dev)).cpu().numpy(), Vo.backward(c, axis=-1)); print("rows", e); assert e < 1e-12
+print("CPLX NT OK")
+"""
+
+
+@pytest.mark.xfail(strict=False, reason="CPLX_NT (complex data on a last table axis as one NT launch, JFX_CPLX_NT=1) was written after "
+                                        "the round's GPU budget was spent: checked by the host emulator only, opt-in until this passes")
+def test_complex_last_axis_nt_variant(cuda):
+    e = dict(os.environ)
+    e["JFX_CPLX_NT"] = "1"
+    r = subprocess.run([sys.executable, "-c", _CPLX_SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600,
+                       env=e, cwd=ROOT)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "CPLX NT OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
