@@ -174,6 +174,21 @@ int jfx_plan_launches(const jfx_plan* plan);
    `in` is never written; `out` must not alias `in` or `workspace`. */
 int jfx_execute(const jfx_plan* plan, void* stream, const void* in, void* out, void* workspace);
 
+/* Slab exchange fused into the transform (sharding.py:83-103 of the reference: pack + lax.all_to_all(tiled=True) [+ the
+   concatenation]): the plan's final pass writes its result rows straight into the receive buffers of all `parts` GPUs
+   of the box.  peer_out[p] = device pointer, valid on THIS device (peer-mapped / symmetric memory over NVLink), of rank
+   p's receive buffer.  For a 3-D result [s0, s1, s2]:
+     split_axis 1 (spectral -> physical): rank p receives out[:, p*s1/P:(p+1)*s1/P, :] as block `rank` of its
+                                          [P, s0, s1/P, s2] buffer  == the [P*s0, s1/P, s2] array phase 2 transforms;
+     split_axis 0 (physical -> spectral): rank p receives out[p*s0/P:(p+1)*s0/P, :, :] as columns rank*s1 .. of its
+                                          [s0/P, P*s1, s2] buffer   (the unpack is included).
+   The caller orders the exchange with a barrier across the ranks after this call (and double-buffers the receive side).
+   Supported when the final pass is a parity-folded fp64 table pass along the last axis (jfx_plan_scatter_supported);
+   otherwise JFX_ERR_UNSUPPORTED and the caller uses jfx_execute + jfx_slab_pack/unpack + its own all-to-all. */
+int jfx_plan_scatter_supported(const jfx_plan* plan, int parts, int split_axis);
+int jfx_execute_scatter(const jfx_plan* plan, void* stream, const void* in, void* const* peer_out, int parts, int rank,
+                        int split_axis, void* workspace);
+
 /* Convenience for host callers (the reference-facing e2e path): copies `in` (host) to the
    device, runs the plan and copies the result back into `out` (host); synchronises `stream`.
    Device buffers are owned and cached by the plan (first call allocates). */

@@ -81,6 +81,9 @@ _SIGNATURES = {
     "jfx_plan_work": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "jfx_plan_executed_flops": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "jfx_plan_launches": (C.c_int, [C.c_void_p]),
+    "jfx_plan_scatter_supported": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "jfx_execute_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p]),
     "jfx_execute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jfx_execute_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jfx_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),

@@ -261,6 +261,68 @@ JFX_HD void epilogue(const Args& q, int tile_m, int tile_n, long long z, int wm,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Scatter epilogue of the NT variants: the contraction writes its result straight into the receive buffers of the slab
+// exchange on every GPU (peer-mapped pointers over NVLink), so that pack + all-to-all (+ unpack) of sharding.py:83-89 of
+// the reference become the stores of this kernel.  The output rows of the pass are (a, b) = (row / B, row % B):
+//   mode 1 (spectral -> physical, split b): rank p = b / (B/P) receives the row at  [src * A + a][b % (B/P)]   of [P*A][B/P][cols]
+//   mode 2 (physical -> spectral, split a): rank p = a / (A/P) receives the row at  [a % (A/P)][src * B + b]    of [A/P][P*B][cols]
+// i.e. exactly what lax.all_to_all(split_axis, concat_axis, tiled=True) leaves on rank p (mode 2 includes the unpack).
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_PEERS = 8;
+struct Scatter {
+  int mode, parts, src, A, B;
+  int pad_;
+  double* peer[MAX_PEERS];
+};
+
+JFX_HD void scatter_row(const Scatter& s, int row, int* dest, long long* drow) {
+  const int a = row / s.B, b = row - a * s.B;
+  if (s.mode == 1) {
+    const int bp = s.B / s.parts;
+    *dest = b / bp;
+    *drow = ((long long)s.src * s.A + a) * bp + (b - *dest * bp);
+  } else {
+    const int ap = s.A / s.parts;
+    *dest = a / ap;
+    *drow = (long long)(a - *dest * ap) * ((long long)s.B * s.parts) + (long long)s.src * s.B + b;
+  }
+}
+
+// mk(dest) returns the store object (s1 / s2 as in epilogue) of rank `dest`'s buffer
+template <int V, class MK>
+JFX_HD void epilogue_scatter(const Args& q, const Scatter& sc, int tile_m, int tile_n, int wm, int wn, int g, int t,
+                             const double (&acc)[8][4][2], MK&& mk) {
+  static_assert(V == OUT_NT || V == IN_NT, "scatter epilogue: NT variants only");
+  const bool vec = q.vec_ok != 0;
+  const int pp = q.par_plus;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = tile_m * BM + wm * WM + i * 8 + (V == OUT_NT ? rho(g) : g);
+    if (row >= q.M) continue;
+    int dest;
+    long long drow;
+    scatter_row(sc, row, &dest, &drow);
+    auto st = mk(dest);
+    const long long rb = drow * q.ldc;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = tile_n * HALF_PER_TILE + wn * 16 + j * 8 + 2 * t;
+      const double p0 = acc[i][j][0], p1 = acc[i][j][1], q0 = acc[i][j + 2][0], q1 = acc[i][j + 2][1];
+      if constexpr (V == OUT_NT) {
+        const bool ok0 = c < q.half, ok1 = c + 1 < q.half;
+        put2(st, vec, rb + c, p0 + q0, p1 + q1, ok0, ok1);
+        put2(st, vec, rb + (q.n_fold - 2 - c), p1 - q1, p0 - q0, ok1, ok0);
+      } else {
+        const double e0 = pp ? q0 : p0, o0 = pp ? p0 : q0, e1 = pp ? q1 : p1, o1 = pp ? p1 : q1;
+        const int k0 = 2 * c;
+        put2(st, vec, rb + k0, e0, o0, k0 < q.n_other, k0 + 1 < q.n_other);
+        put2(st, vec, rb + k0 + 2, e1, o1, k0 + 2 < q.n_other, k0 + 3 < q.n_other);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA copies of one pipeline stage.  issue(map, dst_offset_in_doubles, rank, c0, c1, c2, c3); map 0 = "A" tensor map
 // (K-contiguous operand of the GEMM), 1 = "B" tensor map.  kt = k-tile of the folded problem.
 // ------------------------------------------------------------------------------------------------

@@ -18,6 +18,12 @@ int fold_plan_type(const FoldPlan* fp);   // 0 none, 1 OUT (backward-like), 2 IN
 int launch_dmma_fold(cudaStream_t s, const FoldPlan* fp, long long outer, long long inner_real, const double* in,
                      double* out);
 
+// Last-axis (NT) folded pass whose result rows (a, b) = (row / B, row % B) are written straight into the slab-exchange
+// receive buffers of `parts` GPUs (peer-mapped pointers): mode 1 splits b (spectral -> physical), mode 2 splits a
+// (physical -> spectral, including the unpack).  1 = launched, 0 = not applicable, < 0 = error.
+int launch_dmma_fold_scatter(cudaStream_t s, const FoldPlan* fp, long long outer, const double* in, int mode, int parts,
+                             int src, int A, int B, double* const* peers);
+
 // Complex interleaved data on a LAST table axis (any real table): one NT launch with (re, im) accumulator groups
 // instead of the NN order with two real columns per batch.  Opt-in: JFX_CPLX_NT=1 at plan creation.
 struct CplxPlan;

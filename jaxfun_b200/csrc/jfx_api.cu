@@ -571,6 +571,58 @@ int jfx_plan_launches(const jfx_plan* plan) {
   return (int)plan->passes.size();
 }
 
+// ---- slab exchange fused into the last pass ----------------------------------------------------------
+static int scatter_geometry(const jfx_plan* pl, int parts, int split_axis, int* mode, int* A, int* B) {
+  using namespace jfx;
+  JFX_REQUIRE(pl, JFX_ERR_INVALID, "null plan");
+  JFX_REQUIRE(pl->ndim == 3 && !pl->passes.empty(), JFX_ERR_UNSUPPORTED, "scatter execution: 3-D plans only");
+  JFX_REQUIRE(parts >= 1 && parts <= 8, JFX_ERR_UNSUPPORTED, "scatter execution: 1..8 peers");
+  JFX_REQUIRE(split_axis == 0 || split_axis == 1, JFX_ERR_INVALID, "split_axis must be 0 or 1");
+  JFX_REQUIRE(pl->slabs == 1 && !pl->pair, JFX_ERR_UNSUPPORTED, "scatter execution: plain pass sequence only");
+  const Pass& last = pl->passes.back();
+  JFX_REQUIRE(last.axis == 2 && last.fold != nullptr && pl->desc.dtype == JFX_F64, JFX_ERR_UNSUPPORTED,
+              "scatter execution needs a parity-folded fp64 table pass along the last axis as the final pass");
+  *A = (int)pl->shape_out[0];
+  *B = (int)pl->shape_out[1];
+  *mode = split_axis == 1 ? 1 : 2;
+  JFX_REQUIRE((split_axis == 1 ? *B : *A) % parts == 0, JFX_ERR_INVALID, "split axis %d of extent %d is not divisible by %d",
+              split_axis, split_axis == 1 ? *B : *A, parts);
+  return JFX_OK;
+}
+
+int jfx_plan_scatter_supported(const jfx_plan* plan, int parts, int split_axis) {
+  int mode, A, B;
+  return scatter_geometry(plan, parts, split_axis, &mode, &A, &B) == JFX_OK ? 1 : 0;
+}
+
+int jfx_execute_scatter(const jfx_plan* plan, void* stream, const void* in, void* const* peer_out, int parts, int rank,
+                        int split_axis, void* workspace) {
+  using namespace jfx;
+  JFX_REQUIRE(plan && in && peer_out, JFX_ERR_INVALID, "null argument");
+  int mode, A, B;
+  int rc = scatter_geometry(plan, parts, split_axis, &mode, &A, &B);
+  if (rc != JFX_OK) return rc;
+  JFX_REQUIRE(rank >= 0 && rank < parts, JFX_ERR_INVALID, "rank %d outside 0..%d", rank, parts - 1);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t np = plan->passes.size();
+  JFX_REQUIRE(np == 1 || workspace != nullptr, JFX_ERR_INVALID, "plan needs a %zu byte workspace", plan->ws_bytes);
+  char* w0 = (char*)workspace;
+  char* w1 = w0 + plan->buf_bytes;
+  const void* src = in;
+  for (size_t i = 0; i + 1 < np; ++i) {
+    void* dst = (void*)((i & 1) ? w1 : w0);
+    rc = run_pass(s, plan->passes[i], plan->desc.dtype, src, dst);
+    if (rc != JFX_OK) return rc;
+    src = dst;
+  }
+  const Pass& last = plan->passes.back();
+  rc = dmma::launch_dmma_fold_scatter(s, last.fold, last.geom.outer, (const double*)src, mode, parts, rank, A, B,
+                                      (double* const*)peer_out);
+  if (rc < 0) return rc;
+  JFX_REQUIRE(rc == 1, JFX_ERR_UNSUPPORTED, "scatter pass outside the folded kernel's envelope (alignment)");
+  return JFX_OK;
+}
+
 int jfx_execute(const jfx_plan* plan, void* stream, const void* in, void* out, void* workspace) {
   using namespace jfx;
   JFX_REQUIRE(plan, JFX_ERR_INVALID, "null argument");

@@ -80,9 +80,10 @@ struct GlobalStore {
   __device__ __forceinline__ void s1(long long idx, double v) const { C[idx] = v; }
 };
 
-template <int V>
-__global__ void __launch_bounds__(THREADS, 1)
-dgemm_dmma_fold(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args q) {
+// The whole CTA: pipeline set-up, producer warpgroup, MMA warps.  epi(tile_m, tile_n, z, wm, wn, g, t, acc) stores one warp's
+// share of a finished tile (plain epilogue into this GPU's array, or the scatter epilogue into the peers' receive buffers).
+template <int V, class EPI>
+__device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& q, EPI&& epi) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte aligned tile ring (the swizzles are functions of the shared-memory address bits 4..9)
   const unsigned base = (s32(smem_raw) + 1023u) & ~1023u;
@@ -154,12 +155,30 @@ dgemm_dmma_fold(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const long long r = tl / q.tiles_n;
     const int tm = (int)(r % q.tiles_m);
     const long long z = r / q.tiles_m;
-    epilogue<V>(q, tm, tn, z, wm, wn, g, t, acc, GlobalStore{q.C});
+    epi(tm, tn, z, wm, wn, g, t, acc);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   }
+}
+
+template <int V>
+__global__ void __launch_bounds__(THREADS, 1)
+dgemm_dmma_fold(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args q) {
+  fold_cta<V>(tmA, tmB, q, [&](int tm, int tn, long long z, int wm, int wn, int g, int t, const double (&acc)[8][4][2]) {
+    epilogue<V>(q, tm, tn, z, wm, wn, g, t, acc, GlobalStore{q.C});
+  });
+}
+
+// Same contraction, result scattered into the slab-exchange receive buffers of all GPUs (NT variants; see Scatter)
+template <int V>
+__global__ void __launch_bounds__(THREADS, 1)
+dgemm_dmma_fold_scatter(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args q,
+                        const Scatter sc) {
+  fold_cta<V>(tmA, tmB, q, [&](int tm, int tn, long long, int wm, int wn, int g, int t, const double (&acc)[8][4][2]) {
+    epilogue_scatter<V>(q, sc, tm, tn, wm, wn, g, t, acc, [&](int dest) { return GlobalStore{sc.peer[dest]}; });
+  });
 }
 
 // ---- host ----------------------------------------------------------------------------------------
@@ -275,6 +294,41 @@ int launch_dmma_fold(cudaStream_t s, const FoldPlan* fp, long long outer, long l
     case OUT_NT: return launch_variant<OUT_NT>(s, tmA, tmB, q, sms);
     default: return launch_variant<IN_NT>(s, tmA, tmB, q, sms);
   }
+}
+
+// Last-axis pass with the scatter epilogue.  1 = launched, 0 = not applicable (not an NT fold pass / envelope), < 0 = error.
+int launch_dmma_fold_scatter(cudaStream_t s, const FoldPlan* fp, long long outer, const double* in, int mode, int parts,
+                             int src, int A, int B, double* const* peers) {
+  using namespace fold;
+  if (!fp || parts < 1 || parts > MAX_PEERS || (mode != 1 && mode != 2) || (long long)A * B != outer) return 0;
+  if ((mode == 1 ? B : A) % parts != 0 || src < 0 || src >= parts) return 0;
+  int dev = 0, sms = 0;
+  JFX_CUDA_OK(cudaGetDevice(&dev));
+  JFX_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  Args q;
+  MapDesc mA, mB;
+  // the C pointer only decides vector-store alignment here: every receive buffer must be 16-byte aligned
+  for (int p = 0; p < parts; ++p)
+    if (!peers[p] || (reinterpret_cast<uintptr_t>(peers[p]) & 15)) return 0;
+  if (!make_launch(fp->host, /*nn=*/false, outer, 1, fp->d_nt, in, peers[src], &q, &mA, &mB)) return 0;
+  Scatter sc{};
+  sc.mode = mode; sc.parts = parts; sc.src = src; sc.A = A; sc.B = B;
+  for (int p = 0; p < parts; ++p) sc.peer[p] = peers[p];
+  CUtensorMap tmA, tmB;
+  if (!encode(&tmA, mA) || !encode(&tmB, mB)) return 0;
+  const long long tiles = (long long)q.tiles_n * q.tiles_m * q.batch;
+  const unsigned ctas = (unsigned)(tiles < sms ? tiles : sms);
+  if (q.variant == OUT_NT) {
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_fold_scatter<OUT_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    dgemm_dmma_fold_scatter<OUT_NT><<<ctas, THREADS, SMEM_BYTES, s>>>(tmA, tmB, q, sc);
+  } else if (q.variant == IN_NT) {
+    JFX_CUDA_OK(cudaFuncSetAttribute(dgemm_dmma_fold_scatter<IN_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    dgemm_dmma_fold_scatter<IN_NT><<<ctas, THREADS, SMEM_BYTES, s>>>(tmA, tmB, q, sc);
+  } else {
+    return 0;
+  }
+  JFX_CUDA_OK(cudaGetLastError());
+  return 1;
 }
 
 // ---- complex data on a last table axis (CPLX_NT) ---------------------------------------------------

@@ -174,6 +174,24 @@ class Plan:
                                       C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr() if ws is not None else 0)))
         return out
 
+    # -- slab exchange fused into the last pass (peer stores over NVLink) --------------------
+    def scatter_supported(self, parts: int, split_axis: int) -> bool:
+        return bool(self._lib.jfx_plan_scatter_supported(self._h, int(parts), int(split_axis)))
+
+    def execute_scatter(self, x, peer_ptrs: Sequence[int], rank: int, split_axis: int):
+        """Run the plan; its final pass stores the result into the receive buffers `peer_ptrs[p]` (device pointers valid
+        on this device, one per rank) in the layout the tiled all-to-all of sharding.py:83-89 would leave there."""
+        if tuple(x.shape) != self.shape_in:
+            raise ValueError(f"plan expects shape {self.shape_in}, got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise L.JfxError(-3, "device path needs a CUDA tensor; jaxfun_b200 has no CPU fallback")
+        x = x.contiguous()
+        ws = self.workspace(x.device)
+        ptrs = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        L.check(self._lib.jfx_execute_scatter(self._h, C.c_void_p(current_stream_ptr()), C.c_void_p(x.data_ptr()), ptrs,
+                                              len(peer_ptrs), int(rank), int(split_axis),
+                                              C.c_void_p(ws.data_ptr() if ws is not None else 0)))
+
     # -- host path (e2e: H2D + transform + D2H inside the call) ---------------------------
     def execute_host(self, x: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         if tuple(x.shape) != self.shape_in:

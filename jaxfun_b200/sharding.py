@@ -81,6 +81,13 @@ class SlabBackend:
         return out, work
 
 
+def slab_p2p() -> bool:
+    """JFX_SLAB_P2P=1: the last local pass of phase 1 stores straight into the peers' receive buffers (symmetric memory
+    over NVLink) instead of pack + NCCL all-to-all (+ unpack).  Opt-in: written without multi-GPU access."""
+    import os
+    return os.environ.get("JFX_SLAB_P2P", "0") == "1"
+
+
 def slab_chunks() -> int:
     """Number of chunks of the overlapped exchange (JFX_SLAB_CHUNKS, default 1 = one blocking all-to-all)."""
     import os
@@ -151,6 +158,10 @@ def apply_separable_slab(x, sharding: str, backend: SlabBackend, world_size: int
     Returns the local block of the result, which carries the transposed sharding.  chunks > 1 (default: JFX_SLAB_CHUNKS)
     selects the overlapped exchange."""
     chunks = slab_chunks() if chunks is None else chunks
+    if world_size > 1 and slab_p2p() and hasattr(backend, "scatter_exchange"):
+        y = backend.scatter_exchange(x, sharding, world_size)
+        if y is not None:                      # None: this plan / shape has no fused path -> ordinary exchange below
+            return backend.apply_axes(y, [sharded_axis(sharding)])
     if chunks > 1 and world_size > 1:
         return _apply_separable_slab_chunked(x, sharding, backend, world_size, chunks)
     dim = x.ndim
@@ -187,8 +198,7 @@ class EngineSlabBackend(SlabBackend):
         self.space, self.op, self.N, self.k = space, op, N, k
         self._plans = {}
 
-    def apply_axes(self, x, axes):
-        from . import _lib as L
+    def _plan_for(self, x, axes):
         from .engine import Plan, jfx_dtype
         dtype = jfx_dtype(x.dtype)
         key = (tuple(x.shape), dtype, tuple(axes))
@@ -200,9 +210,52 @@ class EngineSlabBackend(SlabBackend):
                 specs[ax] = sp.axis_spec(self.op, x.shape[ax], dtype, None if self.N is None else self.N[ax],
                                          0 if self.k is None else self.k[ax],
                                          inner=int(np.prod(x.shape[ax + 1:], dtype=np.int64)))
-            plan = Plan(self.op, dtype, tuple(x.shape), specs)
-            self._plans[key] = plan
-        return plan(x)
+            plan = self._plans[key] = Plan(self.op, dtype, tuple(x.shape), specs)
+        return plan
+
+    def apply_axes(self, x, axes):
+        return self._plan_for(x, axes)(x)
+
+    # ---- exchange fused into the last pass of phase 1 (peer stores) ---------------------------------
+    def scatter_exchange(self, x, sharding: str, world_size: int):
+        """Phase 1 + exchange in one go: returns the array phase 2 transforms, or None when the plan has no fused path.
+
+        Receive buffers live in symmetric memory (torch.distributed._symmetric_memory): every rank maps every peer's
+        buffer, the final contraction pass of phase 1 stores each output row into the rank that owns it after the
+        exchange, and one device-side barrier orders the stores before phase 2 reads them.  Two buffers alternate per
+        (shape, direction): a rank can run ahead by at most one transform before it meets the next barrier, so the
+        buffer it overwrites has been read by everybody."""
+        import torch.distributed._symmetric_memory as symm_mem
+        if x.ndim != 3 or x.dtype != torch.float64:
+            return None
+        sh = sharded_axis(sharding)
+        unsharded = [ax for ax in range(3) if ax != sh]
+        split_axis = unsharded[0]
+        plan = self._plan_for(x, unsharded)
+        if not plan.scatter_supported(world_size, split_axis):
+            return None
+        s0, s1, s2 = plan.shape_out
+        recv_shape = (world_size * s0, s1 // world_size, s2) if split_axis == 1 else (s0 // world_size, world_size * s1, s2)
+        key = ("p2p", tuple(x.shape), split_axis)
+        ent = self._plans.get(key)
+        if ent is None:
+            bufs, hdls = [], []
+            if hasattr(symm_mem, "enable_symm_mem_for_group"):      # needed by older torch releases, a no-op in newer ones
+                try:
+                    symm_mem.enable_symm_mem_for_group(dist.group.WORLD.group_name)
+                except Exception:
+                    pass
+            for _ in range(2):
+                b = symm_mem.empty(recv_shape, dtype=torch.float64, device=x.device)
+                hdls.append(symm_mem.rendezvous(b, dist.group.WORLD.group_name))
+                bufs.append(b)
+            ent = self._plans[key] = {"bufs": bufs, "hdls": hdls, "turn": 0}
+        t = ent["turn"]
+        ent["turn"] = t ^ 1
+        hdl, buf = ent["hdls"][t], ent["bufs"][t]
+        plan.execute_scatter(x, [int(p) for p in hdl.buffer_ptrs], dist.get_rank(), split_axis)
+        hdl.barrier(channel=t)
+        return buf
 
     def _repack(self, fn_name: str, x, out_shape, full_shape, axis: int, parts: int):
         from . import _lib as L

@@ -247,6 +247,128 @@ static void run_cplx_case(int n_out, int n_in, long long outer, unsigned seed) {
   if (!ok) ++g_fail;
 }
 
+// Scatter epilogue: P emulated ranks run the same NT pass on their local [A][B][n_in] block and write straight into the
+// receive buffers of all ranks; the result must be what pack + tiled all-to-all (+ unpack) leaves on every rank.
+struct PeerStore {
+  std::vector<double>* out;
+  std::vector<int>* cnt;
+  void s2(long long idx, double v0, double v1) { assert(idx % 2 == 0); s1(idx, v0); s1(idx + 1, v1); }
+  void s1(long long idx, double v) {
+    assert(idx >= 0 && idx < (long long)out->size());
+    (*out)[idx] = v;
+    (*cnt)[idx]++;
+  }
+};
+
+template <int V>
+static void run_tiles_scatter(const Args& q, const Scatter& sc, const MapDesc& mA, const MapDesc& mB,
+                              std::vector<std::vector<double>>& outs, std::vector<std::vector<int>>& cnts) {
+  const int kts = ktiles(q);
+  std::vector<double> stage(3 * TILE);
+  for (int tm = 0; tm < q.tiles_m; ++tm)
+    for (int tn = 0; tn < q.tiles_n; ++tn) {
+      static double acc[MMA_WARPS][32][8][4][2];
+      memset(acc, 0, sizeof(acc));
+      for (int kt = 0; kt < kts; ++kt) {
+        for (auto& v : stage) v = 1e300;
+        stage_copies<V>(q, kt, tm, tn, 0, [&](int map, int dst, int rank, int c0, int c1, int c2, int c3) {
+          const int c[4] = {c0, c1, c2, c3};
+          tma_copy(map == 0 ? mA : mB, stage, dst, rank, c);
+        });
+        for (int w = 0; w < MMA_WARPS; ++w) {
+          std::vector<Rec> rec[32];
+          for (int lane = 0; lane < 32; ++lane) {
+            double dummy[8][4][2];
+            double* d0base = &dummy[0][0][0];
+            ktile<V>(stage.data(), w / WARPS_N, w % WARPS_N, lane >> 2, lane & 3, q.par_plus, dummy,
+                     [&](double& d0, double& d1, double a, double b) { (void)d1; rec[lane].push_back(Rec{(int)((&d0 - d0base) / 2), a, b}); });
+          }
+          for (size_t r = 0; r < rec[0].size(); ++r)
+            for (int lane = 0; lane < 32; ++lane) {
+              const int g = lane >> 2, t = lane & 3, slot = rec[0][r].slot;
+              double d0 = 0, d1 = 0;
+              for (int k = 0; k < 4; ++k) {
+                const double a = rec[g * 4 + k][r].a;
+                d0 += a * rec[(2 * t) * 4 + k][r].b;
+                d1 += a * rec[(2 * t + 1) * 4 + k][r].b;
+              }
+              (&acc[w][lane][0][0][0])[2 * slot] += d0;
+              (&acc[w][lane][0][0][0])[2 * slot + 1] += d1;
+            }
+        }
+      }
+      for (int w = 0; w < MMA_WARPS; ++w)
+        for (int lane = 0; lane < 32; ++lane)
+          epilogue_scatter<V>(q, sc, tm, tn, w / WARPS_N, w % WARPS_N, lane >> 2, lane & 3, acc[w][lane],
+                              [&](int dest) { assert(dest >= 0 && dest < sc.parts); return PeerStore{&outs[dest], &cnts[dest]}; });
+    }
+}
+
+static void run_scatter_case(int type, int mode, int P, int A, int B, int n_fold, int n_other, unsigned seed) {
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  const bool outf = type == FOLD_OUT;
+  const int rows = outf ? n_fold : n_other, cols = outf ? n_other : n_fold;   // table [n_out][n_in]
+  std::vector<double> T((size_t)rows * cols);
+  for (int k = 0; k < n_other; ++k) {
+    const double sg = (k & 1) ? -1.0 : 1.0;
+    for (int j = 0; j < n_fold / 2; ++j) {
+      const double v = U(rng);
+      if (outf) { T[(size_t)j * cols + k] = v; T[(size_t)(n_fold - 1 - j) * cols + k] = sg * v; }
+      else { T[(size_t)k * cols + j] = v; T[(size_t)k * cols + (n_fold - 1 - j)] = sg * v; }
+    }
+  }
+  const FoldInfo fi = analyze(T.data(), rows, cols);
+  const FoldedTable f = build(T.data(), rows, cols, fi);
+  const int n_in = cols, n_out = rows;
+  const long long M = (long long)A * B;
+  // receive buffers: mode 1: [P*A][B/P][n_out]; mode 2: [A/P][P*B][n_out] -> the same number of elements
+  const size_t recv_elems = (size_t)A * B * n_out;
+  std::vector<std::vector<double>> outs(P, std::vector<double>(recv_elems, 7e299)), refs(P, std::vector<double>(recv_elems, 0.0));
+  std::vector<std::vector<int>> cnts(P, std::vector<int>(recv_elems, 0));
+  std::vector<double> tb(f.nt.size() + 2);
+  double* tbl = tb.data() + ((reinterpret_cast<uintptr_t>(tb.data()) & 15) ? 1 : 0);
+  memcpy(tbl, f.nt.data(), f.nt.size() * 8);
+  for (int src = 0; src < P; ++src) {
+    std::vector<double> xb((size_t)M * n_in + 2), cb(4);
+    double* x = xb.data() + ((reinterpret_cast<uintptr_t>(xb.data()) & 15) ? 1 : 0);
+    for (size_t i = 0; i < (size_t)M * n_in; ++i) x[i] = U(rng);
+    // expected: y_src[a][b][r] placed by the exchange
+    for (int a = 0; a < A; ++a)
+      for (int b = 0; b < B; ++b)
+        for (int r = 0; r < n_out; ++r) {
+          long double s = 0;
+          for (int c = 0; c < n_in; ++c) s += (long double)T[(size_t)r * n_in + c] * x[((size_t)a * B + b) * n_in + c];
+          if (mode == 1) {
+            const int bp = B / P, p = b / bp;
+            refs[p][(((size_t)src * A + a) * bp + (b % bp)) * n_out + r] = (double)s;
+          } else {
+            const int ap = A / P, p = a / ap;
+            refs[p][(((size_t)(a % ap)) * ((size_t)B * P) + (size_t)src * B + b) * n_out + r] = (double)s;
+          }
+        }
+    double* cdummy = cb.data() + ((reinterpret_cast<uintptr_t>(cb.data()) & 15) ? 1 : 0);
+    Args q;
+    MapDesc mA, mB;
+    if (!make_launch(f, false, M, 1, tbl, x, cdummy, &q, &mA, &mB)) { printf("FAIL make_launch (scatter)\n"); ++g_fail; return; }
+    Scatter sc{};
+    sc.mode = mode; sc.parts = P; sc.src = src; sc.A = A; sc.B = B;
+    if (q.variant == OUT_NT) run_tiles_scatter<OUT_NT>(q, sc, mA, mB, outs, cnts);
+    else run_tiles_scatter<IN_NT>(q, sc, mA, mB, outs, cnts);
+  }
+  double err = 0;
+  long long bad = 0;
+  for (int p = 0; p < P; ++p)
+    for (size_t i = 0; i < recv_elems; ++i) {
+      err = std::fmax(err, std::fabs(outs[p][i] - refs[p][i]));
+      if (cnts[p][i] != 1) ++bad;
+    }
+  const bool ok = err < 1e-12 && bad == 0;
+  printf("%s scatter mode %d type %d P %d A %d B %d n_fold %d n_other %d  err %.2e  miswritten %lld\n", ok ? "ok  " : "FAIL", mode, type, P,
+         A, B, n_fold, n_other, err, bad);
+  if (!ok) ++g_fail;
+}
+
 int main(int argc, char** argv) {
   // fold_emu --table file rows cols : a real host table (raw float64, row-major) through the NN and NT variants;
   // the reference result uses the table as given (slightly asymmetric nodes), tolerance 1e-12 of the result's max norm
@@ -282,6 +404,13 @@ int main(int argc, char** argv) {
       run_cplx_case(c[0], c[1], 1, seed++);
       run_cplx_case(c[0], c[1], 131, seed++);
     }
+  }
+  // peer-store exchange: backward-type (mode 1, OUT fold) and forward-type (mode 2, IN fold) passes on P emulated ranks
+  for (int P : {2, 4, 8}) {
+    run_scatter_case(FOLD_OUT, 1, P, 3, 8 * P / 2, 32, 16, seed++);
+    run_scatter_case(FOLD_OUT, 1, P, 5, 2 * P, 66, 34, seed++);
+    run_scatter_case(FOLD_IN, 2, P, 2 * P, 5, 32, 16, seed++);
+    run_scatter_case(FOLD_IN, 2, P, P, 24, 66, 33, seed++);
   }
   // tables without the symmetry must be refused
   {
