@@ -139,8 +139,155 @@ static double run_case(const Case& c, int time_iters) {
   return err;
 }
 
+// ---- extras (--extra): the two opt-in paths that have not run on a GPU yet --------------------------------------
+// (a) CPLX_NT: complex rows on a last table axis, JFX_CPLX_NT=1 vs the default NN route
+static void run_cplx_case(int rows, int N, int nq, bool fwd, int time_iters) {
+  std::vector<double> B, F;
+  tables(N, nq, B, F);
+  const std::vector<double>& T = fwd ? F : B;
+  Case c{2, {rows, fwd ? nq : N, 0, 0}, {0, 1, 0, 0}, N, nq, fwd, JFX_C128};
+  setenv("JFX_CPLX_NT", "0", 1);
+  jfx_plan* p0 = make_plan(c, T, true);
+  setenv("JFX_CPLX_NT", "1", 1);
+  jfx_plan* p1 = make_plan(c, T, true);
+  setenv("JFX_CPLX_NT", "0", 1);
+  if (!p0 || !p1) { ++g_fail; return; }
+  const size_t nin = 2ull * rows * (fwd ? nq : N), nout = 2ull * rows * (fwd ? N : nq);
+  std::vector<double> h(nin);
+  unsigned long long sd = 0x2545F4914F6CDD1Dull;
+  for (auto& v : h) { sd ^= sd << 13; sd ^= sd >> 7; sd ^= sd << 17; v = (double)(sd >> 11) / 9007199254740992.0 - 0.5; }
+  double *din, *o0, *o1;
+  cudaMalloc(&din, nin * 8); cudaMalloc(&o0, nout * 8); cudaMalloc(&o1, nout * 8);
+  cudaMemcpy(din, h.data(), nin * 8, cudaMemcpyHostToDevice);
+  cudaMemset(o1, 0xff, nout * 8);
+  int rc0 = jfx_execute(p0, nullptr, din, o0, nullptr), rc1 = jfx_execute(p1, nullptr, din, o1, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc0 || rc1 || e != cudaSuccess) {
+    LOG("FAIL cplx execute rc %d %d cuda %s : %s\n", rc0, rc1, cudaGetErrorString(e), jfx_last_error());
+    ++g_fail;
+    if (e != cudaSuccess) { if (g_log) fclose(g_log); exit(2); }
+  } else {
+    std::vector<double> a(nout), b(nout);
+    cudaMemcpy(a.data(), o0, nout * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(b.data(), o1, nout * 8, cudaMemcpyDeviceToHost);
+    double mx = 0, df = 0;
+    bool nan = false;
+    for (size_t i = 0; i < nout; ++i) {
+      if (!(std::fabs(b[i]) < 1e300)) nan = true;
+      mx = std::fmax(mx, std::fabs(a[i])); df = std::fmax(df, std::fabs(a[i] - b[i]));
+    }
+    const double err = nan ? 1e9 : df / (mx > 0 ? mx : 1);
+    float t0 = 0, t1 = 0;
+    if (time_iters > 0) {
+      cudaEvent_t ev0, ev1; cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+      for (int which = 0; which < 2; ++which) {
+        jfx_plan* p = which ? p1 : p0; double* o = which ? o1 : o0;
+        jfx_execute(p, nullptr, din, o, nullptr);
+        cudaEventRecord(ev0);
+        for (int i = 0; i < time_iters; ++i) jfx_execute(p, nullptr, din, o, nullptr);
+        cudaEventRecord(ev1); cudaEventSynchronize(ev1);
+        cudaEventElapsedTime(which ? &t1 : &t0, ev0, ev1);
+      }
+    }
+    const bool ok = err < 1e-12;
+    if (!ok) ++g_fail;
+    LOG("%s cplx-last-axis %s rows %d N %d nq %d  rel diff %.2e", ok ? "ok  " : "FAIL", fwd ? "fwd" : "bwd", rows, N, nq, err);
+    if (time_iters > 0) LOG("  NN route %.4f ms  CPLX_NT %.4f ms  (x%.1f)", t0 / time_iters, t1 / time_iters, t0 / t1);
+    LOG("\n");
+  }
+  cudaFree(din); cudaFree(o0); cudaFree(o1);
+  jfx_plan_destroy(p0); jfx_plan_destroy(p1);
+}
+
+// (b) jfx_execute_scatter with P emulated ranks on this one GPU against jfx_execute + the exchange done on the host
+static void run_scatter_case(int P, int n0, int n1, int n2, bool fwd) {
+  // backward: local spectral block [n0/P][n1][n2], phase-1 axes (1, 2), split axis 1
+  // forward : local physical block [n0][n1/P][n2], phase-1 axes (0, 2), split axis 0
+  const int split = fwd ? 0 : 1;
+  std::vector<double> B, F;
+  // one table size per case keeps the tool short: cubic extents
+  tables(n2, n2, B, F);
+  const std::vector<double>& T = fwd ? F : B;
+  Case c{3, {fwd ? n0 : n0 / P, fwd ? n1 / P : n1, n2, 0}, {fwd ? 1 : 0, fwd ? 0 : 1, 1, 0}, n2, n2, fwd, JFX_F64};
+  jfx_plan* pl = make_plan(c, T, true);
+  if (!pl) { ++g_fail; return; }
+  if (!jfx_plan_scatter_supported(pl, P, split)) { LOG("FAIL scatter not supported P %d\n", P); ++g_fail; jfx_plan_destroy(pl); return; }
+  const long long s0 = c.shape[0], s1 = c.shape[1], s2 = c.shape[2];
+  const size_t nloc = (size_t)s0 * s1 * s2;
+  size_t ws = 0;
+  jfx_plan_workspace_bytes(pl, &ws);
+  void* w = nullptr;
+  if (ws) cudaMalloc(&w, ws);
+  std::vector<std::vector<double>> hin(P, std::vector<double>(nloc)), hy(P, std::vector<double>(nloc));
+  std::vector<double*> recv(P);
+  for (int p = 0; p < P; ++p) { cudaMalloc(&recv[p], nloc * 8); cudaMemset(recv[p], 0xff, nloc * 8); }
+  double *din, *dy;
+  cudaMalloc(&din, nloc * 8); cudaMalloc(&dy, nloc * 8);
+  unsigned long long sd = 0x9E3779B97F4A7C15ull;
+  int rc = 0;
+  for (int r = 0; r < P; ++r) {
+    for (auto& v : hin[r]) { sd ^= sd << 13; sd ^= sd >> 7; sd ^= sd << 17; v = (double)(sd >> 11) / 9007199254740992.0 - 0.5; }
+    cudaMemcpy(din, hin[r].data(), nloc * 8, cudaMemcpyHostToDevice);
+    rc |= jfx_execute(pl, nullptr, din, dy, w);
+    cudaMemcpy(hy[r].data(), dy, nloc * 8, cudaMemcpyDeviceToHost);
+    rc |= jfx_execute_scatter(pl, nullptr, din, (void* const*)recv.data(), P, r, split, w);
+    if (cudaDeviceSynchronize() != cudaSuccess || rc) {
+      LOG("FAIL scatter execute rc %d : %s / %s\n", rc, jfx_last_error(), cudaGetErrorString(cudaGetLastError()));
+      ++g_fail;
+      if (g_log) fclose(g_log);
+      exit(2);
+    }
+  }
+  double err = 0, mx = 0;
+  bool nan = false;
+  std::vector<double> got(nloc);
+  for (int p = 0; p < P; ++p) {
+    cudaMemcpy(got.data(), recv[p], nloc * 8, cudaMemcpyDeviceToHost);
+    for (int r = 0; r < P; ++r)
+      for (long long a = 0; a < s0; ++a)
+        for (long long b = 0; b < s1; ++b) {
+          long long drow;
+          if (!fwd) { const long long bp = s1 / P; if (b / bp != p) continue; drow = ((long long)r * s0 + a) * bp + b % bp; }
+          else { const long long ap = s0 / P; if (a / ap != p) continue; drow = (a % ap) * (s1 * P) + (long long)r * s1 + b; }
+          for (long long k = 0; k < s2; ++k) {
+            const double want = hy[r][(a * s1 + b) * s2 + k], g = got[drow * s2 + k];
+            if (!(std::fabs(g) < 1e300)) nan = true;
+            err = std::fmax(err, std::fabs(want - g)); mx = std::fmax(mx, std::fabs(want));
+          }
+        }
+  }
+  const bool ok = !nan && err < 1e-13 * mx;
+  if (!ok) ++g_fail;
+  LOG("%s scatter %s P %d local %lld x %lld x %lld  max diff %.2e%s\n", ok ? "ok  " : "FAIL", fwd ? "fwd (split 0)" : "bwd (split 1)", P, s0, s1,
+      s2, err, nan ? " (unwritten elements)" : "");
+  for (int p = 0; p < P; ++p) cudaFree(recv[p]);
+  cudaFree(din); cudaFree(dy); if (w) cudaFree(w);
+  jfx_plan_destroy(pl);
+}
+
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && !strcmp(argv[1], "--quick");
+  if (argc > 1 && !strcmp(argv[1], "--extra")) {
+    g_log = fopen("gpurun_out/fold_check_extra.txt", "w");
+    if (jfx_device_count() < 1) { LOG("no CUDA device\n"); return 3; }
+    for (int fwd = 0; fwd < 2; ++fwd) {
+      run_cplx_case(300, 16, 16, fwd, 0);
+      run_cplx_case(1, 64, 64, fwd, 0);
+      run_cplx_case(777, 62, 64, fwd, 0);
+      run_cplx_case(1000, 64, 96, fwd, 0);
+      run_cplx_case(16384, 128, 128, fwd, 5);
+      run_cplx_case(65536, 256, 256, fwd, 5);
+    }
+    for (int P : {2, 4, 8})
+      for (int fwd = 0; fwd < 2; ++fwd) {
+        // the two transformed axes share one table here, so their extents are equal: (1, 2) backward, (0, 2) forward
+        if (!fwd) { run_scatter_case(P, 32, 64, 64, false); run_scatter_case(P, 16, 96, 96, false); }
+        else { run_scatter_case(P, 64, 48, 64, true); run_scatter_case(P, 96, 16, 96, true); }
+      }
+    LOG(g_fail ? "FOLD CHECK EXTRA: %d FAILURES\n" : "FOLD CHECK EXTRA: ALL OK\n", g_fail);
+    if (g_log) fclose(g_log);
+    return g_fail ? 1 : 0;
+  }
   g_log = fopen(quick ? "gpurun_out/fold_check_quick.txt" : "gpurun_out/fold_check.txt", "w");
   if (jfx_device_count() < 1) { LOG("no CUDA device\n"); return 3; }
   // timing first (the numbers matter most if the box time runs out): 256^3 backward / forward, f64
