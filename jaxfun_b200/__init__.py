@@ -8,7 +8,7 @@ _lib.load()  # fail loudly when the CUDA extension has not been built
 from . import galerkin  # noqa: E402
 from .engine import PinnedArray, Plan, device_count, require_device  # noqa: E402,F401
 from .galerkin import TensorProduct, TensorProductSpace  # noqa: E402,F401
-from .galerkin.composite import Composite, FunctionSpace  # noqa: E402,F401
+from .galerkin.composite import Composite, DirectSum, FunctionSpace  # noqa: E402,F401
 from .galerkin.Chebyshev import Chebyshev  # noqa: E402,F401
 from .galerkin.ChebyshevU import ChebyshevU  # noqa: E402,F401
 from .galerkin.Fourier import Fourier  # noqa: E402,F401
@@ -17,5 +17,5 @@ from .galerkin.Legendre import Legendre  # noqa: E402,F401
 from .galerkin.Ultraspherical import Ultraspherical  # noqa: E402,F401
 
 __all__ = ["galerkin", "Plan", "PinnedArray", "TensorProduct", "TensorProductSpace", "Chebyshev",
-           "ChebyshevU", "Composite", "FunctionSpace", "Fourier", "Jacobi", "Legendre", "Ultraspherical", "device_count",
+           "ChebyshevU", "Composite", "DirectSum", "FunctionSpace", "Fourier", "Jacobi", "Legendre", "Ultraspherical", "device_count",
            "require_device"]

@@ -104,7 +104,9 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
   for (int ax = 0; ax < d->ndim; ++ax) {
     const jfx_axis_desc& a = d->axis[ax];
     if (a.basis == JFX_BASIS_NONE) continue;
-    Pass p;
+    // the pass lives in the plan from the start: an early error return then releases its device tables with the plan
+    pl->passes.emplace_back();
+    Pass& p = pl->passes.back();
     p.axis = ax;
     int n_in = (int)cur[ax], n_out;
     if (a.basis == JFX_BASIS_TABLE || a.basis == JFX_BASIS_CTABLE) {
@@ -186,7 +188,6 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
     }
     cur[ax] = n_out;
     max_inter = std::max(max_inter, (size_t)prod(cur, 0, d->ndim) * es);
-    pl->passes.push_back(p);
   }
   for (int i = 0; i < d->ndim; ++i) pl->shape_out[i] = cur[i];
   const int64_t out_elems = prod(cur, 0, d->ndim);

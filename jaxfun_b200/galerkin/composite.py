@@ -210,12 +210,149 @@ def stencil_from_bcs(bcs: dict, orthogonal) -> dict:
     return st
 
 
+def bc_basis(bcs: dict, orthogonal_cls, **kw) -> np.ndarray:
+    """Numeric counterpart of `get_bc_basis` (composite.py:835-896): rows = lifting functions B_i = sum_j S_ij P_j with
+    (boundary functional b)(B_i) = delta_bi, built on the first block of `nb` consecutive modes whose boundary matrix is
+    invertible.  The boundary functionals are derivatives in the REFERENCE coordinate, as `bnd_values` (Jacobi.py:257-288)."""
+    names = ordered_bc_names(bcs)
+    nb = len(names)
+    nd = sum(_BC_ORDER[kind] for _, kind in names)
+    orth = orthogonal_cls(nb + nd, **kw)
+    F = np.empty((nb, nb + nd))
+    for b, (side, kind) in enumerate(names):
+        if kind not in _BC_ORDER:
+            raise NotImplementedError(f"boundary condition kind {kind!r} (Robin) has no numeric lifting basis here")
+        F[b] = orth.evaluate_basis_derivative(np.array([-1.0 if side == "left" else 1.0]), _BC_ORDER[kind])[0]
+    for first in range(nd + 1):
+        A = F[:, first:first + nb]
+        if np.linalg.matrix_rank(A) == nb:
+            S = np.zeros((nb, first + nb))
+            S[:, first:] = np.linalg.inv(A).T
+            S[np.abs(S) < 1e-15] = 0.0
+            return S
+    raise ValueError("no invertible boundary matrix for these boundary conditions")
+
+
+class DirectSum:
+    """V = Composite (+) boundary lift (`DirectSum`, composite.py:502-638; `BCGeneric`, :411-488).
+
+    The lift is a FIXED element sum_b val_b B_b of the orthogonal space; its coefficients `c_b = bnd_vals @ S_bc`
+    (zero padded, composite.py:583-597) are computed once on the host.  Every transform is the homogeneous Composite's
+    engine plan plus that constant: `backward(c) = a.backward(c) + V c_b` (same value as the reference's
+    `orthogonal.backward(to_orthogonal(c))`, one launch instead of two), `forward(u) = a.from_orthogonal(
+    orthogonal.forward(u) - c_b)`, `scalar_product = a.scalar_product` (no boundary part in the test functions)."""
+
+    is_orthogonal = False
+
+    def __init__(self, a: Composite, bcs: dict) -> None:
+        self.basespaces = (a,)
+        self.a = a
+        self.bcs = bcs
+        self.orthogonal = a.orthogonal
+        self.N = a.N
+        self.name = a.name + "+B"
+        kw = {}
+        if type(a.orthogonal).__name__ == "Jacobi":
+            kw = dict(alpha=a.orthogonal.alpha, beta=a.orthogonal.beta)
+        self.S_bc = bc_basis(bcs, type(a.orthogonal), **kw)
+        vals = np.array([float(bcs[side][kind]) for side, kind in ordered_bc_names(bcs)])
+        cb = vals @ self.S_bc                                  # BCGeneric.to_orthogonal(bnd_vals) = vals @ S
+        self.c_b = np.zeros(self.N)
+        self.c_b[:cb.shape[0]] = cb
+        self._bvals = vals
+        self._lift_cache: dict = {}
+
+    # ---- what the reference forwards to the homogeneous part (composite.py:521-537) -----------------------------
+    def __getitem__(self, i):
+        return self.a if i == 0 else self
+    def __len__(self):
+        return 2
+    @property
+    def dim(self) -> int:
+        return self.a.dim
+    @property
+    def num_dofs(self) -> int:
+        return self.a.dim
+    @property
+    def domain(self):
+        return self.a.domain
+    @property
+    def num_quad_points(self) -> int:
+        return self.a.num_quad_points
+    @property
+    def shape(self):
+        return (self.num_quad_points,)
+    def mesh(self, kind: str = "quadrature", N=None):
+        return self.a.mesh(kind, N)
+    def quad_points_and_weights(self, N=None):
+        return self.a.quad_points_and_weights(N)
+    def get_orthogonal(self):
+        return self.orthogonal
+    def get_homogeneous(self):
+        return self.a
+    def bnd_vals(self) -> np.ndarray:
+        return self._bvals.copy()
+
+    # ---- the constant lift, broadcast along one axis --------------------------------------------------------------
+    def _add(self, x, vec: np.ndarray, axis: int, sign: float = 1.0, key=None):
+        """x + sign * vec broadcast along `axis`; `key` names a constant whose device copy is kept."""
+        shp = [1] * x.ndim
+        shp[axis] = -1
+        if isinstance(x, np.ndarray):
+            return x + sign * vec.reshape(shp)
+        import torch
+        t = self._lift_cache.get((key, x.device, x.dtype)) if key is not None else None
+        if t is None:
+            t = torch.from_numpy(np.ascontiguousarray(vec)).to(device=x.device, dtype=x.dtype)
+            if key is not None:
+                self._lift_cache[(key, x.device, x.dtype)] = t
+        return torch.add(x, t.reshape(shp), alpha=sign)
+
+    def _physical_lift(self, n_quad: int, k: int) -> np.ndarray:
+        key = ("u_b", n_quad, k)
+        v = self._lift_cache.get(key)
+        if v is None:
+            T = self.orthogonal._dense_table(L.OP_BACKWARD_PRIMITIVE if k else L.OP_BACKWARD, self.N, n_quad, k)
+            v = self._lift_cache[key] = np.ascontiguousarray(T @ self.c_b)
+        return v
+
+    # ---- transforms (composite.py:583-634) ------------------------------------------------------------------------------
+    def to_orthogonal(self, c, axis: int = -1):
+        return self._add(self.a.to_orthogonal(c, axis), self.c_b, axis, key="c_b")
+
+    def from_orthogonal(self, x, axis: int = -1):
+        return self.a.from_orthogonal(self._add(x, self.c_b, axis, -1.0, key="c_b"), axis)
+
+    def backward(self, c, N=None, axis: int = -1):
+        n_quad = self.num_quad_points if N is None else int(N)
+        return self._add(self.a.backward(c, N, axis), self._physical_lift(n_quad, 0), axis, key=("dev_u_b", n_quad, 0))
+
+    def backward_primitive(self, c, k: int = 0, N=None, axis: int = -1):
+        n_quad = self.num_quad_points if N is None else int(N)
+        return self._add(self.a.backward_primitive(c, k, N, axis), self._physical_lift(n_quad, k), axis, key=("dev_u_b", n_quad, k))
+
+    def forward(self, u, axis: int = -1):
+        return self.from_orthogonal(self.orthogonal.forward(u, axis), axis)
+
+    def scalar_product(self, u, axis: int = -1):
+        return self.a.scalar_product(u, axis)
+
+    def evaluate(self, x, c, axis: int = -1):
+        X = np.atleast_1d(np.asarray(self.orthogonal.map_reference_domain(np.asarray(x, dtype=float))))
+        lift = np.asarray(self.orthogonal.eval_basis_functions(X)) @ self.c_b
+        return self._add(self.a.evaluate(x, c, axis), np.ascontiguousarray(lift), axis)
+
+
 def FunctionSpace(N: int, space, bcs=None, domain=None, name: str = "fun", fun_str: str = "phi", scaling=None, **kw):
     """`jaxfun.galerkin.functionspace.FunctionSpace` (functionspace.py:63-173) for the cases whose stencil is
     known in closed form: no BCs -> the orthogonal space; homogeneous Dirichlet on both ends of a Chebyshev /
     Legendre space -> phi_k = P_k - P_{k+2} (both families have P_k(+-1) = (+-1)^k)."""
     if bcs is None:
         return space(N, domain=domain, name=name, fun_str=fun_str, **kw)
+    if any(v != 0 for side in bcs.values() for v in side.values()):
+        # functionspace.py:150-173: homogeneous Composite (+) boundary lift
+        hom = {side: {kind: 0 for kind in kinds} for side, kinds in bcs.items()}
+        return DirectSum(FunctionSpace(N, space, hom, domain=domain, name=name, fun_str=fun_str, scaling=scaling, **kw), bcs)
     left, right = bcs.get("left", {}), bcs.get("right", {})
     if set(left) == {"D"} and set(right) == {"D"} and left["D"] == 0 and right["D"] == 0 and \
             space.__name__ in ("Chebyshev", "Legendre"):

@@ -291,6 +291,21 @@ class Jacobi(OrthogonalSpace):
     def psi(self, n, k):
         return sp.rf(n + self.alpha + self.beta + 1, k) * sp.Rational(1, 2**k)
 
+    # Jacobi.py:257-288: k-th derivative of basis function i at X = -1 / X = +1 (reference coordinate)
+    def bnd_values(self, k=0):
+        alpha, beta = self.alpha, self.beta
+
+        def gam(i):
+            return self.psi(i, k) if k > 0 else 1
+
+        def left_fn(i):
+            return self.gn(i) * (-1) ** (k + i) * gam(i) * sp.binomial(i + beta, i - k)
+
+        def right_fn(i):
+            return self.gn(i) * gam(i) * sp.binomial(i + alpha, i - k)
+
+        return left_fn, right_fn
+
     def h(self, n, k=0):
         assert k == 0, "only the k = 0 norm is on the transform path"
         f = sp.rf(n + 1, alf) / sp.rf(n + bet + 1, alf) * 2 ** (alf + bet + 1) / (2 * n + alf + bet + 1)
@@ -953,4 +968,113 @@ class Composite(OrthogonalSpace):
         return self.orthogonal.eval_basis_functions(X) @ self.S.T
 
     def evaluate(self, x, c, axis=-1):
+        return self.orthogonal.evaluate(x, self.to_orthogonal(c, axis), axis)
+
+
+# =================================================================================================
+# Inhomogeneous boundary values: BCGeneric lifting basis and DirectSum  (galerkin/composite.py:40-118, 411-488,
+# 502-638, 835-896) — SURVEY §8(f) rank 1
+# =================================================================================================
+_BC_DERIV = {"D": 0, "N": 1, "N2": 2, "N3": 3, "N4": 4}
+
+
+class BoundaryConditions(dict):
+    """composite.py:40-118 (Dirichlet / Neumann / higher-derivative conditions; Robin is not restated)."""
+
+    def __init__(self, bc):
+        super().__init__({"left": dict(bc.get("left", {})), "right": dict(bc.get("right", {}))})
+
+    def orderednames(self):                                     # composite.py:75-79
+        return ["L" + k for k in sorted(self["left"])] + ["R" + k for k in sorted(self["right"])]
+
+    def orderedvals(self):                                      # composite.py:81-88
+        return [self[lr][k] for lr in ("left", "right") for k in sorted(self[lr])]
+
+    def num_bcs(self):                                          # composite.py:90-92
+        return len(self.orderedvals())
+
+    def num_derivatives(self):                                  # composite.py:94-101
+        return sum(_BC_DERIV[k] for v in self.values() for k in v)
+
+    def get_homogeneous(self):                                  # composite.py:111-118
+        return BoundaryConditions({lr: {k: 0 for k in v} for lr, v in self.items()})
+
+
+def get_bc_basis(bcs, orthogonal):
+    """composite.py:835-896: rows = lifting functions B_i = sum_j S_ij P_j with (boundary functional b)(B_i) = delta_bi;
+    the first block of `nb` consecutive modes whose boundary matrix is invertible is used."""
+    bcs = BoundaryConditions(bcs)
+    nb = bcs.num_bcs()
+
+    def computematrix(first):
+        rows = []
+        for key in bcs.orderednames():
+            side, kind = key[0], key[1:]
+            f = orthogonal.bnd_values(k=_BC_DERIV[kind])[0 if side == "L" else 1]
+            rows.append([sp.simplify(f(j)) for j in range(first, first + nb)])
+        A = sp.Matrix(rows)
+        return sp.simplify(A.solve(sp.eye(nb)).T)
+
+    first, sol = 0, None
+    for first in range(bcs.num_derivatives() + 1):
+        try:
+            sol = computematrix(first)
+            break
+        except Exception:                                       # sympy NonInvertibleMatrixError
+            continue
+    S = np.zeros((nb, first + nb))
+    S[:, first:] = np.array(sol.tolist(), dtype=float)
+    return S
+
+
+class DirectSum:
+    """V = Composite (+) BCGeneric (composite.py:502-638): the expansion is the homogeneous part plus a fixed boundary lift
+    sum_b val_b B_b whose orthogonal coefficients are `bnd_vals @ S_bc`, zero padded (composite.py:583-597)."""
+
+    def __init__(self, a, bcs):
+        self.a = a
+        self.bcs = BoundaryConditions(bcs)
+        self.orthogonal = a.orthogonal
+        self.N = a.N
+        self.domain = a.domain
+        small = type(a.orthogonal)(self.bcs.num_bcs() + self.bcs.num_derivatives(), domain=tuple(a.domain))
+        self.S_bc = get_bc_basis(self.bcs, small)               # composite.py:440-450
+        cb = np.asarray(self.bnd_vals(), dtype=float) @ self.S_bc   # BCGeneric.to_orthogonal: c @ S (composite.py:277-280)
+        self.c_b = np.zeros(self.N)
+        self.c_b[:cb.shape[0]] = cb
+
+    def bnd_vals(self):                                         # composite.py:463-470
+        return np.array([float(v) for v in self.bcs.orderedvals()])
+
+    @property
+    def dim(self):
+        return self.a.dim
+
+    def mesh(self, kind="quadrature", N=None):
+        return self.a.mesh(kind, N)
+
+    def _lift(self, x, axis, sign=1.0):
+        shp = [1] * np.ndim(x)
+        shp[axis] = -1
+        return x + sign * self.c_b.reshape(shp)
+
+    def to_orthogonal(self, c, axis=-1):                        # composite.py:583-589
+        return self._lift(self.a.to_orthogonal(c, axis), axis)
+
+    def from_orthogonal(self, x, axis=-1):                      # composite.py:591-597
+        return self.a.from_orthogonal(self._lift(np.asarray(x), axis, -1.0), axis)
+
+    def backward(self, c, N=None, axis=-1):                     # composite.py:611-614
+        return self.orthogonal.backward(self.to_orthogonal(c, axis), N=N, axis=axis)
+
+    def backward_primitive(self, c, k=0, N=None, axis=-1):      # composite.py:616-624
+        return self.orthogonal.backward_primitive(self.to_orthogonal(c, axis), k=k, N=N, axis=axis)
+
+    def forward(self, u, axis=-1):                              # composite.py:626-629
+        return self.from_orthogonal(self.orthogonal.forward(u, axis=axis), axis)
+
+    def scalar_product(self, u, axis=-1):                       # composite.py:631-634
+        return self.a.scalar_product(u, axis)
+
+    def evaluate(self, x, c, axis=-1):                          # composite.py:599-602
         return self.orthogonal.evaluate(x, self.to_orthogonal(c, axis), axis)

@@ -1,0 +1,58 @@
+"""DirectSum spaces (inhomogeneous boundary values: homogeneous Composite + fixed boundary lift, composite.py:502-638 of
+the reference) on the GPU against the oracle's restatement; the lifting basis itself is pinned on the host against the
+reference's own get_bc_basis (tests/test_directsum_host.py)."""
+import numpy as np
+import pytest
+import torch
+
+import jaxfun_oracle as O
+import jaxfun_b200 as jf
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(x, cuda):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(cuda)
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("base", ["Chebyshev", "Legendre"])
+@pytest.mark.parametrize("N,dom", [(12, None), (32, None), (64, (-2.0, 3.0))])
+def test_directsum_1d_matches_oracle(cuda, base, N, dom):
+    bcs = {"left": {"D": 1.0}, "right": {"D": -2.0}}
+    Dp = jf.FunctionSpace(N, getattr(jf, base), bcs, domain=dom)
+    Do = O.DirectSum(O.Composite(N, getattr(O, base), {0: 1, 2: -1}, domain=dom), bcs)
+    assert isinstance(Dp, jf.DirectSum) and Dp.dim == N - 2 == Do.dim
+    assert np.abs(Dp.c_b - Do.c_b).max() < 1e-14
+    rng = np.random.default_rng(N)
+    c = rng.standard_normal((5, N - 2))
+    u_ref = Do.backward(c, axis=-1)
+    assert rel(Dp.backward(dev(c, cuda)), u_ref) < 1e-12
+    assert rel(Dp.backward(dev(c, cuda), N=N + 8), Do.backward(c, N=N + 8, axis=-1)) < 1e-12
+    assert rel(Dp.backward_primitive(dev(c, cuda), 1), Do.backward_primitive(c, 1, axis=-1)) < 1e-11
+    assert rel(Dp.to_orthogonal(dev(c, cuda)), Do.to_orthogonal(c, axis=-1)) < 1e-13
+    a = rng.standard_normal((5, N))
+    assert rel(Dp.from_orthogonal(dev(a, cuda)), Do.from_orthogonal(a, axis=-1)) < 1e-11
+    assert rel(Dp.forward(dev(u_ref, cuda)), Do.forward(u_ref, axis=-1)) < 1e-11
+    assert rel(Dp.forward(Dp.backward(dev(c, cuda))), c) < 1e-11
+    assert rel(Dp.scalar_product(dev(u_ref, cuda)), Do.scalar_product(u_ref, axis=-1)) < 1e-12
+    # the expansion takes the prescribed boundary values whatever the free coefficients are
+    lo, hi = (float(v) for v in Dp.domain)
+    ends = Dp.evaluate(np.array([lo, hi]), dev(c, cuda)).cpu().numpy()
+    assert np.abs(ends - np.array([1.0, -2.0])).max() < 1e-12 * max(1.0, np.abs(u_ref).max())
+
+
+def test_directsum_along_a_leading_axis(cuda):
+    N = 24
+    bcs = {"left": {"D": 0.5}, "right": {"D": 0.25}}
+    Dp = jf.FunctionSpace(N, jf.Legendre, bcs)
+    Do = O.DirectSum(O.Composite(N, O.Legendre, {0: 1, 2: -1}), bcs)
+    rng = np.random.default_rng(1)
+    c = rng.standard_normal((N - 2, 6))
+    u_ref = Do.backward(c, axis=0)
+    assert rel(Dp.backward(dev(c, cuda), axis=0), u_ref) < 1e-12
+    assert rel(Dp.forward(dev(u_ref, cuda), axis=0), c) < 1e-11

@@ -1,0 +1,67 @@
+"""Boundary-lifting basis of DirectSum spaces (composite.py:411-488, 502-638, 835-896 of the reference) on the host:
+the oracle's symbolic restatement and the product's numeric construction against lifting matrices produced by the
+reference's OWN `get_bc_basis` / `BoundaryConditions` (tests/golden/make_golden_bc.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import jaxfun_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = json.load(open(os.path.join(HERE, "golden", "reference_bc_basis.json")))["cases"]
+IDS = [f"{c['space']}-{'-'.join(c['names'])}" for c in CASES]
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_oracle_bc_basis_matches_reference(case):
+    B = O.BoundaryConditions(case["bcs"])
+    assert B.orderednames() == case["names"]
+    assert [float(v) for v in B.orderedvals()] == case["vals"]
+    assert B.num_bcs() == case["num_bcs"] and B.num_derivatives() == case["num_derivatives"]
+    S = O.get_bc_basis(B, getattr(O, case["space"])(B.num_bcs() + B.num_derivatives()))
+    ref = np.array(case["S"])
+    assert S.shape == ref.shape
+    assert np.abs(S - ref).max() < 1e-15
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_product_bc_basis_matches_reference(case):
+    import jaxfun_b200 as jf
+    from jaxfun_b200.galerkin.composite import bc_basis, ordered_bc_names
+    S = bc_basis(case["bcs"], getattr(jf, case["space"]))
+    ref = np.array(case["S"])
+    assert S.shape == ref.shape
+    assert np.abs(S - ref).max() < 1e-14
+    assert ["LR"[side == "right"] + kind for side, kind in ordered_bc_names(case["bcs"])] == case["names"]
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_lift_satisfies_the_boundary_values(case):
+    """The lift sum_b val_b B_b takes exactly the prescribed boundary values (derivatives in the reference coordinate)."""
+    import jaxfun_b200 as jf
+    from jaxfun_b200.galerkin.composite import _BC_ORDER, ordered_bc_names
+    N = 16
+    D = jf.FunctionSpace(N, getattr(jf, case["space"]), case["bcs"])
+    assert type(D).__name__ == "DirectSum" and D.dim == N - case["num_bcs"]
+    assert np.allclose(D.bnd_vals(), case["vals"])
+    for (side, kind), val in zip(ordered_bc_names(case["bcs"]), case["vals"]):
+        f = D.orthogonal.evaluate_basis_derivative(np.array([-1.0 if side == "left" else 1.0]), _BC_ORDER[kind])[0]
+        assert abs(f @ D.c_b - val) < 1e-12 * max(1.0, abs(val)), (side, kind)
+    # and the homogeneous part contributes nothing there
+    for side, kind in ordered_bc_names(case["bcs"]):
+        f = D.a.evaluate_basis_derivative(np.array([-1.0 if side == "left" else 1.0]), _BC_ORDER[kind])[0]
+        assert np.abs(f).max() < 1e-9 * max(1.0, N ** (2 * _BC_ORDER[kind])), (side, kind)
+
+
+def test_oracle_directsum_roundtrip_and_boundary_values():
+    rng = np.random.default_rng(3)
+    bcs = {"left": {"D": 1.0}, "right": {"D": -2.0}}
+    D = O.DirectSum(O.Composite(24, O.Legendre, {0: 1, 2: -1}, domain=(0, 3)), bcs)
+    c = rng.standard_normal((5, 22))
+    u = D.backward(c)
+    assert np.abs(D.forward(u) - c).max() < 1e-12
+    ends = D.evaluate(np.array([0.0, 3.0]), c)
+    assert np.abs(ends - np.array([1.0, -2.0])).max() < 1e-12
+    assert np.abs(D.from_orthogonal(D.to_orthogonal(c)) - c).max() < 1e-12
