@@ -33,7 +33,7 @@ def check(T, To, c, tag):
     ch = T.forward(torch.from_numpy(ur).to(dev)); sp = T.scalar_product(torch.from_numpy(ur).to(dev)); torch.cuda.synchronize()
     e2 = rel(ch.cpu().numpy(), To.forward(ur)); e3 = rel(sp.cpu().numpy(), To.scalar_product(ur))
     print(tag, e1, e2, e3); worst = max(worst, e1, e2, e3)
-    assert max(e1, e2, e3) < 1e-12, (tag, e1, e2, e3)
+    assert e1 < 1e-12 and e2 < 1e-11 and e3 < 1e-12, (tag, e1, e2, e3)   # the suite's bars: forward 1e-11
 for n in (16, 32, 64, 96):
     check(jf.TensorProduct(*[jf.Legendre(n)] * 3), O.TensorProductSpace(*[O.Legendre(n)] * 3), rng.standard_normal((n,) * 3), f"Leg^3 {n}")
 check(jf.TensorProduct(jf.Legendre(128), jf.Legendre(128)), O.TensorProductSpace(O.Legendre(128), O.Legendre(128)),
@@ -64,7 +64,8 @@ def _env(fold):
 def test_fold_check_c_abi(cuda):
     tool = os.path.join(ROOT, "tools", "fold_check")
     if not os.path.exists(tool):
-        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", tool, tool + ".cu",
+        import shutil
+        subprocess.check_call([shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-o", tool, tool + ".cu",
                                "-L" + os.path.join(ROOT, "jaxfun_b200"), "-ljfx", "-Xlinker", "-rpath", "-Xlinker",
                                "$ORIGIN/../jaxfun_b200"])
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -116,3 +117,66 @@ def test_complex_last_axis_nt_variant(cuda):
                        env=e, cwd=ROOT)
     print(r.stdout[-3000:])
     assert r.returncode == 0 and "CPLX NT OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+_SCATTER_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/oracle")
+import jaxfun_b200 as jf
+from jaxfun_b200 import _lib as L, sharding as S
+dev = torch.device("cuda:0")
+N = (32, 48, 64)
+for P in (2, 4, 8):
+    rng = np.random.default_rng(P)
+    T = jf.TensorProduct(*[jf.Legendre(n) for n in N])
+    c = torch.from_numpy(rng.standard_normal(N)).to(dev)
+    u_ref = T.backward(c)
+    for op, sharding, full in ((L.OP_BACKWARD, S.SPECTRAL, c), (L.OP_FORWARD, S.PHYSICAL, u_ref)):
+        be = S.EngineSlabBackend(T, op)
+        blocks = [S.local_block(full, sharding, r, P).contiguous() for r in range(P)]
+        sh = S.sharded_axis(sharding)
+        unsharded = [ax for ax in range(3) if ax != sh]
+        split_axis = unsharded[0]
+        plan = be._plan_for(blocks[0], unsharded)
+        assert plan.scatter_supported(P, split_axis)
+        s0, s1, s2 = plan.shape_out
+        shape = (P * s0, s1 // P, s2) if split_axis == 1 else (s0 // P, P * s1, s2)
+        recv = [torch.full(shape, float("nan"), dtype=torch.float64, device=dev) for _ in range(P)]
+        for r in range(P):
+            plan.execute_scatter(blocks[r], [b.data_ptr() for b in recv], r, split_axis)
+        torch.cuda.synchronize()
+        ys = [be.apply_axes(b, unsharded) for b in blocks]          # ordinary path for comparison
+        for p in range(P):
+            if split_axis == 1:
+                want = torch.cat([torch.chunk(ys[r], P, dim=1)[p] for r in range(P)], dim=0)
+            else:
+                want = torch.cat([torch.chunk(ys[r], P, dim=0)[p] for r in range(P)], dim=1)
+            assert tuple(want.shape) == tuple(recv[p].shape)
+            e = float((recv[p] - want).abs().max()) / float(want.abs().max())
+            assert e < 1e-13, (P, op, p, e)
+    print("P", P, "ok")
+print("SCATTER OK")
+"""
+
+_UNRUN = ("written after the round's GPU budget was spent: checked by the host emulator (tests/emu/fold_emu.cpp) only, opt-in "
+          "until this passes on a GPU")
+
+
+@pytest.mark.xfail(strict=False, reason="jfx_execute_scatter (slab exchange fused into the last contraction pass) " + _UNRUN)
+def test_scatter_execution_emulated_ranks(cuda):
+    """The peer-store exchange on ONE GPU, in its own process: P emulated ranks run phase 1 with jfx_execute_scatter into P
+    receive buffers; every buffer must equal what pack + tiled all-to-all (+ unpack) of the ordinary path leaves on that rank."""
+    r = subprocess.run([sys.executable, "-c", _SCATTER_SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600,
+                       cwd=ROOT)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "SCATTER OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.xfail(strict=False, reason="fold_check --extra (CPLX_NT and jfx_execute_scatter through the C ABI) " + _UNRUN)
+def test_fold_check_extra_c_abi(cuda):
+    tool = os.path.join(ROOT, "tools", "fold_check")
+    assert os.path.exists(tool)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    r = subprocess.run([tool, "--extra"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0 and "FOLD CHECK EXTRA: ALL OK" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
