@@ -383,6 +383,26 @@ int main(int argc, char** argv) {
     printf(g_fail ? "FOLD EMU: %d FAILURES\n" : "FOLD EMU: ALL OK\n", g_fail);
     return g_fail ? 1 : 0;
   }
+  // fold_emu --fuzz count seed : random shapes inside the engine's envelope (extents >= 16, mirrored extent even,
+  // OUT needs an even number of modes), both orders, both parities
+  if (argc == 4 && !strcmp(argv[1], "--fuzz")) {
+    const int count = atoi(argv[2]);
+    std::mt19937 rng((unsigned)atoi(argv[3]));
+    auto rnd = [&](int lo, int hi) { return lo + (int)(rng() % (unsigned)(hi - lo + 1)); };
+    for (int i = 0; i < count; ++i) {
+      const int type = rnd(1, 2), pp = rnd(0, 1);
+      const int n_fold = 2 * rnd(8, 110);
+      int n_other = rnd(16, 200);
+      if (type == FOLD_OUT) n_other &= ~1;
+      const bool nn = rnd(0, 1) != 0;
+      const long long outer = nn ? rnd(1, 3) : rnd(1, 300);
+      const long long inner = nn ? 2 * rnd(1, 140) : 1;
+      run_case(type, pp, n_fold, n_other, outer, inner, 1000u + (unsigned)i);
+    }
+    for (int i = 0; i < count / 4; ++i) run_cplx_case(rnd(1, 200), rnd(1, 200), rnd(1, 300), 5000u + (unsigned)i);
+    printf(g_fail ? "FOLD EMU: %d FAILURES\n" : "FOLD EMU: ALL OK\n", g_fail);
+    return g_fail ? 1 : 0;
+  }
   unsigned seed = 1;
   const int sizes[][2] = {{8, 8}, {16, 16}, {34, 30}, {64, 64}, {96, 64}, {130, 128}, {256, 256}, {48, 32}, {66, 66}, {192, 192}};
   for (auto& s : sizes)

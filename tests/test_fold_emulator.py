@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("emu") / "fold_emu")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "emu", "fold_emu.cpp")])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "emu", "fold_emu.cpp")])
     return exe
 
 
@@ -32,6 +32,13 @@ def test_synthetic_tables_all_variants(emu):
     assert "FOLD EMU: ALL OK" in r.stdout
     assert r.stdout.count("\nok  ") + r.stdout.startswith("ok  ") >= 178
     assert r.stdout.count("variant 4 (complex last axis)") == 18
+
+
+def test_random_shapes(emu):
+    """80 random fold shapes inside the engine's envelope (extents >= 16, ragged tiles, k tails) + 20 of the complex variant."""
+    r = subprocess.run([emu, "--fuzz", "80", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "FOLD EMU: ALL OK" in r.stdout, r.stdout[-3000:]
+    assert r.stdout.count("\nok  ") + r.stdout.startswith("ok  ") == 100
 
 
 @pytest.mark.parametrize("space,n", [("Legendre", 64), ("Legendre", 128), ("ChebyshevU", 64), ("Ultraspherical", 32),
