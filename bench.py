@@ -385,6 +385,41 @@ def run_ours(args):
             "legendre3": {"ms_per_pair": tL, "transforms_per_s": 2e3 / tL, "tflops": ach},
             "chebyshev3": {"ms_per_pair": tC, "transforms_per_s": 2e3 / tC, "gbs_compulsory": achC},
         }
+        # live A/B of the parity folding on the Legendre pair (outside the timed region; context for `roofline`):
+        # the same plans created with JFX_DMMA_FOLD=0 run the plain tensor-core kernel dgemm_dmma_tma
+        try:
+            prev = os.environ.get("JFX_DMMA_FOLD")
+            os.environ["JFX_DMMA_FOLD"] = "0"
+            try:
+                TLp = jf.TensorProduct(*[jf.Legendre(n) for _ in range(3)])
+                qb, qf = TLp._plan(L.OP_BACKWARD, cL), TLp._plan(L.OP_FORWARD, cL)
+            finally:
+                if prev is None:
+                    os.environ.pop("JFX_DMMA_FOLD", None)
+                else:
+                    os.environ["JFX_DMMA_FOLD"] = prev
+            for _ in range(3):
+                qb.execute(cL, uL); qf.execute(uL, oL)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(10):
+                qb.execute(cL, uL); qf.execute(uL, oL)
+            a1.record()
+            torch.cuda.synchronize()
+            t_plain = a0.elapsed_time(a1) / 10
+            ref_o = oL.clone()
+            pLb.execute(cL, uL); pLf.execute(uL, oL)
+            torch.cuda.synchronize()
+            line["fold_ab"] = {
+                "legendre3_ms_per_pair_plain": t_plain, "legendre3_ms_per_pair_folded": tL, "speedup": t_plain / tL,
+                "plain_tflops": (qb.flops + qf.flops) / (t_plain * 1e-3) / 1e12,
+                "plain_frac_of_peak": (qb.flops + qf.flops) / (t_plain * 1e-3) / 1e12 / fp64_peak,
+                "max_rel_diff_folded_vs_plain": float((oL - ref_o).abs().max() / ref_o.abs().max()),
+                "note": "same Legendre^3 backward+forward with JFX_DMMA_FOLD=0 at plan creation (dgemm_dmma_tma), 10 iterations, CUDA events",
+            }
+            del qb, qf, TLp, ref_o
+        except Exception as e:  # pragma: no cover  (context only: never fail the bench line over it)
+            line["fold_ab"] = {"error": f"{type(e).__name__}: {e}"}
     else:
         ach = 2 * 6.0 * float(n) ** 4 / world / (ms / args.steps * 1e-3) / 1e12
         line["roofline"] = {"kernel": "dgemm_dmma_fold / dgemm_dmma_tma inside the slab transform (per rank, incl. exchange time)",
