@@ -376,7 +376,7 @@ struct FoldInfo {
 // images only up to an ulp (fastgl.py:512-544 takes cos(theta) and cos(pi - theta)), which shows in its Vandermonde as an
 // asymmetry of 1e-14 (n = 64) to 4e-13 (n = 1024) of max |T|; a table without the symmetry is off by O(1).  build() folds
 // the mean of the two mirror images, so the folded result differs from the plain contraction by at most half of that.
-inline FoldInfo analyze(const double* T, int rows, int cols, double tol = 1e-12) {
+inline FoldInfo analyze(const double* T, int rows, int cols, double tol = 1e-12, double tol_local = 1e-10) {
   FoldInfo none{FOLD_NONE, 0};
   if (rows < 2 || cols < 2) return none;
   double tmax = 0;
@@ -387,15 +387,22 @@ inline FoldInfo analyze(const double* T, int rows, int cols, double tol = 1e-12)
   }
   if (tmax == 0) return none;
   const double eps = tol * tmax;
+  // Two conditions: the asymmetry is below tol of max |T| everywhere, and below tol_local of the scale of the coefficient it
+  // belongs to (the column of mode k for OUT, the row of mode k for IN).  The second one matters for tables whose modes differ
+  // by orders of magnitude (derivative tables grow like k^4): a small mode must be symmetric relative to ITSELF, because the
+  // caller's coefficients may weight it arbitrarily.  Measured on the host tables: <= 7e-12 (Legendre backward, n = 1024).
   // OUT: T[rows-1-j][k] = sigma_k T[j][k]
   if (rows % 2 == 0 && cols % 2 == 0) {
     for (int pp = 0; pp < 2; ++pp) {
       bool ok = true;
-      for (int j = 0; j < rows / 2 && ok; ++j)
-        for (int k = 0; k < cols; ++k) {
-          const double s = ((k & 1) == pp) ? 1.0 : -1.0;
-          if (std::fabs(T[(long long)(rows - 1 - j) * cols + k] - s * T[(long long)j * cols + k]) > eps) { ok = false; break; }
-        }
+      for (int k = 0; k < cols && ok; ++k) {
+        const double s = ((k & 1) == pp) ? 1.0 : -1.0;
+        double cmax = 0, dmax = 0;
+        for (int j = 0; j < rows; ++j) cmax = std::fmax(cmax, std::fabs(T[(long long)j * cols + k]));
+        for (int j = 0; j < rows / 2; ++j)
+          dmax = std::fmax(dmax, std::fabs(T[(long long)(rows - 1 - j) * cols + k] - s * T[(long long)j * cols + k]));
+        if (dmax > eps || dmax > tol_local * cmax) ok = false;
+      }
       if (ok) return FoldInfo{FOLD_OUT, pp};
     }
   }
@@ -405,8 +412,11 @@ inline FoldInfo analyze(const double* T, int rows, int cols, double tol = 1e-12)
       bool ok = true;
       for (int k = 0; k < rows && ok; ++k) {
         const double s = ((k & 1) == pp) ? 1.0 : -1.0;
+        double rmax = 0, dmax = 0;
+        for (int j = 0; j < cols; ++j) rmax = std::fmax(rmax, std::fabs(T[(long long)k * cols + j]));
         for (int j = 0; j < cols / 2; ++j)
-          if (std::fabs(T[(long long)k * cols + (cols - 1 - j)] - s * T[(long long)k * cols + j]) > eps) { ok = false; break; }
+          dmax = std::fmax(dmax, std::fabs(T[(long long)k * cols + (cols - 1 - j)] - s * T[(long long)k * cols + j]));
+        if (dmax > eps || dmax > tol_local * rmax) ok = false;
       }
       if (ok) return FoldInfo{FOLD_IN, pp};
     }

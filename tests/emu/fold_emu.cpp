@@ -440,6 +440,23 @@ int main(int argc, char** argv) {
     for (auto& v : T) v = U(rng);
     if (analyze(T.data(), 64, 64).type != FOLD_NONE) { printf("FAIL: random table accepted\n"); ++g_fail; }
   }
+  // a mode that is tiny against max |T| but NOT symmetric relative to itself must be refused (local criterion)
+  {
+    const int n = 32;
+    std::vector<double> T(n * n);
+    std::mt19937_64 rng(5);
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    for (int k = 0; k < n; ++k) {
+      const double sc = k == 3 ? 1e-9 : 1.0, sg = (k & 1) ? -1.0 : 1.0;
+      for (int j = 0; j < n / 2; ++j) {
+        const double v = sc * U(rng);
+        T[j * n + k] = v;
+        T[(n - 1 - j) * n + k] = sg * v * (k == 3 ? 1.0 + 1e-6 : 1.0);   // 1e-6 relative asymmetry in the small column: 1e-15 of max |T|
+      }
+    }
+    if (analyze(T.data(), n, n).type != FOLD_NONE) { printf("FAIL: locally asymmetric column accepted\n"); ++g_fail; }
+    else printf("ok   locally asymmetric small column refused\n");
+  }
   printf(g_fail ? "FOLD EMU: %d FAILURES\n" : "FOLD EMU: ALL OK\n", g_fail);
   return g_fail ? 1 : 0;
 }
