@@ -191,8 +191,8 @@ def run_reference(args):
 
 def workload_config(n, gpus):
     if gpus > 1:
-        from jaxfun_b200.sharding import slab_chunks, slab_p2p
-        return {"slab_chunks": slab_chunks(), "slab_p2p": slab_p2p(), "workload": f"C5: Legendre^3 {n}^3 fp64 slab-decomposed (axis0<->axis1 all-to-all), backward+forward per step",
+        from jaxfun_b200.sharding import slab_chunks, slab_fused_pack, slab_p2p
+        return {"slab_chunks": slab_chunks(), "slab_p2p": slab_p2p(), "slab_fused_pack": slab_fused_pack(), "workload": f"C5: Legendre^3 {n}^3 fp64 slab-decomposed (axis0<->axis1 all-to-all), backward+forward per step",
                 "shape": [n, n, n], "parallelism": f"slab{gpus}", "l2": "arrays (>= 134 MB per rank) larger than L2",
                 "scaling_note": "strong scaling of ONE 512^3 problem; its one-GPU time is in single_gpu_same_size "
                                 "(the N=1 default line runs BASELINE configs[1], 256^3, and is not the denominator)"}

@@ -88,6 +88,13 @@ def slab_p2p() -> bool:
     return os.environ.get("JFX_SLAB_P2P", "0") == "1"
 
 
+def slab_fused_pack() -> bool:
+    """JFX_SLAB_FUSED_PACK=1: spectral -> physical keeps the NCCL all-to-all, but the last local pass writes the packed send
+    buffer itself (the scatter epilogue of jfx_execute_scatter aimed at this rank's own buffer) — no jfx_slab_pack launch."""
+    import os
+    return os.environ.get("JFX_SLAB_FUSED_PACK", "0") == "1"
+
+
 def slab_chunks() -> int:
     """Number of chunks of the overlapped exchange (JFX_SLAB_CHUNKS, default 1 = one blocking all-to-all)."""
     import os
@@ -164,6 +171,12 @@ def apply_separable_slab(x, sharding: str, backend: SlabBackend, world_size: int
             return backend.apply_axes(y, [sharded_axis(sharding)])
     if chunks > 1 and world_size > 1:
         return _apply_separable_slab_chunked(x, sharding, backend, world_size, chunks)
+    if world_size > 1 and sharding == SPECTRAL and slab_fused_pack() and hasattr(backend, "packed_phase1"):
+        send = backend.packed_phase1(x, world_size)
+        if send is not None:
+            recv = backend.all_to_all(send)
+            y = recv.reshape((recv.shape[0] * recv.shape[1],) + tuple(recv.shape[2:]))
+            return backend.apply_axes(y, [0])
     dim = x.ndim
     sh = sharded_axis(sharding)
     unsharded = [ax for ax in range(dim) if ax != sh]
@@ -256,6 +269,23 @@ class EngineSlabBackend(SlabBackend):
         plan.execute_scatter(x, [int(p) for p in hdl.buffer_ptrs], dist.get_rank(), split_axis)
         hdl.barrier(channel=t)
         return buf
+
+    def packed_phase1(self, x, world_size: int, rank: int | None = None):
+        """Phase 1 of spectral -> physical with the pack fused into its last pass: returns the send buffer
+        [P, s0, s1/P, s2] (block p goes to rank p), or None when the plan has no scatter epilogue.  The epilogue computes
+        peer[p] + ((rank*s0 + a)*(s1/P) + b')*s2; pointing peer[p] at (block p of the send buffer) - rank*s0*(s1/P)*s2
+        elements turns that into block p, row (a, b') of THIS rank's buffer."""
+        if x.ndim != 3 or x.dtype != torch.float64:
+            return None
+        plan = self._plan_for(x, [1, 2])
+        if not plan.scatter_supported(world_size, 1):
+            return None
+        rank = dist.get_rank() if rank is None else rank
+        s0, s1, s2 = plan.shape_out
+        send = torch.empty((world_size, s0, s1 // world_size, s2), dtype=x.dtype, device=x.device)
+        block = s0 * (s1 // world_size) * s2 * 8
+        plan.execute_scatter(x, [send.data_ptr() + (p - rank) * block for p in range(world_size)], rank, 1)
+        return send
 
     def _repack(self, fn_name: str, x, out_shape, full_shape, axis: int, parts: int):
         from . import _lib as L

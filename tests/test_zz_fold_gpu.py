@@ -154,6 +154,15 @@ for P in (2, 4, 8):
             assert tuple(want.shape) == tuple(recv[p].shape)
             e = float((recv[p] - want).abs().max()) / float(want.abs().max())
             assert e < 1e-13, (P, op, p, e)
+    # the same epilogue aimed at this rank's own send buffer = phase 1 with the pack fused (JFX_SLAB_FUSED_PACK)
+    be = S.EngineSlabBackend(T, L.OP_BACKWARD)
+    for r in range(P):
+        blk = S.local_block(c, S.SPECTRAL, r, P).contiguous()
+        send = be.packed_phase1(blk, P, rank=r)
+        torch.cuda.synchronize()
+        want = be.pack(be.apply_axes(blk, [1, 2]), 1, P)
+        assert send is not None and tuple(send.shape) == tuple(want.shape)
+        assert float((send - want).abs().max()) < 1e-13 * float(want.abs().max()), (P, r)
     print("P", P, "ok")
 print("SCATTER OK")
 """

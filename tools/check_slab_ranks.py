@@ -35,6 +35,6 @@ for it in range(3):                                         # several rounds: ex
 t = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(t)
 if rank == 0:
-    print("SLAB CHECK", "OK" if int(t.item()) == 0 else "FAILED", f"chunks={S.slab_chunks()} p2p={S.slab_p2p()}", flush=True)
+    print("SLAB CHECK", "OK" if int(t.item()) == 0 else "FAILED", f"chunks={S.slab_chunks()} p2p={S.slab_p2p()} fused_pack={S.slab_fused_pack()}", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if int(t.item()) == 0 else 1)

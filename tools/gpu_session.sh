@@ -22,7 +22,7 @@ case "${1:-help}" in
         python tools/profile_step.py chebyshev 256 > /dev/null 2>&1
     ls -la gpurun_out ;;
 4)  # 2 GPUs (gpurun --gpus 2): NCCL exchange vs chunked overlap vs peer-store exchange, same 512^3 workload
-    for mode in "" "JFX_SLAB_CHUNKS=4" "JFX_SLAB_P2P=1"; do
+    for mode in "" "JFX_SLAB_CHUNKS=4" "JFX_SLAB_FUSED_PACK=1" "JFX_SLAB_P2P=1"; do
       env $mode timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
           tools/check_slab_ranks.py 128 2>&1 | tail -4
       env $mode python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 \
