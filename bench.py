@@ -340,13 +340,15 @@ def run_ours(args):
                 "dgemm_dmma_tma (FP64 tensor-core per-axis Vandermonde contraction, TMA-fed mbarrier pipeline)"
         line["roofline"] = {
             "kernel": kname, "bound": "tensor",
-            "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-            "executed": ach_exec, "executed_frac": ach_exec / fp64_peak,
-            "note": ("achieved counts the ALGORITHMIC flops of SURVEY 8(d) (2 N Nq per line and axis); the folded kernel issues "
-                     "half of them (mirror symmetry of the Legendre table), so frac can exceed 1 — executed / executed_frac "
-                     "is the tensor-pipe utilisation") if folded else "executed = algorithmic (no folding)",
+            # primary figures = flops actually ISSUED to the tensor pipe (<= peak by construction); the SURVEY 8(d) algorithmic
+            # count (2 N Nq per line and axis) is reported beside them: the folded kernel needs only half of it
+            "achieved": ach_exec, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_exec / fp64_peak,
+            "algorithmic": {"achieved": ach, "frac": ach / fp64_peak, "flops_per_launch": flops_L / n_l},
+            "note": ("achieved / frac count the multiply-adds the folded kernel issues (half the algorithmic flops of SURVEY 8(d), "
+                     "thanks to the mirror symmetry of the Legendre table) = tensor-pipe utilisation; `algorithmic` rates the same "
+                     "launches by the 8(d) count and can exceed the pipe peak") if folded else "issued = algorithmic flops (no folding)",
             "traffic": ncu_traffic("dgemm_dmma_fold" if folded else "dgemm_dmma"), "launches_per_step": n_l,
-            "avg_launch_ms": tL / n_l, "flops_per_launch": flops_L / n_l, "executed_flops_per_launch": flops_L_exec / n_l,
+            "avg_launch_ms": tL / n_l, "flops_per_launch": flops_L_exec / n_l,
             "peak_source": "live calibration: max(register-resident DMMA loop [best of 1/2/8 CTAs per SM], DFMA loop, "
                            "cuBLAS DGEMM 8192^3); MEASURED_PEAKS.json has no FP64 figure",
             "fp64_calibration_tflops": {"dmma_regs": dm.value, "dfma_regs": df.value, "cublas_dgemm_8192": cublas_tf,
