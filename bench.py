@@ -424,10 +424,22 @@ def run_ours(args):
             line["fold_ab"] = {"error": f"{type(e).__name__}: {e}"}
     else:
         ach = 2 * 6.0 * float(n) ** 4 / world / (ms / args.steps * 1e-3) / 1e12
+        # share of the algorithmic flops the local plans actually issue (0.5 when every pass is parity-folded)
+        issued_ratio = 1.0
+        try:
+            from jaxfun_b200.engine import Plan as _Plan
+            plans = [p for be in S._backends.values() for p in be._plans.values() if isinstance(p, _Plan)]
+            fa, fe = sum(p.flops for p in plans), sum(p.flops_executed for p in plans)
+            if fa > 0:
+                issued_ratio = fe / fa
+        except Exception:
+            pass
         line["roofline"] = {"kernel": "dgemm_dmma_fold / dgemm_dmma_tma inside the slab transform (per rank, incl. exchange time)",
-                            "bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                            "frac": ach / fp64_peak, "traffic": None,
-                            "note": "algorithmic flops (6 N^4 per transform); parity-folded passes issue half of them",
+                            "bound": "tensor", "achieved": ach * issued_ratio, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": ach * issued_ratio / fp64_peak, "traffic": None,
+                            "algorithmic": {"achieved": ach, "frac": ach / fp64_peak},
+                            "note": "achieved = flops issued per rank (parity-folded passes issue half of the 6 N^4 per transform "
+                                    "counted in `algorithmic`), over the whole step time including the exchange",
                             "peak_source": "live calibration (see N=1 line)"}
         if rank == 0:
             # same global problem on ONE GPU, for parallel-efficiency context (not part of `value`)
