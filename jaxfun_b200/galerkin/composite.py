@@ -255,11 +255,19 @@ class DirectSum:
         if type(a.orthogonal).__name__ == "Jacobi":
             kw = dict(alpha=a.orthogonal.alpha, beta=a.orthogonal.beta)
         self.S_bc = bc_basis(bcs, type(a.orthogonal), **kw)
-        vals = np.array([float(bcs[side][kind]) for side, kind in ordered_bc_names(bcs)])
-        cb = vals @ self.S_bc                                  # BCGeneric.to_orthogonal(bnd_vals) = vals @ S
-        self.c_b = np.zeros(self.N)
-        self.c_b[:cb.shape[0]] = cb
+        self.raw_vals = [bcs[side][kind] for side, kind in ordered_bc_names(bcs)]
+        try:
+            vals = np.array([float(v) for v in self.raw_vals])
+        except (TypeError, ValueError):
+            # boundary values that are functions of the OTHER coordinates (sympy expressions / callables / sample arrays):
+            # only meaningful inside a tensor product (DirectSumTPS, tensorproductspace.py:575-851)
+            vals = None
         self._bvals = vals
+        self.c_b = None
+        if vals is not None:
+            cb = vals @ self.S_bc                              # BCGeneric.to_orthogonal(bnd_vals) = vals @ S
+            self.c_b = np.zeros(self.N)
+            self.c_b[:cb.shape[0]] = cb
         self._lift_cache: dict = {}
 
     # ---- what the reference forwards to the homogeneous part (composite.py:521-537) -----------------------------
@@ -291,7 +299,13 @@ class DirectSum:
     def get_homogeneous(self):
         return self.a
     def bnd_vals(self) -> np.ndarray:
+        self._require_constant()
         return self._bvals.copy()
+
+    def _require_constant(self) -> None:
+        if self.c_b is None:
+            raise ValueError("the boundary values of this DirectSum depend on other coordinates: use it as a factor of "
+                             "TensorProduct(...), which builds the lift (DirectSumTPS)")
 
     # ---- the constant lift, broadcast along one axis --------------------------------------------------------------
     def _add(self, x, vec: np.ndarray, axis: int, sign: float = 1.0, key=None):
@@ -309,6 +323,7 @@ class DirectSum:
         return torch.add(x, t.reshape(shp), alpha=sign)
 
     def _physical_lift(self, n_quad: int, k: int) -> np.ndarray:
+        self._require_constant()
         key = ("u_b", n_quad, k)
         v = self._lift_cache.get(key)
         if v is None:
@@ -318,26 +333,32 @@ class DirectSum:
 
     # ---- transforms (composite.py:583-634) ------------------------------------------------------------------------------
     def to_orthogonal(self, c, axis: int = -1):
+        self._require_constant()
         return self._add(self.a.to_orthogonal(c, axis), self.c_b, axis, key="c_b")
 
     def from_orthogonal(self, x, axis: int = -1):
+        self._require_constant()
         return self.a.from_orthogonal(self._add(x, self.c_b, axis, -1.0, key="c_b"), axis)
 
     def backward(self, c, N=None, axis: int = -1):
+        self._require_constant()
         n_quad = self.num_quad_points if N is None else int(N)
         return self._add(self.a.backward(c, N, axis), self._physical_lift(n_quad, 0), axis, key=("dev_u_b", n_quad, 0))
 
     def backward_primitive(self, c, k: int = 0, N=None, axis: int = -1):
+        self._require_constant()
         n_quad = self.num_quad_points if N is None else int(N)
         return self._add(self.a.backward_primitive(c, k, N, axis), self._physical_lift(n_quad, k), axis, key=("dev_u_b", n_quad, k))
 
     def forward(self, u, axis: int = -1):
+        self._require_constant()
         return self.from_orthogonal(self.orthogonal.forward(u, axis), axis)
 
     def scalar_product(self, u, axis: int = -1):
         return self.a.scalar_product(u, axis)
 
     def evaluate(self, x, c, axis: int = -1):
+        self._require_constant()
         X = np.atleast_1d(np.asarray(self.orthogonal.map_reference_domain(np.asarray(x, dtype=float))))
         lift = np.asarray(self.orthogonal.eval_basis_functions(X)) @ self.c_b
         return self._add(self.a.evaluate(x, c, axis), np.ascontiguousarray(lift), axis)
@@ -349,7 +370,7 @@ def FunctionSpace(N: int, space, bcs=None, domain=None, name: str = "fun", fun_s
     Legendre space -> phi_k = P_k - P_{k+2} (both families have P_k(+-1) = (+-1)^k)."""
     if bcs is None:
         return space(N, domain=domain, name=name, fun_str=fun_str, **kw)
-    if any(v != 0 for side in bcs.values() for v in side.values()):
+    if any(not (isinstance(v, (int, float)) and v == 0) for side in bcs.values() for v in side.values()):
         # functionspace.py:150-173: homogeneous Composite (+) boundary lift
         hom = {side: {kind: 0 for kind in kinds} for side, kinds in bcs.items()}
         return DirectSum(FunctionSpace(N, space, hom, domain=domain, name=name, fun_str=fun_str, scaling=scaling, **kw), bcs)

@@ -152,8 +152,152 @@ class TensorProductSpace:
         return c
 
 
+def _sample_boundary_value(v, symbols, grids, shape):
+    """Boundary datum on the quadrature mesh of the other axes: number | sympy expression in x, y, z | callable | samples."""
+    import sympy as sp
+    if callable(v) and not isinstance(v, sp.Basic):
+        return np.broadcast_to(np.asarray(v(*grids)), shape).copy()
+    if isinstance(v, np.ndarray):
+        assert tuple(v.shape) == tuple(shape), f"boundary samples have shape {v.shape}, the mesh of the other axes {shape}"
+        return v
+    e = sp.sympify(v)
+    if not e.free_symbols:
+        return np.full(shape, complex(e) if e.has(sp.I) else float(e))
+    by_name = {str(sym): sym for sym in e.free_symbols}
+    unknown = set(by_name) - set(symbols)
+    assert not unknown, f"boundary value {e} depends on {sorted(unknown)}; the other axes are {symbols}"
+    f = sp.lambdify([by_name.get(n, sp.Symbol(n)) for n in symbols], e, modules="numpy")
+    return np.broadcast_to(np.asarray(f(*grids)), shape).copy()
+
+
+class DirectSumTPS:
+    """Tensor product with ONE DirectSum factor whose boundary values may depend on the other coordinates
+    (`DirectSumTPS`, tensorproductspace.py:575-851; the case of `examples/poisson2D_periodic.py`).
+
+    The lift is a fixed element of the orthogonal tensor-product space: every boundary datum g_b(other coordinates) is
+    projected onto the other factors (`project1D` = forward transform of its samples, inner.py:1027-1046) and multiplied
+    by the lifting function B_b along the DirectSum axis (tensorproductspace.py:817-830).  Its coefficients `lift` are
+    built once on the host; transforms are the homogeneous tensor product's engine plans plus that constant:
+    `backward(c) = hom.backward(c) + orthogonal.backward(lift)` (cached), `forward(u) = hom.from_orthogonal(
+    orthogonal.forward(u) - lift)`.  Two inhomogeneous directions (corner compatibility, :620-668) are not built."""
+
+    def __init__(self, basespaces, system=None, name: str = "DSTPS") -> None:
+        from .composite import DirectSum
+        idx = [i for i, s in enumerate(basespaces) if isinstance(s, DirectSum)]
+        if len(idx) != 1:
+            raise NotImplementedError("DirectSumTPS with two inhomogeneous directions is not part of this build")
+        b, d = idx[0], len(basespaces)
+        if d == 3 and b == 0:
+            raise ValueError("DirectSum cannot be the first space in a 3D tensor product.")   # tensorproductspace.py:612-615
+        D = basespaces[b]
+        self.bc_axis, self.name, self.system = b, name, system
+        self.basespaces = list(basespaces)
+        self.hom = TensorProduct(*[s.a if i == b else s for i, s in enumerate(basespaces)], system=system, name=name + "0")
+        self.orthogonal = TensorProduct(*[s.orthogonal if i == b else s.get_orthogonal() for i, s in enumerate(basespaces)],
+                                        system=system, name=name + "o")
+        others = [s for i, s in enumerate(self.hom.basespaces) if i != b]
+        names = ["x", "y", "z"][:d]
+        symbols = [n for i, n in enumerate(names) if i != b]
+        grids = np.meshgrid(*[np.asarray(s.mesh(), dtype=float) for s in others], indexing="ij")
+        shape = tuple(g.shape for g in grids)[0]
+        lift = None
+        for j, v in enumerate(D.raw_vals):
+            gh = _sample_boundary_value(v, symbols, grids, shape)
+            for ax, s in enumerate(others):                    # project1D along every other axis, then to orthogonal
+                T = np.asarray(s._dense_table(L.OP_FORWARD, s.dim, s.num_quad_points, 0))
+                gh = np.moveaxis(np.tensordot(T, gh, axes=(1, ax)), 0, ax)
+                if not s.is_orthogonal:
+                    gh = np.moveaxis(np.tensordot(np.asarray(s.S).T, gh, axes=(1, ax)), 0, ax)
+            row = np.zeros(D.N)
+            row[:D.S_bc.shape[1]] = D.S_bc[j]
+            term = np.expand_dims(gh, b) * row.reshape([-1 if i == b else 1 for i in range(d)])
+            lift = term if lift is None else lift + term
+        if not self.orthogonal.complex_data:
+            assert np.abs(np.imag(lift)).max() == 0 if np.iscomplexobj(lift) else True
+            lift = np.real(lift)
+        self.lift = np.ascontiguousarray(lift)
+        self._cache: dict = {}
+
+    # ---- bookkeeping forwarded to the homogeneous product --------------------------------------------------------
+    def __len__(self) -> int:
+        return len(self.basespaces)
+    @property
+    def dims(self) -> int:
+        return len(self.basespaces)
+    @property
+    def shape(self):
+        return self.hom.shape
+    @property
+    def num_dofs(self):
+        return self.hom.num_dofs
+    @property
+    def dim(self) -> int:
+        return self.hom.dim
+    def mesh(self, kind: str = "quadrature", N=None, broadcast: bool = True):
+        return self.hom.mesh(kind, N, broadcast)
+    def get_homogeneous(self):
+        return self.hom
+    def get_orthogonal(self):
+        return self.orthogonal
+
+    # ---- the constant lift ----------------------------------------------------------------------------------------------
+    def _lift_like(self, x):
+        if isinstance(x, np.ndarray):
+            return self.lift.astype(x.dtype) if np.iscomplexobj(x) or not np.iscomplexobj(self.lift) else self.lift
+        import torch
+        key = ("lift", x.device, x.dtype)
+        t = self._cache.get(key)
+        if t is None:
+            t = self._cache[key] = torch.from_numpy(self.lift).to(device=x.device, dtype=x.dtype)
+        return t
+
+    def _physical_lift(self, like, k, N):
+        key = ("phys", getattr(like, "device", "host"), like.dtype, k, N)
+        u = self._cache.get(key)
+        if u is None:
+            lc = self._lift_like(like)
+            u = self.orthogonal.backward(lc, N) if k is None else self.orthogonal.backward_primitive(lc, k, N)
+            self._cache[key] = u
+        return u
+
+    def _coeff_dtype(self, c):
+        c, _ = as_jfx_array(c, self.orthogonal.complex_data)
+        return c
+
+    # ---- transforms (tensorproductspace.py:781-851) ----------------------------------------------------------------------
+    def to_orthogonal(self, c):
+        c = self._coeff_dtype(c)
+        return self.hom.to_orthogonal(c) + self._lift_like(c)
+
+    def from_orthogonal(self, a):
+        a = self._coeff_dtype(a)
+        return self.hom.from_orthogonal(a - self._lift_like(a))
+
+    def backward(self, c, N=None):
+        c = self._coeff_dtype(c)
+        N = None if N is None else tuple(N)
+        return self.hom.backward(c, N) + self._physical_lift(c, None, N)
+
+    def backward_primitive(self, c, k, N=None):
+        c = self._coeff_dtype(c)
+        k, N = tuple(int(v) for v in k), None if N is None else tuple(N)
+        return self.hom.backward_primitive(c, k, N) + self._physical_lift(c, k, N)
+
+    def forward(self, u):
+        return self.from_orthogonal(self.orthogonal.forward(u))
+
+    def scalar_product(self, u):
+        raise RuntimeError("Scalar product requires homogeneous test space (call on get_homogeneous())")
+
+    def evaluate_mesh(self, c, kind: str = "quadrature", N=None):
+        return self.orthogonal.evaluate_mesh(self.to_orthogonal(c), kind, N)
+
+
 def TensorProduct(*basespaces: OrthogonalSpace, system=None, name: str = "T") -> TensorProductSpace:
-    """Factory (tensorproductspace.py:507-557): deep-copies the factor spaces."""
+    """Factory (tensorproductspace.py:507-557): deep-copies the factor spaces; a DirectSum factor makes it a DirectSumTPS."""
+    from .composite import DirectSum
+    if any(isinstance(s, DirectSum) for s in basespaces):
+        return DirectSumTPS(list(basespaces), system, name)
     spaces = []
     for s in basespaces:
         plans, s._plans = s._plans, {}

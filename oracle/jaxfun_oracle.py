@@ -1078,3 +1078,51 @@ class DirectSum:
 
     def evaluate(self, x, c, axis=-1):                          # composite.py:599-602
         return self.orthogonal.evaluate(x, self.to_orthogonal(c, axis), axis)
+
+
+class DirectSumTPS:
+    """tensorproductspace.py:575-851 for ONE DirectSum factor (the poisson2D_periodic case): the boundary data are
+    projected onto the other factors (`project1D`, inner.py:1027-1046 = forward transform of their samples on the mesh),
+    `to_orthogonal` adds `pad(v.to_orthogonal(bndvals))` for the tensor space v = (others x BCGeneric) (:817-830),
+    backward / forward go through the orthogonal tensor product (:781-790)."""
+
+    def __init__(self, spaces, bc_axis, bcs, boundary_samples):
+        # spaces: factor spaces with the homogeneous Composite on `bc_axis`; boundary_samples[j]: datum j sampled on the
+        # tensor mesh of the other axes (what lambdify(...)(V.mesh()) gives in project1D)
+        self.spaces, self.b = list(spaces), bc_axis
+        a = self.spaces[bc_axis]
+        self.bcs = BoundaryConditions(bcs)
+        small = type(a.orthogonal)(self.bcs.num_bcs() + self.bcs.num_derivatives(), domain=tuple(a.domain))
+        self.S_bc = get_bc_basis(self.bcs, small)
+        self.orth = TensorProductSpace(*[s.orthogonal if hasattr(s, "S") else s for s in self.spaces])   # get_orthogonal()
+        others = [s for i, s in enumerate(self.spaces) if i != bc_axis]
+        uh = []
+        for g in boundary_samples:                               # project1D onto the other factors
+            g = np.asarray(g)
+            for ax, sp_ in enumerate(others):
+                g = sp_.forward(g, axis=ax)
+                if hasattr(sp_, "S"):
+                    g = sp_.to_orthogonal(g, axis=ax)
+            uh.append(g)
+        bnd = np.stack(uh, axis=bc_axis)                         # the BCGeneric axis holds the boundary index (:705-708)
+        ai = np.moveaxis(np.tensordot(self.S_bc.T, bnd, axes=(1, bc_axis)), 0, bc_axis)   # BCGeneric.to_orthogonal: @ S
+        full = [s.orthogonal.N if hasattr(s, "S") else s.N for s in self.spaces]
+        self.lift = np.pad(ai, [(0, full[i] - ai.shape[i]) for i in range(len(full))])     # jnp.pad (:826-829)
+
+    def _hom(self, c, name):
+        for ax, s in enumerate(self.spaces):
+            if hasattr(s, "S"):
+                c = getattr(s, name)(c, axis=ax)
+        return c
+
+    def to_orthogonal(self, c):                                  # :817-830
+        return self._hom(np.asarray(c), "to_orthogonal") + self.lift
+
+    def from_orthogonal(self, c):                                # :832-851
+        return self._hom(np.asarray(c) - self.lift, "from_orthogonal")
+
+    def backward(self, c, N=None):                               # :781-786
+        return self.orth.backward(self.to_orthogonal(c), N=N)
+
+    def forward(self, u):                                        # :788-790
+        return self.from_orthogonal(self.orth.forward(u))

@@ -56,3 +56,30 @@ def test_directsum_along_a_leading_axis(cuda):
     u_ref = Do.backward(c, axis=0)
     assert rel(Dp.backward(dev(c, cuda), axis=0), u_ref) < 1e-12
     assert rel(Dp.forward(dev(u_ref, cuda), axis=0), c) < 1e-11
+
+
+def test_directsum_tensor_product_fourier_legendre(cuda):
+    """Fourier x (Legendre Dirichlet with boundary data depending on x) — the space of examples/poisson2D_periodic.py —
+    against the oracle's DirectSumTPS; the boundary functions are reproduced for arbitrary free coefficients."""
+    import sympy as sp
+    x, y = sp.symbols("x y", real=True)
+    ue = sp.cos(2 * x) * (1 - y**2) + sp.sin(x) * y + 0.3
+    bcs = {"left": {"D": ue.subs(y, -1)}, "right": {"D": ue.subs(y, 1)}}
+    NF, NL = 32, 24
+    T = jf.TensorProduct(jf.Fourier(NF), jf.FunctionSpace(NL, jf.Legendre, bcs))
+    Fo, Co = O.Fourier(NF), O.Composite(NL, O.Legendre, {0: 1, 2: -1})
+    xm = np.asarray(Fo.mesh())
+    samples = [sp.lambdify(x, ue.subs(y, s))(xm) + 0 * xm for s in (-1, 1)]
+    To = O.DirectSumTPS([Fo, Co], 1, {"left": {"D": 1}, "right": {"D": 1}}, samples)
+    assert np.abs(T.lift - To.lift).max() < 1e-14
+    rng = np.random.default_rng(5)
+    c = rng.standard_normal((NF, NL - 2)) + 1j * rng.standard_normal((NF, NL - 2))
+    assert rel(T.to_orthogonal(dev(c, cuda)), To.to_orthogonal(c)) < 1e-13
+    u_ref = To.backward(c)
+    assert rel(T.backward(dev(c, cuda)), u_ref) < 1e-12
+    assert rel(T.forward(dev(u_ref, cuda)), To.forward(u_ref)) < 1e-11
+    assert rel(T.forward(T.backward(dev(c, cuda))), c) < 1e-11
+    a = T.to_orthogonal(dev(c, cuda)).cpu().numpy()
+    k = np.arange(NL)
+    assert np.abs(Fo.backward(a @ ((-1.0) ** k), axis=0) - samples[0]).max() < 1e-12
+    assert np.abs(Fo.backward(a @ np.ones(NL), axis=0) - samples[1]).max() < 1e-12

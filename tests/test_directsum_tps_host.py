@@ -1,0 +1,108 @@
+"""DirectSumTPS (tensor product with one DirectSum factor whose boundary data depend on the other coordinates,
+tensorproductspace.py:575-851 of the reference; the case of examples/poisson2D_periodic.py) WITHOUT a GPU: the product's
+host-built lift and its transform algebra, run on a numpy stand-in for the engine plans, against the oracle's restatement,
+plus the property that defines the space: the expansion takes the prescribed boundary functions whatever the free
+coefficients are.  (The reference's own DirectSumTPS needs its flax-based `la` package and cannot run here: parity of this
+class is pinned through `get_bc_basis` — tests/test_directsum_host.py — and these properties only.)"""
+import numpy as np
+import pytest
+import sympy as sp
+
+import jaxfun_oracle as O
+
+
+@pytest.fixture()
+def numpy_engine(monkeypatch):
+    """Replace the device plans by dense numpy table applications (same tables the engine would get)."""
+    import jaxfun_b200 as jf  # noqa: F401
+    from jaxfun_b200 import _lib as L
+    from jaxfun_b200.galerkin import tensorproductspace as TP
+    from jaxfun_b200.galerkin.orthogonal import OrthogonalSpace
+
+    def run(self, op, x, axis, N=None, k=0, table=None, cache=True):
+        x = np.asarray(x)
+        axis = axis % x.ndim
+        if table is None:
+            if op in (L.OP_FORWARD, L.OP_SCALAR_PRODUCT):
+                n_quad, n_coeff = x.shape[axis], self.dim
+            else:
+                n_quad, n_coeff = (self.num_quad_points if N is None else int(N)), x.shape[axis]
+            table = self._dense_table(op, n_coeff, n_quad, k)
+        return np.moveaxis(np.tensordot(table, x, axes=(1, axis)), 0, axis)
+
+    def tp(self, op, x, N=None, k=None):
+        x = np.asarray(x)
+        if self.complex_data and not np.iscomplexobj(x):
+            x = x.astype(complex)
+        for ax, s in enumerate(self.basespaces):
+            x = run(s, op, x, ax, None if N is None else N[ax], 0 if k is None else k[ax])
+        return x
+
+    monkeypatch.setattr(OrthogonalSpace, "_run", run)
+    monkeypatch.setattr(TP.TensorProductSpace, "backward", lambda self, c, N=None: tp(self, L.OP_BACKWARD, c, N))
+    monkeypatch.setattr(TP.TensorProductSpace, "forward", lambda self, u: tp(self, L.OP_FORWARD, u))
+    monkeypatch.setattr(TP, "as_jfx_array", lambda x, cplx=False: (
+        (np.asarray(x).astype(complex) if cplx and not np.iscomplexobj(x) else np.asarray(x)), True))
+    return L
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def test_fourier_x_legendre_directsum(numpy_engine):
+    import jaxfun_b200 as jf
+    x, y = sp.symbols("x y", real=True)
+    ue = sp.cos(2 * x) * (1 - y**2) + sp.sin(x) * y + 0.3          # boundary data depend on x
+    bcs = {"left": {"D": ue.subs(y, -1)}, "right": {"D": ue.subs(y, 1)}}
+    NF, NL = 16, 12
+    T = jf.TensorProduct(jf.Fourier(NF), jf.FunctionSpace(NL, jf.Legendre, bcs))
+    assert type(T).__name__ == "DirectSumTPS" and T.num_dofs == (NF, NL - 2)
+    Fo, Co = O.Fourier(NF), O.Composite(NL, O.Legendre, {0: 1, 2: -1})
+    xm = np.asarray(Fo.mesh())
+    samples = [sp.lambdify(x, ue.subs(y, s))(xm) + 0 * xm for s in (-1, 1)]
+    To = O.DirectSumTPS([Fo, Co], 1, {"left": {"D": 1}, "right": {"D": 1}}, samples)
+    assert rel(T.lift, To.lift) < 1e-14
+    rng = np.random.default_rng(0)
+    c = rng.standard_normal((NF, NL - 2)) + 1j * rng.standard_normal((NF, NL - 2))
+    assert rel(T.to_orthogonal(c), To.to_orthogonal(c)) < 1e-14
+    assert rel(T.backward(c), To.backward(c)) < 1e-13
+    u = To.backward(c)
+    assert rel(T.forward(u), To.forward(u)) < 1e-12
+    assert rel(T.forward(T.backward(c)), c) < 1e-12
+    # the boundary functions are reproduced: evaluate the orthogonal expansion at y = -1 / +1 (P_k(-1) = (-1)^k, P_k(1) = 1)
+    a = T.to_orthogonal(c)
+    k = np.arange(NL)
+    assert np.abs(Fo.backward(a @ ((-1.0) ** k), axis=0) - samples[0]).max() < 1e-12
+    assert np.abs(Fo.backward(a @ np.ones(NL), axis=0) - samples[1]).max() < 1e-12
+    with pytest.raises(RuntimeError):
+        T.scalar_product(u)
+
+
+def test_three_factors_with_a_homogeneous_composite(numpy_engine):
+    import jaxfun_b200 as jf
+    x, y = sp.symbols("x y", real=True)
+    g0, g1 = sp.sin(x) * (1 - y**2), sp.cos(x) + y
+    T = jf.TensorProduct(jf.Fourier(8), jf.FunctionSpace(10, jf.Chebyshev, {"left": {"D": 0}, "right": {"D": 0}}),
+                         jf.FunctionSpace(12, jf.Legendre, {"left": {"D": g0}, "right": {"D": g1}}))
+    F3, C3, L3 = O.Fourier(8), O.Composite(10, O.Chebyshev, {0: 1, 2: -1}), O.Composite(12, O.Legendre, {0: 1, 2: -1})
+    X, Y = np.meshgrid(np.asarray(F3.mesh()), np.asarray(C3.mesh()), indexing="ij")
+    samples = [sp.lambdify((x, y), g)(X, Y) + 0 * X for g in (g0, g1)]
+    To = O.DirectSumTPS([F3, C3, L3], 2, {"left": {"D": 1}, "right": {"D": 1}}, samples)
+    assert rel(T.lift, To.lift) < 1e-14
+    rng = np.random.default_rng(1)
+    c = rng.standard_normal((8, 8, 10)) + 1j * rng.standard_normal((8, 8, 10))
+    assert rel(T.backward(c), To.backward(c)) < 1e-13
+    assert rel(T.forward(T.backward(c)), c) < 1e-12
+
+
+def test_unsupported_layouts_are_refused():
+    import jaxfun_b200 as jf
+    x = sp.Symbol("x", real=True)
+    D = jf.FunctionSpace(8, jf.Legendre, {"left": {"D": sp.sin(x)}, "right": {"D": 0}})
+    with pytest.raises(ValueError):
+        D.backward(np.zeros(6))                                   # function-valued data need the tensor product
+    with pytest.raises(NotImplementedError):
+        jf.TensorProduct(D, D)                                    # two inhomogeneous directions
+    with pytest.raises(ValueError):                               # tensorproductspace.py:612-615
+        jf.TensorProduct(jf.FunctionSpace(8, jf.Legendre, {"left": {"D": 1.0}, "right": {"D": 0}}), jf.Fourier(8), jf.Fourier(8))
