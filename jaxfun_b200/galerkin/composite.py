@@ -210,6 +210,19 @@ def stencil_from_bcs(bcs: dict, orthogonal) -> dict:
     return st
 
 
+def _is_zero(v) -> bool:
+    """`v != 0` of BoundaryConditions.is_homogeneous (composite.py:103-109) for numbers, numpy scalars and sympy values."""
+    if callable(v) and not isinstance(v, sp.Basic):
+        return False
+    if isinstance(v, np.ndarray):
+        return False
+    try:
+        e = sp.sympify(v)
+        return (not e.free_symbols) and complex(e) == 0
+    except (sp.SympifyError, TypeError, ValueError):
+        return False
+
+
 def bc_basis(bcs: dict, orthogonal_cls, **kw) -> np.ndarray:
     """Numeric counterpart of `get_bc_basis` (composite.py:835-896): rows = lifting functions B_i = sum_j S_ij P_j with
     (boundary functional b)(B_i) = delta_bi, built on the first block of `nb` consecutive modes whose boundary matrix is
@@ -370,7 +383,7 @@ def FunctionSpace(N: int, space, bcs=None, domain=None, name: str = "fun", fun_s
     Legendre space -> phi_k = P_k - P_{k+2} (both families have P_k(+-1) = (+-1)^k)."""
     if bcs is None:
         return space(N, domain=domain, name=name, fun_str=fun_str, **kw)
-    if any(not (isinstance(v, (int, float)) and v == 0) for side in bcs.values() for v in side.values()):
+    if any(not _is_zero(v) for side in bcs.values() for v in side.values()):
         # functionspace.py:150-173: homogeneous Composite (+) boundary lift
         hom = {side: {kind: 0 for kind in kinds} for side, kinds in bcs.items()}
         return DirectSum(FunctionSpace(N, space, hom, domain=domain, name=name, fun_str=fun_str, scaling=scaling, **kw), bcs)
