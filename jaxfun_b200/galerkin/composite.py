@@ -383,6 +383,7 @@ def FunctionSpace(N: int, space, bcs=None, domain=None, name: str = "fun", fun_s
     Legendre space -> phi_k = P_k - P_{k+2} (both families have P_k(+-1) = (+-1)^k)."""
     if bcs is None:
         return space(N, domain=domain, name=name, fun_str=fun_str, **kw)
+    bcs = {side: {kind: (0 if _is_zero(v) else v) for kind, v in kinds.items()} for side, kinds in bcs.items()}
     if any(not _is_zero(v) for side in bcs.values() for v in side.values()):
         # functionspace.py:150-173: homogeneous Composite (+) boundary lift
         hom = {side: {kind: 0 for kind in kinds} for side, kinds in bcs.items()}
