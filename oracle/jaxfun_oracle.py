@@ -15,6 +15,10 @@ derivative / complex-line variants, mixed-basis tensor products, nonlinear terms
 tables) are replayed against this oracle in `tests/test_golden.py` (nodes / weights / wavenumbers
 bit-exact, transforms < 1e-12; observed <= 3e-15).  What that does NOT pin is XLA's last-bit rounding
 of cos / FFT / dot versus numpy / scipy ("bit level unpinned" — see DESIGN.md).
+The widening rows are pinned less directly: Composite / DirectSum through the reference's own `get_bc_basis`
+output (`tests/golden/reference_bc_basis.json`, made by tests/golden/make_golden_bc.py) and its examples' acceptance
+criteria; `DirectSumTPS` is PARITY UNPINNED (the reference class needs its flax-based `la` package, which cannot be
+mounted here) and is checked through the property that defines it — the prescribed boundary functions are reproduced.
 
 Third-party arithmetic restated here: jax.numpy.fft / jax.scipy.fft.dct (jaxlib 0.11.0) ->
 numpy.fft / scipy.fft; scipy.special.roots_jacobi (scipy 1.17.0 pinned, 1.18.1 here).
