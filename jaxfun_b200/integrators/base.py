@@ -89,11 +89,35 @@ class BaseIntegrator:
         raise NotImplementedError
 
     # base.py:269-344 (no snapshots/progress bar: the loop itself)
-    def solve(self, u0, dt: float, steps: int, N=None):
+    def solve(self, u0, dt: float, steps: int, N=None, graph: bool = False):
+        """`graph=True` captures ONE step (its nonlinear evaluations and fused diagonal combinations: only kernel launches,
+        no allocation outside the capture pool, no host synchronisation) into a CUDA graph after two eager warm-up steps and
+        replays it — what the reference gets from `lax.fori_loop` inside `jit` (base.py:329): one launch per step instead of
+        ~25 for ETDRK4."""
         self.setup(dt)
         u = u0
-        for _ in range(steps):
-            u = self.step(u, dt, N)
+        done = 0
+        if graph and steps > 3 and torch is not None and getattr(u0, "is_cuda", False):
+            side = torch.cuda.Stream(device=u0.device)
+            side.wait_stream(torch.cuda.current_stream(u0.device))
+            with torch.cuda.stream(side):                      # warm-up on the capture stream: plans, tables, workspaces
+                buf = u0
+                for _ in range(2):
+                    buf = self.step(buf, dt, N)
+                    done += 1
+                static_in = buf.clone()
+            torch.cuda.current_stream(u0.device).wait_stream(side)
+            torch.cuda.synchronize(u0.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                static_out = self.step(static_in, dt, N)
+            for _ in range(steps - done):
+                g.replay()
+                static_in.copy_(static_out)
+            u = static_in.clone()
+        else:
+            for _ in range(steps):
+                u = self.step(u, dt, N)
         if not bool(torch.isfinite(torch.view_as_real(u) if u.is_complex() else u).all()):
             raise FloatingPointError("time integration diverged")  # base.py:332-334
         return u

@@ -189,3 +189,37 @@ def test_fold_check_extra_c_abi(cuda):
     r = subprocess.run([tool, "--extra"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     print(r.stdout[-4000:])
     assert r.returncode == 0 and "FOLD CHECK EXTRA: ALL OK" in r.stdout, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+_GRAPH_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/oracle")
+import jaxfun_b200 as jf, jaxfun_oracle as O
+from jaxfun_b200.integrators import ETDRK4, RK4, NonlinearTerm, field
+dev = torch.device("cuda:0")
+N, dom = 64, (-np.pi, np.pi)
+V, Vo = jf.Fourier(N, domain=dom), O.Fourier(N, domain=dom)
+k = Vo.wavenumbers().astype(float) * float(Vo.domain_factor)
+Ldiag = torch.from_numpy(1j * k**3).to(dev)
+u, (x,) = field(V)
+term = NonlinearTerm(V, -u * u.diff(x))
+u0 = torch.from_numpy(Vo.forward(0.5 / np.cosh(0.5 * Vo.mesh()) ** 2 + 0j)).to(dev)
+for cls, dt in ((ETDRK4, 1e-3), (RK4, 1e-4)):
+    eager = cls(V, linear_diag=Ldiag, nonlinear=term).solve(u0, dt, 12)
+    graphed = cls(V, linear_diag=Ldiag, nonlinear=term).solve(u0, dt, 12, graph=True)
+    torch.cuda.synchronize()
+    assert torch.equal(eager, graphed), (cls.__name__, float((eager - graphed).abs().max()))
+    print(cls.__name__, "graphed == eager")
+print("GRAPH OK")
+"""
+
+
+@pytest.mark.xfail(strict=False, reason="BaseIntegrator.solve(graph=True) (one CUDA graph per time step) " + _UNRUN.replace(
+    "checked by the host emulator (tests/emu/fold_emu.cpp) only", "never run"))
+def test_graphed_time_stepping_equals_eager(cuda):
+    """12 ETDRK4 / RK4 steps of KdV with the step captured into a CUDA graph give bit-identical coefficients (own process:
+    a failed capture must not leave the suite's stream in capture mode)."""
+    r = subprocess.run([sys.executable, "-c", _GRAPH_SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600,
+                       cwd=ROOT)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "GRAPH OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
