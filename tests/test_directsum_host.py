@@ -65,3 +65,22 @@ def test_oracle_directsum_roundtrip_and_boundary_values():
     ends = D.evaluate(np.array([0.0, 3.0]), c)
     assert np.abs(ends - np.array([1.0, -2.0])).max() < 1e-12
     assert np.abs(D.from_orthogonal(D.to_orthogonal(c)) - c).max() < 1e-12
+
+
+# ---- homogeneous stencils: numeric derivation vs the reference's symbolic get_stencil_matrix ---------------------------
+STENCILS = json.load(open(os.path.join(HERE, "golden", "reference_stencils.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", STENCILS, ids=[f"{c['space']}-{c['bcs']}" for c in STENCILS])
+def test_numeric_stencil_matches_reference_get_stencil_matrix(case):
+    """`stencil_from_bcs` (per-row solve of the boundary functionals) reproduces the values of the reference's symbolic
+    stencil {shift: expr(n)} (composite.py:765-838; golden made by tests/golden/make_golden_stencil.py) to the last digits."""
+    import jaxfun_b200 as jf
+    from jaxfun_b200.galerkin.composite import stencil_from_bcs
+    rows = case["rows"]
+    ref = {int(k): np.array(v) for k, v in case["stencil"].items()}
+    mine = stencil_from_bcs(case["bcs"], getattr(jf, case["space"])(case["N"]))
+    for k in set(ref) | set(mine):
+        a = ref.get(k, np.zeros(rows))
+        b = np.asarray(mine.get(k, np.zeros(rows))) * np.ones(rows)
+        assert np.abs(a - b).max() < 1e-13, (k, a, b)
