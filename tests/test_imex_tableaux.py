@@ -44,3 +44,21 @@ def test_tableau_structure():
             assert abs(sum(bt.b) - 1.0) < 1e-14
             for i in range(bt.stages):
                 assert abs(sum(bt.A[i]) - bt.c[i]) < 1e-14
+
+
+@pytest.mark.parametrize("name", ["IMEX_EULER", "ARS222", "ARS443"])
+def test_tableau_equals_the_reference_constants(name):
+    """The restated tableaux against the reference's own `integrators/tableau.py` (dumped by
+    tests/golden/make_golden_tableaux.py), including the derived properties the IMEX step branches on."""
+    import json
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_tableaux.json")))["tableaux"][name]
+    tab = getattr(T, name)
+    assert tab.stages == G["stages"]
+    for part in ("explicit", "implicit"):
+        mine = getattr(tab, part)
+        assert np.abs(np.array(mine.A, dtype=float) - np.array(G[part]["A"])).max() < 1e-15
+        assert np.abs(np.array(mine.b, dtype=float) - np.array(G[part]["b"])).max() < 1e-15
+        assert np.abs(np.array(mine.c, dtype=float) - np.array(G[part]["c"])).max() < 1e-15
+    assert tab.is_stiffly_accurate == G["is_stiffly_accurate"]
+    assert tab.implicit_is_stiffly_accurate == G["implicit_is_stiffly_accurate"]
+    assert np.allclose(np.array(tab.distinct_diagonal_coeffs, dtype=float), np.array(G["distinct_diagonal_coeffs"]), rtol=0, atol=1e-15)
