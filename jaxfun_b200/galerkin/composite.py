@@ -165,6 +165,24 @@ class Composite(OrthogonalSpace):
 
 
 _BC_ORDER = {"D": 0, "N": 1, "N2": 2, "N3": 3, "N4": 4}
+_ROBIN = {"R": 0, "W": 1}        # Robin kinds: value = (alfa, val); functional = d^k0 u + alfa d^(k0+1) u (composite.py:812-826)
+
+
+def _bc_functional(orthogonal, side: str, kind: str, value) -> np.ndarray:
+    """Boundary functional of every basis function P_m: d^k P_m / dX^k at X = -1 / +1 (reference coordinate, as
+    `bnd_values`, Jacobi.py:257-288), or the Robin combination."""
+    X = np.array([-1.0 if side == "left" else 1.0])
+    if kind in _ROBIN:
+        k0, alfa = _ROBIN[kind], float(value[0])
+        return orthogonal.evaluate_basis_derivative(X, k0)[0] + alfa * orthogonal.evaluate_basis_derivative(X, k0 + 1)[0]
+    if kind not in _BC_ORDER:
+        raise NotImplementedError(f"boundary condition kind {kind!r}")
+    return orthogonal.evaluate_basis_derivative(X, _BC_ORDER[kind])[0]
+
+
+def _bc_value(v):
+    """The prescribed value: Robin conditions carry (alfa, val) (BoundaryConditions.orderedvals, composite.py:81-88)."""
+    return v[1] if isinstance(v, (tuple, list)) else v
 
 
 def ordered_bc_names(bcs: dict) -> list[tuple[str, str]]:
@@ -172,7 +190,7 @@ def ordered_bc_names(bcs: dict) -> list[tuple[str, str]]:
     (`BoundaryConditions.orderednames`, composite.py:40-118)."""
     out = []
     for side in ("left", "right"):
-        for kind in sorted(bcs.get(side, {}), key=lambda v: _BC_ORDER[v]):
+        for kind in sorted(bcs.get(side, {})):           # alphabetical, as the reference: D < N < N2 < .. < R < W
             out.append((side, kind))
     return out
 
@@ -181,19 +199,16 @@ def stencil_from_bcs(bcs: dict, orthogonal) -> dict:
     """Numeric counterpart of `get_stencil_matrix` (composite.py:765-838): phi_n = P_n + sum_{j=1..nb} d_j(n) P_{n+j}
     with d(n) solving  sum_j d_j f_b(n + j) = -f_b(n)  for every homogeneous boundary functional
     f_b(m) = d^k P_m / dX^k at X = -1 or +1.  The reference solves this system symbolically in n; here it is
-    solved per basis index from the boundary values of the (derivative) Vandermonde.  Robin conditions are
-    not covered."""
+    solved per basis index from the boundary values of the (derivative) Vandermonde.  Robin conditions
+    are the combinations d^k0 u + alfa d^(k0+1) u of composite.py:812-826."""
     names = ordered_bc_names(bcs)
     nb = len(names)
     N = orthogonal.N
     F = np.empty((nb, N))
     for b, (side, kind) in enumerate(names):
-        if kind not in _BC_ORDER:
-            raise NotImplementedError(f"boundary condition kind {kind!r} (Robin) has no numeric stencil here")
-        if bcs[side][kind] != 0:
+        if not _is_zero(_bc_value(bcs[side][kind])):
             raise NotImplementedError("inhomogeneous boundary values need the DirectSum lifting (composite.py:502-634)")
-        X = np.array([-1.0 if side == "left" else 1.0])
-        F[b] = orthogonal.evaluate_basis_derivative(X, _BC_ORDER[kind])[0]
+        F[b] = _bc_functional(orthogonal, side, kind, bcs[side][kind])
     rows = N - nb
     d = np.zeros((nb, rows))
     for i in range(rows):
@@ -229,13 +244,11 @@ def bc_basis(bcs: dict, orthogonal_cls, **kw) -> np.ndarray:
     invertible.  The boundary functionals are derivatives in the REFERENCE coordinate, as `bnd_values` (Jacobi.py:257-288)."""
     names = ordered_bc_names(bcs)
     nb = len(names)
-    nd = sum(_BC_ORDER[kind] for _, kind in names)
-    orth = orthogonal_cls(nb + nd, **kw)
-    F = np.empty((nb, nb + nd))
+    nd = sum(_BC_ORDER.get(kind, 0) for _, kind in names)          # num_derivatives (composite.py:94-101): Robin counts 0
+    orth = orthogonal_cls(nb + nd + (2 if any(k in _ROBIN for _, k in names) else 0), **kw)
+    F = np.empty((nb, orth.N))
     for b, (side, kind) in enumerate(names):
-        if kind not in _BC_ORDER:
-            raise NotImplementedError(f"boundary condition kind {kind!r} (Robin) has no numeric lifting basis here")
-        F[b] = orth.evaluate_basis_derivative(np.array([-1.0 if side == "left" else 1.0]), _BC_ORDER[kind])[0]
+        F[b] = _bc_functional(orth, side, kind, bcs[side][kind])
     for first in range(nd + 1):
         A = F[:, first:first + nb]
         if np.linalg.matrix_rank(A) == nb:
@@ -268,7 +281,7 @@ class DirectSum:
         if type(a.orthogonal).__name__ == "Jacobi":
             kw = dict(alpha=a.orthogonal.alpha, beta=a.orthogonal.beta)
         self.S_bc = bc_basis(bcs, type(a.orthogonal), **kw)
-        self.raw_vals = [bcs[side][kind] for side, kind in ordered_bc_names(bcs)]
+        self.raw_vals = [_bc_value(bcs[side][kind]) for side, kind in ordered_bc_names(bcs)]
         try:
             vals = np.array([float(v) for v in self.raw_vals])
         except (TypeError, ValueError):
@@ -383,10 +396,12 @@ def FunctionSpace(N: int, space, bcs=None, domain=None, name: str = "fun", fun_s
     Legendre space -> phi_k = P_k - P_{k+2} (both families have P_k(+-1) = (+-1)^k)."""
     if bcs is None:
         return space(N, domain=domain, name=name, fun_str=fun_str, **kw)
-    bcs = {side: {kind: (0 if _is_zero(v) else v) for kind, v in kinds.items()} for side, kinds in bcs.items()}
-    if any(not _is_zero(v) for side in bcs.values() for v in side.values()):
+    bcs = {side: {kind: (0 if (not isinstance(v, (tuple, list)) and _is_zero(v)) else v) for kind, v in kinds.items()}
+           for side, kinds in bcs.items()}
+    if any(not _is_zero(_bc_value(v)) for side in bcs.values() for v in side.values()):
         # functionspace.py:150-173: homogeneous Composite (+) boundary lift
-        hom = {side: {kind: 0 for kind in kinds} for side, kinds in bcs.items()}
+        hom = {side: {kind: ((v[0], 0) if isinstance(v, (tuple, list)) else 0) for kind, v in kinds.items()}
+               for side, kinds in bcs.items()}
         return DirectSum(FunctionSpace(N, space, hom, domain=domain, name=name, fun_str=fun_str, scaling=scaling, **kw), bcs)
     left, right = bcs.get("left", {}), bcs.get("right", {})
     if set(left) == {"D"} and set(right) == {"D"} and left["D"] == 0 and right["D"] == 0 and \

@@ -979,11 +979,11 @@ class Composite(OrthogonalSpace):
 # Inhomogeneous boundary values: BCGeneric lifting basis and DirectSum  (galerkin/composite.py:40-118, 411-488,
 # 502-638, 835-896) — SURVEY §8(f) rank 1
 # =================================================================================================
-_BC_DERIV = {"D": 0, "N": 1, "N2": 2, "N3": 3, "N4": 4}
+_BC_DERIV = {"D": 0, "R": 0, "N": 1, "N2": 2, "N3": 3, "N4": 4}
 
 
 class BoundaryConditions(dict):
-    """composite.py:40-118 (Dirichlet / Neumann / higher-derivative conditions; Robin is not restated)."""
+    """composite.py:40-118.  Robin conditions ("R": u + alfa u', "W": u' + alfa u'') carry the tuple (alfa, value)."""
 
     def __init__(self, bc):
         super().__init__({"left": dict(bc.get("left", {})), "right": dict(bc.get("right", {}))})
@@ -992,7 +992,8 @@ class BoundaryConditions(dict):
         return ["L" + k for k in sorted(self["left"])] + ["R" + k for k in sorted(self["right"])]
 
     def orderedvals(self):                                      # composite.py:81-88
-        return [self[lr][k] for lr in ("left", "right") for k in sorted(self[lr])]
+        vals = [self[lr][k] for lr in ("left", "right") for k in sorted(self[lr])]
+        return [v[1] if isinstance(v, (tuple, list)) else v for v in vals]
 
     def num_bcs(self):                                          # composite.py:90-92
         return len(self.orderedvals())
@@ -1014,7 +1015,14 @@ def get_bc_basis(bcs, orthogonal):
         rows = []
         for key in bcs.orderednames():
             side, kind = key[0], key[1:]
-            f = orthogonal.bnd_values(k=_BC_DERIV[kind])[0 if side == "L" else 1]
+            lr = 0 if side == "L" else 1
+            if kind in "WR":                                     # composite.py:860-872
+                k0 = 0 if kind == "R" else 1
+                alfa = bcs["left" if side == "L" else "right"][kind][0]
+                f0, f1 = orthogonal.bnd_values(k=k0)[lr], orthogonal.bnd_values(k=k0 + 1)[lr]
+                rows.append([sp.simplify(f0(j) + alfa * f1(j)) for j in range(first, first + nb)])
+                continue
+            f = orthogonal.bnd_values(k=_BC_DERIV[kind])[lr]
             rows.append([sp.simplify(f(j)) for j in range(first, first + nb)])
         A = sp.Matrix(rows)
         return sp.simplify(A.solve(sp.eye(nb)).T)

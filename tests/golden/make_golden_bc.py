@@ -34,6 +34,8 @@ BCS = [
     {"left": {"D": 2.0}},
     {"right": {"D": -1.0, "N": 0.25}},
     {"left": {"D": 1.0, "N": 0.0, "N2": -1.0}, "right": {"D": 2.0, "N": 0.0, "N2": 0.5}},
+    {"left": {"R": (0.3, 1.0)}, "right": {"D": -1.0}},              # Robin: u + 0.3 u' = 1 on the left
+    {"left": {"R": (2.0, 0.5)}, "right": {"R": (-1.0, 0.25)}},
 ]
 
 cases = []
