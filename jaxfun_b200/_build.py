@@ -46,13 +46,21 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".cu")] + [
+        os.path.join(HERE, "..", "include", "jfx.h")]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    extra = os.environ.get("JFX_NVCC_EXTRA", "")
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        # incremental: an object newer than its source and every header is kept (force / verbose / extra flags rebuild all)
+        if (not force and not verbose and not extra and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(os.path.getmtime(os.path.join(CSRC, src)), newest_header)):
+            continue
         cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("JFX_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     failed = False
     for src, p in procs:
         out, _ = p.communicate()

@@ -22,6 +22,17 @@
 //   OUT_NT: R0 = X[128 rows][k0..k0+15],        R1 = X[128 rows][k0+16..k0+31],  R2 = folded table [128 c'][16 k']
 //           (parity split in the fragment load: one LDS.128 fetches (even k, odd k) for the plus and the minus MMA)
 //   IN_NT : R0 = X[128 rows][j0..j0+15],        R1 = mirror columns,    R2 = folded table
+//
+// Asymmetry correction (OUT fold).  The reference's Gauss-Legendre nodes are mirror images only to an ulp
+// (utils/fastgl.py:548-556 takes cos(theta) and cos(pi - theta)), so its Vandermonde is T = A + E with A the
+// symmetric part that is folded and E[j,k] = (T[j,k] - sigma_k T[n-1-j,k]) / 2 ~ P_k'(x_j) * 1e-16, which for the
+// highest modes reaches 3e-12 of the mode's own magnitude at n = 1024 — above the 1e-12 parity bar for an input that
+// excites only such a mode.  With p = sum_{k plus} E c, q = sum_{k minus} E c the exact result is
+//        u_j = (P + q) + (Q + p),   u_{n-1-j} = (P + q) - (Q + p)
+// i.e. the SAME butterfly on accumulators that additionally received E against the coefficients of the OPPOSITE parity.
+// The modes whose asymmetry exceeds tol_fix (a tail k' >= kcorr0 of the folded index) therefore get extra k-tiles: the
+// table tile comes from correction columns appended to the folded table, the data tiles are fetched with the parity
+// swapped (NN: by the TMA coordinates; NT: by the fragment select).  MMA warps and epilogue do not change.
 #pragma once
 #include <cstdint>
 #include <cmath>
@@ -79,16 +90,67 @@ struct Args {
   double* C;
   long long ldc, strideC;
   int vec_ok;          // 16-byte aligned vector stores allowed
+  // k-tiles: kts_main tiles of the folded problem, then kts_corr asymmetry-correction tiles covering k' >= kcorr0
+  int kts_main, kts_corr, kcorr0;
 };
 
+// parity argument of ktile() for k-tile kt: correction tiles pair every accumulator group with the opposite parity
+JFX_HD int ktile_par(const Args& q, int kt) { return kt >= q.kts_main ? 1 - q.par_plus : q.par_plus; }
+
 // ------------------------------------------------------------------------------------------------
-// one k-tile of the MMA warps (lane (g, t) of warp (wm, wn)); S = base of the stage (3 tiles)
+// Fragment addressing.  The swizzled offsets kc_off / nc_off of every fragment a lane loads in a k-tile differ from a
+// handful of per-lane constants only by COMPILE-TIME terms (m-tile / n-tile index, k-step), because the XOR of the
+// swizzle acts on bit fields that the k-step and the lane index occupy separately.  frag_init() computes those
+// constants once per kernel (offsets in doubles from the stage base); ktile() then addresses every fragment as
+// constant + immediate, so the k loop carries no address arithmetic and few live registers (the compiler cannot see the
+// bit-disjointness by itself: it kept ~60 precomputed addresses live and recomputed the rest with LOP3 / LEA per load).
+//   lane (g, t), th = t >> 1, tl = t & 1, k-step kk = 0..3 (k = 4 kk + t inside the 16-wide k-tile)
+//   K-contiguous tile, row r = R + 8 m + g:   kc_off(r, 4 kk + t) = 16 (R + g) + 128 m + 4 (kk ^ (g >> 1)) + 2 (th ^ (g & 1)) + tl
+//   N-contiguous tile, col n = 32 wn + 8 j + g: nc_off(4 kk + t, n) = 512 wn + 128 j + 32 kk + 8 t + 2 ((g >> 1) ^ (2 (kk & 1) + th)) + (g & 1)
+//   mirrored reads use k' = 15 - k = 4 (3 - kk) + (3 - t)
+// ------------------------------------------------------------------------------------------------
+struct Frag {
+  int p[4];   // NN: table fragment (A) per kk                 NT: table fragment (B) per kk
+  int q[4];   // NN: X fragment per (kk & 1) [+2: mirrored]    OUT_NT: X double2 per (kk & 1);  IN_NT: X per kk
+  int r[4];   //                                               IN_NT: mirrored X per kk
+};
+
+template <int V>
+JFX_HD Frag frag_init(int wm, int wn, int g, int t) {
+  Frag f{};
+  const int th = t >> 1, tl = t & 1, g0 = g & 1, g2 = g >> 1;
+  if constexpr (V == OUT_NN || V == IN_NN) {
+    const int a_lane = (wm * WM + g) * 16 + ((th ^ g0) << 1) + tl;
+    for (int kk = 0; kk < 4; ++kk) f.p[kk] = a_lane + ((kk ^ g2) << 2);
+    for (int par = 0; par < 2; ++par) {
+      f.q[par] = wn * 512 + t * 8 + (((g2 ^ ((par << 1) | th)) << 1) | g0);
+      f.q[2 + par] = wn * 512 + (3 - t) * 8 + (((g2 ^ (((1 - par) << 1) | (1 - th))) << 1) | g0);   // IN_NN mirror tile
+    }
+  } else {
+    const int b_lane = (wn * WN + g) * 16 + ((th ^ g0) << 1) + tl;
+    for (int kk = 0; kk < 4; ++kk) f.p[kk] = b_lane + ((kk ^ g2) << 2);
+    if constexpr (V == OUT_NT || V == CPLX_NT) {
+      const int rr = rho(g);
+      for (int par = 0; par < 2; ++par) f.q[par] = (wm * WM + rr) * 16 + ((((par ^ g0) << 2) | (t ^ g2)) << 1);
+    } else {
+      const int u_lane = (wm * WM + g) * 16;
+      for (int kk = 0; kk < 4; ++kk) {
+        f.q[kk] = u_lane + ((kk ^ g2) << 2) + ((th ^ g0) << 1) + tl;
+        f.r[kk] = u_lane + (((3 - kk) ^ g2) << 2) + (((1 - th) ^ g0) << 1) + (1 - tl);
+      }
+    }
+  }
+  return f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one k-tile of the MMA warps (lane (g, t) of warp (wm, wn)); S = base of the stage (3 tiles), fr = frag_init()
 // mma(d0, d1, a, b) is the m8n8k4 step (device: mma.sync; emulator: a recorder)
 // ------------------------------------------------------------------------------------------------
 template <int V, class MMA>
-JFX_HD void ktile(const double* S, int wm, int wn, int g, int t, int par_plus, double (&acc)[8][4][2], MMA&& mma) {
+JFX_HD void ktile(const double* S, const Frag& fr, int par_plus, double (&acc)[8][4][2], MMA&& mma) {
   if constexpr (V == CPLX_NT) {
-    ktile<OUT_NT>(S, wm, wn, g, t, 0, acc, mma);
+    ktile<OUT_NT>(S, fr, 0, acc, mma);
     return;
   }
   const double* R0 = S;
@@ -96,21 +158,19 @@ JFX_HD void ktile(const double* S, int wm, int wn, int g, int t, int par_plus, d
   const double* R2 = S + 2 * TILE;
 #pragma unroll
   for (int kk = 0; kk < BK / 4; ++kk) {
-    const int kx = kk * 4 + t;
     if constexpr (V == OUT_NN || V == IN_NN) {
       // plus half (m-tiles 0..3) then minus half (m-tiles 4..7): 8 fragment registers live at a time
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = R0[kc_off(wm * WM + (h * 4 + i) * 8 + g, kx)];
+        for (int i = 0; i < 4; ++i) a[i] = R0[fr.p[kk] + (h * 4 + i) * 128];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int n = wn * WN + j * 8 + g;
           if constexpr (V == OUT_NN) {
-            b[j] = (h ? R2 : R1)[nc_off(kx, n)];
+            b[j] = (h ? R2 : R1)[fr.q[kk & 1] + j * 128 + kk * 32];
           } else {
-            const double u = R1[nc_off(kx, n)], v = R2[nc_off(15 - kx, n)];
+            const double u = R1[fr.q[kk & 1] + j * 128 + kk * 32], v = R2[fr.q[2 + (kk & 1)] + j * 128 + (3 - kk) * 32];
             b[j] = h ? u - v : u + v;
           }
         }
@@ -122,7 +182,7 @@ JFX_HD void ktile(const double* S, int wm, int wn, int g, int t, int par_plus, d
     } else {
       double b[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = R2[kc_off(wn * WN + j * 8 + g, kx)];
+      for (int j = 0; j < 4; ++j) b[j] = R2[fr.p[kk] + j * 128];
       // four m-tiles at a time: plus / minus operand pairs of 4 rows live together
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -131,15 +191,12 @@ JFX_HD void ktile(const double* S, int wm, int wn, int g, int t, int par_plus, d
         for (int ii = 0; ii < 4; ++ii) {
           const int i = h * 4 + ii;
           if constexpr (V == OUT_NT) {
-            const int r = wm * WM + i * 8 + rho(g);
-            const int chunk = 4 * (kk & 1) + t;
             const double* sub = (kk >> 1) ? R1 : R0;
-            const Double2 v = *reinterpret_cast<const Double2*>(sub + r * 16 + ((chunk ^ (r & 7)) << 1));
+            const Double2 v = *reinterpret_cast<const Double2*>(sub + fr.q[kk & 1] + i * 128);
             ap[ii] = par_plus ? v.y : v.x;
             aq[ii] = par_plus ? v.x : v.y;
           } else {
-            const int r = wm * WM + i * 8 + g;
-            const double u = R0[kc_off(r, kx)], v = R1[kc_off(r, 15 - kx)];
+            const double u = R0[fr.q[kk] + i * 128], v = R1[fr.r[kk] + i * 128];
             ap[ii] = u + v;
             aq[ii] = u - v;
           }
@@ -329,12 +386,17 @@ JFX_HD void epilogue_scatter(const Args& q, const Scatter& sc, int tile_m, int t
 template <int V, class ISSUE>
 JFX_HD void stage_copies(const Args& q, int kt, int tile_m, int tile_n, int z, ISSUE&& issue) {
   const int m0 = tile_m * BM, n0 = tile_n * BN, k0 = kt * BK;
+  // correction tiles (kt >= kts_main): table columns simply continue after the padded main part; the data are the
+  // coefficients k' = kcorr0 + ... again, with the parity roles swapped
+  const bool corr = kt >= q.kts_main;
+  const int kx = corr ? q.kcorr0 + (kt - q.kts_main) * BK : k0;
   if constexpr (V == OUT_NN) {
+    const int pp = corr ? 1 - q.par_plus : q.par_plus;
     issue(0, 0, 2, k0, m0, 0, 0);
 #pragma unroll
     for (int sub = 0; sub < BN / 8; ++sub) {
-      issue(1, TILE + sub * 128, 4, n0 + 8 * sub, q.par_plus, k0, z);
-      issue(1, 2 * TILE + sub * 128, 4, n0 + 8 * sub, 1 - q.par_plus, k0, z);
+      issue(1, TILE + sub * 128, 4, n0 + 8 * sub, pp, kx, z);
+      issue(1, 2 * TILE + sub * 128, 4, n0 + 8 * sub, 1 - pp, kx, z);
     }
   } else if constexpr (V == IN_NN) {
     issue(0, 0, 2, k0, m0, 0, 0);
@@ -344,8 +406,8 @@ JFX_HD void stage_copies(const Args& q, int kt, int tile_m, int tile_n, int z, I
       issue(1, 2 * TILE + sub * 128, 3, n0 + 8 * sub, q.n_fold - 16 - k0, z, 0);
     }
   } else if constexpr (V == OUT_NT || V == CPLX_NT) {
-    issue(0, 0, 2, 2 * k0, m0, 0, 0);
-    issue(0, TILE, 2, 2 * k0 + 16, m0, 0, 0);
+    issue(0, 0, 2, 2 * kx, m0, 0, 0);
+    issue(0, TILE, 2, 2 * kx + 16, m0, 0, 0);
     issue(1, 2 * TILE, 2, k0, n0, 0, 0);
   } else {
     issue(0, 0, 2, k0, m0, 0, 0);
@@ -369,15 +431,26 @@ struct MapDesc {
 struct FoldInfo {
   int type;       // FoldType
   int par_plus;
+  int kcorr0;     // OUT fold: folded mode index k' from which the asymmetry correction applies (-1: none needed)
 };
+
+// Relative asymmetry a mode may keep WITHOUT correction: the folded result of an input that excites only this mode
+// differs from the reference's by at most this fraction of the mode's own magnitude (the parity bar is 1e-12).
+constexpr double TOL_FIX = 3e-13;
 
 // T: [rows][cols] row-major.  Detects the OUT fold (rows mirrored, both extents even) or the IN fold (columns mirrored,
 // column count even), with sigma_k strictly alternating.  tol is relative to max |T|.  The reference's nodes are mirror
 // images only up to an ulp (fastgl.py:512-544 takes cos(theta) and cos(pi - theta)), which shows in its Vandermonde as an
 // asymmetry of 1e-14 (n = 64) to 4e-13 (n = 1024) of max |T|; a table without the symmetry is off by O(1).  build() folds
-// the mean of the two mirror images, so the folded result differs from the plain contraction by at most half of that.
-inline FoldInfo analyze(const double* T, int rows, int cols, double tol = 1e-12, double tol_local = 1e-10) {
-  FoldInfo none{FOLD_NONE, 0};
+// the mean of the two mirror images A; what is lost is E = (T - sigma * mirror T) / 2.  Per mode (column of an OUT table, row
+// of an IN table) max |E| / max |T| is the error of a single-mode input relative to its own result:
+//   <= tol_fix                    : folded as is;
+//   OUT, larger, in the tail      : folded, and the modes k' >= kcorr0 get correction k-tiles (exact again, see the header);
+//   OUT, more than 1/4 of the modes, or IN : not folded (plain kernel).
+// Measured on the host tables: only the Legendre backward Vandermonde needs it (n = 320: 2 modes, 512: 15, 1024: 101 of 1024).
+inline FoldInfo analyze(const double* T, int rows, int cols, double tol = 1e-12, double tol_local = 1e-10,
+                        double tol_fix = TOL_FIX) {
+  FoldInfo none{FOLD_NONE, 0, -1};
   if (rows < 2 || cols < 2) return none;
   double tmax = 0;
   for (long long i = 0; i < (long long)rows * cols; ++i) {
@@ -387,14 +460,13 @@ inline FoldInfo analyze(const double* T, int rows, int cols, double tol = 1e-12,
   }
   if (tmax == 0) return none;
   const double eps = tol * tmax;
-  // Two conditions: the asymmetry is below tol of max |T| everywhere, and below tol_local of the scale of the coefficient it
-  // belongs to (the column of mode k for OUT, the row of mode k for IN).  The second one matters for tables whose modes differ
-  // by orders of magnitude (derivative tables grow like k^4): a small mode must be symmetric relative to ITSELF, because the
-  // caller's coefficients may weight it arbitrarily.  Measured on the host tables: <= 7e-12 (Legendre backward, n = 1024).
+  // Outer bounds first: the asymmetry is below tol of max |T| everywhere, and below tol_local of the scale of the coefficient
+  // it belongs to (a table that merely looks symmetric at the scale of its largest mode is refused).
   // OUT: T[rows-1-j][k] = sigma_k T[j][k]
   if (rows % 2 == 0 && cols % 2 == 0) {
     for (int pp = 0; pp < 2; ++pp) {
       bool ok = true;
+      int first_bad = cols;
       for (int k = 0; k < cols && ok; ++k) {
         const double s = ((k & 1) == pp) ? 1.0 : -1.0;
         double cmax = 0, dmax = 0;
@@ -402,8 +474,13 @@ inline FoldInfo analyze(const double* T, int rows, int cols, double tol = 1e-12,
         for (int j = 0; j < rows / 2; ++j)
           dmax = std::fmax(dmax, std::fabs(T[(long long)(rows - 1 - j) * cols + k] - s * T[(long long)j * cols + k]));
         if (dmax > eps || dmax > tol_local * cmax) ok = false;
+        if (0.5 * dmax > tol_fix * cmax && k < first_bad) first_bad = k;
       }
-      if (ok) return FoldInfo{FOLD_OUT, pp};
+      if (!ok) continue;
+      const int kfold = cols / 2;
+      int kc = first_bad < cols ? first_bad / 2 : -1;
+      if (kc >= 0 && (kfold - kc) * 4 > kfold) continue;   // too many modes to correct: the plain kernel is the better choice
+      return FoldInfo{FOLD_OUT, pp, kc};
     }
   }
   // IN: T[k][cols-1-j] = sigma_k T[k][j]
@@ -416,9 +493,9 @@ inline FoldInfo analyze(const double* T, int rows, int cols, double tol = 1e-12,
         for (int j = 0; j < cols; ++j) rmax = std::fmax(rmax, std::fabs(T[(long long)k * cols + j]));
         for (int j = 0; j < cols / 2; ++j)
           dmax = std::fmax(dmax, std::fabs(T[(long long)k * cols + (cols - 1 - j)] - s * T[(long long)k * cols + j]));
-        if (dmax > eps || dmax > tol_local * rmax) ok = false;
+        if (dmax > eps || 0.5 * dmax > tol_fix * rmax) ok = false;
       }
-      if (ok) return FoldInfo{FOLD_IN, pp};
+      if (ok) return FoldInfo{FOLD_IN, pp, -1};
     }
   }
   return none;
@@ -428,6 +505,7 @@ struct FoldedTable {
   int type = FOLD_NONE, par_plus = 0;
   int n_fold = 0, n_other = 0, half = 0, kfold = 0;
   int rows_nn = 0, rows_nt = 0, ld = 0;       // padded row counts of the two layouts, leading dimension (even)
+  int kts_main = 0, kts_corr = 0, kcorr0 = 0;  // k-tiles of the folded problem / of the asymmetry correction (columns kts_main * BK ...)
   std::vector<double> nn, nt;                  // folded tables for the NN and NT warp layouts, [rows][ld]
 };
 
@@ -460,7 +538,13 @@ inline FoldedTable build(const double* T, int rows, int cols, const FoldInfo& fi
   const int pairs = out ? f.half : (f.n_other + 1) / 2;     // mirror pairs (OUT) / mode pairs (IN) along the table rows
   const int tiles = (pairs + HALF_PER_TILE - 1) / HALF_PER_TILE;
   f.rows_nn = f.rows_nt = tiles * 128;
-  f.ld = (f.kfold + 1) & ~1;
+  f.kts_main = (f.kfold + BK - 1) / BK;
+  const bool corr = out && fi.kcorr0 >= 0 && fi.kcorr0 < f.kfold;
+  f.kcorr0 = corr ? fi.kcorr0 : f.kfold;
+  f.kts_corr = corr ? (f.kfold - f.kcorr0 + BK - 1) / BK : 0;
+  // without correction columns the row is just the folded modes (the TMA unit zero-fills the k tail); with them the main part
+  // is padded to whole k-tiles so that the correction columns start at kts_main * BK
+  f.ld = corr ? (f.kts_main + f.kts_corr) * BK : ((f.kfold + 1) & ~1);
   if (f.ld < 2) f.ld = 2;
   f.nn.assign((size_t)f.rows_nn * f.ld, 0.0);
   f.nt.assign((size_t)f.rows_nt * f.ld, 0.0);
@@ -477,6 +561,13 @@ inline FoldedTable build(const double* T, int rows, int cols, const FoldInfo& fi
         for (int kp = 0; kp < f.kfold; ++kp) {
           const int k = 2 * kp + par;
           dst[(size_t)r * f.ld + kp] = 0.5 * (T[(long long)idx * cols + k] + sg * T[(long long)(rows - 1 - idx) * cols + k]);
+        }
+        // correction columns: the plus group accumulates E against the MINUS-parity coefficients and vice versa,
+        // E[j, k] = (T[j, k] - sigma_k T[n-1-j, k]) / 2
+        for (int c = 0; c < (corr ? f.kfold - f.kcorr0 : 0); ++c) {
+          const int k = 2 * (f.kcorr0 + c) + (1 - par);
+          dst[(size_t)r * f.ld + (size_t)f.kts_main * BK + c] =
+              0.5 * (T[(long long)idx * cols + k] + sg * T[(long long)(rows - 1 - idx) * cols + k]);
         }
       } else {
         const int k = 2 * idx + par;
@@ -501,6 +592,10 @@ inline bool make_launch(const FoldedTable& f, bool nn, long long outer, long lon
   a.variant = nn ? (out ? OUT_NN : IN_NN) : (out ? OUT_NT : IN_NT);
   a.par_plus = f.par_plus;
   a.n_fold = f.n_fold; a.n_other = f.n_other; a.half = f.half; a.kfold = f.kfold;
+  a.kts_main = f.kts_main; a.kts_corr = f.kts_corr; a.kcorr0 = f.kcorr0;
+  // table columns the tensor map exposes: the folded modes (k tail zero-filled by the TMA unit), or — with correction
+  // columns — the whole padded row
+  const unsigned long long tcols = f.kts_corr ? (unsigned long long)f.ld : (unsigned long long)f.kfold;
   a.C = C;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al16(table) || !al16(X)) return false;
@@ -512,7 +607,7 @@ inline bool make_launch(const FoldedTable& f, bool nn, long long outer, long lon
     a.tiles_m = f.rows_nn / BM; a.tiles_n = (int)((inner + BN - 1) / BN); a.batch = (int)outer;
     a.ldc = inner; a.strideC = (long long)n_out * inner;
     a.vec_ok = al16(C) ? 1 : 0;                     // inner even -> every row / batch offset is even
-    *mA = MapDesc{table, 2, {(unsigned long long)f.kfold, (unsigned long long)f.rows_nn, 1, 1},
+    *mA = MapDesc{table, 2, {tcols, (unsigned long long)f.rows_nn, 1, 1},
                   {(unsigned long long)f.ld * 8, 0, 0}, {BK, BM, 1, 1}, 128};
     if (out) {
       // X_o[k][n] with k = 2 kk + parity: dims (n, parity, kk, batch)
@@ -530,14 +625,14 @@ inline bool make_launch(const FoldedTable& f, bool nn, long long outer, long lon
     a.vec_ok = (al16(C) && n_out % 2 == 0) ? 1 : 0;
     *mA = MapDesc{X, 2, {(unsigned long long)n_in, (unsigned long long)outer, 1, 1},
                   {(unsigned long long)n_in * 8, 0, 0}, {BK, BM, 1, 1}, 128};
-    *mB = MapDesc{table, 2, {(unsigned long long)f.kfold, (unsigned long long)f.rows_nt, 1, 1},
+    *mB = MapDesc{table, 2, {tcols, (unsigned long long)f.rows_nt, 1, 1},
                   {(unsigned long long)f.ld * 8, 0, 0}, {BK, BN, 1, 1}, 128};
   }
   *q = a;
   return true;
 }
 
-inline int ktiles(const Args& q) { return (q.kfold + BK - 1) / BK; }
+JFX_HD int ktiles(const Args& q) { return q.kts_main + q.kts_corr; }
 
 // ---- CPLX_NT: complex interleaved rows [outer][n_in] (as 2 n_in doubles) times a real table [n_out][n_in] ------------
 struct CplxTable {
@@ -572,6 +667,7 @@ inline bool make_launch_cplx(const CplxTable& c, long long outer, const double* 
   a.n_fold = 0; a.half = 0;
   a.n_other = 2 * c.n_out;            // output columns (doubles) per row
   a.kfold = c.n_in;                   // complex coefficients per row = reduction length per accumulator group
+  a.kts_main = (c.n_in + BK - 1) / BK; a.kts_corr = 0; a.kcorr0 = c.n_in;
   a.C = C;
   a.M = (int)outer; a.N = c.rows_nt;
   a.tiles_m = (int)((outer + BM - 1) / BM); a.tiles_n = c.rows_nt / BN; a.batch = 1;

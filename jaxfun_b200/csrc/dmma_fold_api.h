@@ -13,6 +13,9 @@ bool fold_enabled();
 int fold_plan_create(const double* table, int rows, int cols, FoldPlan** out);
 void fold_plan_destroy(FoldPlan* fp);
 int fold_plan_type(const FoldPlan* fp);   // 0 none, 1 OUT (backward-like), 2 IN (forward-like)
+// multiply-adds issued relative to the plain contraction: 1/2, plus the asymmetry-correction k-tiles of the highest modes
+double fold_plan_flop_fraction(const FoldPlan* fp);
+int fold_plan_corrected_modes(const FoldPlan* fp);
 // The array is [outer][n_in][inner_real] doubles (complex data: inner_real = 2 * inner).
 // 1 = launched, 0 = outside the envelope (use the plain kernel), < 0 = error.
 int launch_dmma_fold(cudaStream_t s, const FoldPlan* fp, long long outer, long long inner_real, const double* in,
@@ -25,7 +28,7 @@ int launch_dmma_fold_scatter(cudaStream_t s, const FoldPlan* fp, long long outer
                              int src, int A, int B, double* const* peers);
 
 // Complex interleaved data on a LAST table axis (any real table): one NT launch with (re, im) accumulator groups
-// instead of the NN order with two real columns per batch.  Opt-in: JFX_CPLX_NT=1 at plan creation.
+// instead of the NN order with two real columns per batch.  Default; JFX_CPLX_NT=0 at plan creation keeps the NN route.
 struct CplxPlan;
 bool cplx_nt_enabled();
 int cplx_plan_create(const double* table, int n_out, int n_in, CplxPlan** out);

@@ -29,7 +29,7 @@ struct Pass {
   void* d_table = nullptr;  // owned
   bool table_complex = false;
   bool dmma = false;
-  dmma::CplxPlan* cplx = nullptr;  // owned; complex data on a last table axis as one NT launch (JFX_CPLX_NT=1)
+  dmma::CplxPlan* cplx = nullptr;  // owned; complex data on a last table axis as one NT launch (default; JFX_CPLX_NT=0 disables)
   dmma::FoldPlan* fold = nullptr;  // owned; parity-folded tables when the table has the mirror symmetry (default; JFX_DMMA_FOLD=0 disables)
   FastParams fp{};
   FastTables* ft = nullptr;  // owned
@@ -184,7 +184,7 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
       const double cm = dtype_is_complex(d->dtype) ? (p.table_complex ? 4.0 : 2.0) : 1.0;
       const double fl = 2.0 * cm * (double)p.geom.outer * p.geom.inner * (double)n_in * n_out;
       pl->flops += fl;
-      pl->flops_executed += p.fold ? 0.5 * fl : fl;
+      pl->flops_executed += p.fold ? dmma::fold_plan_flop_fraction(p.fold) * fl : fl;
     }
     cur[ax] = n_out;
     max_inter = std::max(max_inter, (size_t)prod(cur, 0, d->ndim) * es);
@@ -522,6 +522,14 @@ int jfx_plan_create(const jfx_plan_desc* desc, jfx_plan** out) {
   JFX_REQUIRE(pl, JFX_ERR_NOMEM, "out of host memory");
   int rc = build_plan(desc, pl.get());
   if (rc != JFX_OK) return rc;
+  // The constant tables were uploaded with cudaMemcpy from pageable host memory, which returns once the data are STAGED: the
+  // DMA into device memory may still be in flight, and it is ordered with the legacy default stream only.  A first execution
+  // on the caller's stream could read a partially written table (seen on the B200: 32 wrong values in the first 512^3 pass
+  // after plan creation, none afterwards).  Plan creation may synchronise; jfx_execute never does.
+  {
+    const char* e = getenv("JFX_NO_CREATE_SYNC");   // debugging switch for exactly that race (tools/stress_first_call.py)
+    if (!(e && e[0] == '1')) JFX_CUDA_OK(cudaDeviceSynchronize());
+  }
   // tables were copied: do not keep dangling host pointers
   for (int i = 0; i < JFX_MAX_DIMS; ++i) pl->desc.axis[i].table = nullptr;
   *out = pl.release();
@@ -717,6 +725,7 @@ int jfx_nonlinear_create(const jfx_nonlinear_desc* d, jfx_nonlinear** out) {
     const int rc = try_fuse_rows(d, nl.get());
     if (rc != JFX_OK) return rc;
   }
+  JFX_CUDA_OK(cudaDeviceSynchronize());   // table uploads complete before the first execution (see jfx_plan_create)
   *out = nl.release();
   return JFX_OK;
 }

@@ -19,11 +19,24 @@ namespace jfx {
 namespace dmma {
 namespace fold {
 
-// 8 MMA warps (two warpgroups) + one producer warpgroup of which only warp 8 / lane 0 works.  The third warpgroup exists
-// so that setmaxnreg can move registers: the kernel starts with 168 registers per thread (65536 / 384), the producer
-// warpgroup drops to 40 and the MMA warpgroups rise to 232 (2 * 128 * 232 + 128 * 40 = 64512 = 384 * 168).
+// 8 MMA warps + ONE producer warp (lane 0 works) = 288 threads.  The hardware allocates registers for the CTA rounded up
+// to 12 warps, so every thread gets 65536 / 384 -> 168 registers; with the per-lane fragment bases of frag_init() the MMA
+// code fits (a dozen local-memory accesses per k-tile in the IN variants, none in OUT_NT).
+// Round 1 gave the MMA warps 232 registers with setmaxnreg (producer warpgroup .dec 40, MMA warpgroups .inc 232).  That
+// version produced WRONG RESULTS on the B200 whenever the first TMA loads of a launch were slow (row stride >= 2 MiB, e.g.
+// the first axis of a 512^3 forward): in the first tile of some CTAs the warps of warpgroup 0 accumulated garbage in the
+// second half of their k-tile code.  Found by tests/test_at_size_gpu.py, reproduced by tools/diag_in_nn.py, gone without
+// the register hand-over; JFX_FOLD_SETMAXNREG=1 at compile time restores the old scheme for experiments.
+#ifndef JFX_FOLD_SETMAXNREG
+#define JFX_FOLD_SETMAXNREG 0
+#endif
+#if JFX_FOLD_SETMAXNREG
 constexpr int THREADS = MMA_WARPS * 32 + 128;
 constexpr int REGS_PRODUCER = 40, REGS_MMA = 232;
+#else
+constexpr int THREADS = MMA_WARPS * 32 + 32;
+#endif
+#define JFX_FOLD_BOUNDS __launch_bounds__(THREADS, 1)
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8;
 constexpr unsigned SPIN_LIMIT = 1u << 27;
 
@@ -98,12 +111,14 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
   }
   __syncthreads();
 
-  const int kts = (q.kfold + BK - 1) / BK;
+  const int kts = ktiles(q);
   const long long total_tiles = (long long)q.tiles_n * q.tiles_m * q.batch;
 
   if (warp >= MMA_WARPS) {
     // ================================ producer warpgroup ================================
+#if JFX_FOLD_SETMAXNREG
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+#endif
     if (warp != MMA_WARPS || lane != 0) return;
     long long it = 0;
     for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
@@ -131,9 +146,12 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
   }
 
   // ================================ MMA warps ================================
+#if JFX_FOLD_SETMAXNREG
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_MMA));
+#endif
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   const int g = lane >> 2, t = lane & 3;
+  const Frag fr = frag_init<V>(wm, wn, g, t);
   double acc[8][4][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -147,7 +165,7 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
       const unsigned ph = (unsigned)((it / STAGES) & 1);
       mbar_wait(bar_full + 8 * s, ph);
       const double* S = reinterpret_cast<const double*>(gbase + (size_t)s * STAGE_BYTES);
-      ktile<V>(S, wm, wn, g, t, q.par_plus, acc, MmaOp{});
+      ktile<V>(S, fr, ktile_par(q, kt), acc, MmaOp{});
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + 8 * s);
     }
@@ -164,7 +182,7 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
 }
 
 template <int V>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void JFX_FOLD_BOUNDS
 dgemm_dmma_fold(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args q) {
   fold_cta<V>(tmA, tmB, q, [&](int tm, int tn, long long z, int wm, int wn, int g, int t, const double (&acc)[8][4][2]) {
     epilogue<V>(q, tm, tn, z, wm, wn, g, t, acc, GlobalStore{q.C});
@@ -173,7 +191,7 @@ dgemm_dmma_fold(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 // Same contraction, result scattered into the slab-exchange receive buffers of all GPUs (NT variants; see Scatter)
 template <int V>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void JFX_FOLD_BOUNDS
 dgemm_dmma_fold_scatter(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args q,
                         const Scatter sc) {
   fold_cta<V>(tmA, tmB, q, [&](int tm, int tn, long long, int wm, int wn, int g, int t, const double (&acc)[8][4][2]) {
@@ -271,6 +289,14 @@ void fold_plan_destroy(FoldPlan* fp) {
 
 int fold_plan_type(const FoldPlan* fp) { return fp ? fp->host.type : 0; }
 
+// multiply-adds the folded pass issues relative to the plain contraction: 1/2, plus the asymmetry-correction k-tiles
+double fold_plan_flop_fraction(const FoldPlan* fp) {
+  if (!fp || fp->host.kfold <= 0) return 1.0;
+  const fold::FoldedTable& f = fp->host;
+  return 0.5 * (double)(f.kfold + (f.kts_corr ? f.kfold - f.kcorr0 : 0)) / (double)f.kfold;
+}
+int fold_plan_corrected_modes(const FoldPlan* fp) { return fp && fp->host.kts_corr ? 2 * (fp->host.kfold - fp->host.kcorr0) : 0; }
+
 // 1 = launched, 0 = outside the envelope (caller uses the plain kernel), < 0 = error
 int launch_dmma_fold(cudaStream_t s, const FoldPlan* fp, long long outer, long long inner_real, const double* in,
                      double* out) {
@@ -337,11 +363,11 @@ struct CplxPlan {
   double* d_nt = nullptr;
 };
 
-// opt-in until it has run on a GPU (JFX_CPLX_NT=1, read at plan creation); without it such passes run the NN order
-// with two real columns per batch, which is correct but wastes 63 / 64 of every tile
+// default (validated on the B200 against the NN route through the C ABI, tools/fold_check --extra: 25-35x faster);
+// JFX_CPLX_NT=0 (read at plan creation) keeps the NN order with two real columns per batch, which wastes 63 / 64 of every tile
 bool cplx_nt_enabled() {
   const char* e = getenv("JFX_CPLX_NT");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }
 
 int cplx_plan_create(const double* table, int n_out, int n_in, CplxPlan** out) {

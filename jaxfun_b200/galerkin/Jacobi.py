@@ -8,8 +8,12 @@ SymPy (`_a`, `_b`, `h0`, Jacobi.py:306-391); here the same closed forms are eval
 float64 (removable singularities at n = 0 taken analytically).
 
 `backward` is the reference's recurrence *series evaluation* (Jacobi.py:65-110) restated as a
-contraction with the Vandermonde table built by that recurrence, so it runs on the FP64 tensor
-cores instead of an N-step sequential scan.
+contraction with the table built by that SAME recurrence (`series_table`: its coefficient arrays are the reference's own
+sympy expressions a(n+1, n), a(n, n+1), a(n, n) lambdified over arange(N), so the table columns carry the rounding of the
+reference's scan), and runs on the FP64 tensor cores instead of an N-step sequential scan.  `forward` / `scalar_product`
+use the Vandermonde of `eval_basis_functions`, as the reference does (orthogonal.py:264-277).  The two recurrences agree to
+k^2 ulp only: at n = 1024 a single high mode differs by 2e-11 of its own magnitude between them, so the backward table must
+follow `_evaluate`, not `vandermonde`, to stay within the 1e-12 parity bar for such inputs.
 """
 from __future__ import annotations
 
@@ -84,6 +88,50 @@ class Jacobi(OrthogonalSpace):
         bp = bp * g[2:n + 2] / g[1:n + 1]       # b(i=k+1, j=k+2)
         return bm, bp, bb
 
+    # ---- the reference's series-evaluation recurrence (Jacobi.py:65-110) ------------------------------
+    def gn_symbolic(self, n):
+        """Scaling g_n as a SymPy expression (Jacobi.py:344-357; subclasses override like the reference's do)."""
+        import sympy as sp
+        return sp.S.One
+
+    def _a_symbolic(self, i, j):
+        """`Jacobi.a(i, j)` (Jacobi.py:359-374, 421-447): gn(j) / gn(i) * _a(i, j), simplified when symbolic."""
+        import sympy as sp
+        a, b = sp.nsimplify(self.alpha), sp.nsimplify(self.beta)
+        delta = lambda m, n: sp.KroneckerDelta(m, n)  # noqa: E731
+        f = (2 * (j + a) * (j + b) / ((2 * j + a + b + 1) * (2 * j + a + b)) * delta(i + 1, j)
+             - (a**2 - b**2) / ((2 * j + a + b + 2) * (2 * j + a + b)) * delta(i, j)
+             + 2 * (j + 1) * (j + a + b + 1) / ((2 * j + a + b + 2) * (2 * j + a + b + 1)) * delta(i - 1, j))
+        return sp.simplify(self.gn_symbolic(j) / self.gn_symbolic(i) * f)
+
+    def series_coefficients(self, N: int):
+        """(am, ap, aa) exactly as `Jacobi._evaluate` builds them (Jacobi.py:81-89): the SymPy expressions a(n+1, n),
+        a(n, n+1) and — only when alpha != beta — a(n, n), lambdified and evaluated over arange(N) in float64."""
+        import sympy as sp
+        key = (type(self).__name__, str(sp.nsimplify(self.alpha)), str(sp.nsimplify(self.beta)), int(N))
+        v = _SERIES_CACHE.get(key)
+        if v is None:
+            v = _SERIES_CACHE[key] = _series_coefficients(self, int(N))
+        return v
+
+    def series_table(self, X, n_coeff: int) -> np.ndarray:
+        """[len(X), n_coeff] table whose column k is `_evaluate(X, e_k)` of the reference (Jacobi.py:91-110):
+        x0 = 1, x1 = (X - aa[0]) / am[0] * x0, x2 = ((X - aa[i-1]) x1 - ap[i-2] x0) / am[i-1]."""
+        X = np.atleast_1d(np.asarray(X, dtype=float))
+        V = np.empty((X.shape[0], n_coeff))
+        x0 = np.ones_like(X)
+        V[:, 0] = x0
+        if n_coeff == 1:
+            return V
+        am, ap, aa = self.series_coefficients(n_coeff)
+        x1 = (X - aa[0]) / am[0] * x0
+        V[:, 1] = x1
+        for i in range(2, n_coeff):
+            x2 = ((X - aa[i - 1]) * x1 - ap[i - 2] * x0) / am[i - 1]
+            V[:, i] = x2
+            x0, x1 = x1, x2
+        return V
+
     # ---- host tables ---------------------------------------------------------------------------------
     def quad_points_and_weights(self, N: int | None = None):
         N = self.num_quad_points if N is None else N
@@ -136,3 +184,26 @@ class Jacobi(OrthogonalSpace):
             out[n] = x2
             x0, x1 = x1, x2
         return out
+
+
+_SERIES_CACHE: dict = {}
+
+
+def _series_coefficients(space, N: int):
+    import sympy as sp
+    n = sp.Symbol("n", integer=True, positive=True)
+
+    def lamb(expr):
+        v = sp.lambdify(n, expr, modules=["scipy", "numpy"])(np.arange(N))
+        if np.ndim(v) == 0:                                   # Jacobi.py:83-86: scalar results are broadcast
+            v = np.full(N, float(v))
+        return np.asarray(v, dtype=float)
+
+    am = lamb(space._a_symbolic(n + 1, n))
+    ap = lamb(space._a_symbolic(n, n + 1))
+    aa = np.zeros_like(am)
+    if sp.nsimplify(space.alpha) != sp.nsimplify(space.beta):
+        aa = lamb(space._a_symbolic(n, n))
+    for v in (am, ap, aa):
+        v.setflags(write=False)
+    return am, ap, aa

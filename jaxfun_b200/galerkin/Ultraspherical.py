@@ -20,3 +20,8 @@ class Ultraspherical(Jacobi):
 
     def gn_values(self, n: int) -> np.ndarray:
         return self._inv_jacobi_at_one(n)
+
+    def gn_symbolic(self, n):
+        """1 / P_n^{(alpha,beta)}(1) (Ultraspherical.py:74-83)."""
+        import sympy as sp
+        return sp.S.One / sp.jacobi(n, sp.nsimplify(self.alpha), sp.nsimplify(self.beta), 1)

@@ -390,6 +390,35 @@ class DirectSum:
         return self._add(self.a.evaluate(x, c, axis), np.ascontiguousarray(lift), axis)
 
 
+def _normalize_neumann(bcs: dict, domain) -> dict:
+    """`BoundaryConditions.__init__` for dict input (composite.py:66-73, built with domain=domain by functionspace.py:134):
+    Neumann-type values ("N", "N2", ...) are given in physical units and divided by df**nd, df = 2 / (b - a), so that they
+    prescribe derivatives with respect to the reference coordinate.  Dirichlet and Robin entries are left alone."""
+    if domain is None:
+        return bcs
+    a, b = (float(v) for v in domain)
+    df = 2.0 / (b - a)
+    if df == 1.0:
+        return bcs
+
+    def scaled(v, f):
+        if callable(v) and not isinstance(v, sp.Basic):
+            return lambda *xs, _v=v: np.asarray(_v(*xs)) / f
+        if isinstance(v, np.ndarray):
+            return v / f
+        return sp.sympify(v) / f if isinstance(v, sp.Basic) else v / f
+
+    out = {}
+    for side, kinds in bcs.items():
+        out[side] = {}
+        for kind, v in kinds.items():
+            if kind[0] == "N" and not (not isinstance(v, (tuple, list)) and _is_zero(v)):
+                nd = int(kind[1:]) if len(kind) > 1 else 1
+                v = scaled(v, df**nd)
+            out[side][kind] = v
+    return out
+
+
 def FunctionSpace(N: int, space, bcs=None, domain=None, name: str = "fun", fun_str: str = "phi", scaling=None, **kw):
     """`jaxfun.galerkin.functionspace.FunctionSpace` (functionspace.py:63-173) for the cases whose stencil is
     known in closed form: no BCs -> the orthogonal space; homogeneous Dirichlet on both ends of a Chebyshev /
@@ -398,6 +427,7 @@ def FunctionSpace(N: int, space, bcs=None, domain=None, name: str = "fun", fun_s
         return space(N, domain=domain, name=name, fun_str=fun_str, **kw)
     bcs = {side: {kind: (0 if (not isinstance(v, (tuple, list)) and _is_zero(v)) else v) for kind, v in kinds.items()}
            for side, kinds in bcs.items()}
+    bcs = _normalize_neumann(bcs, domain)
     if any(not _is_zero(_bc_value(v)) for side in bcs.values() for v in side.values()):
         # functionspace.py:150-173: homogeneous Composite (+) boundary lift
         hom = {side: {kind: ((v[0], 0) if isinstance(v, (tuple, list)) else 0) for kind, v in kinds.items()}

@@ -189,7 +189,9 @@ class OrthogonalSpace:
             # the reference evaluates at mesh() (true domain) and maps back (orthogonal.py:226-227,
             # 113-115); keep that round trip so the nodes carry the same rounding
             xj = self.map_reference_domain(self.mesh("quadrature", n_quad))
-            T = self.vandermonde(xj)[:, :n_coeff]          # backward: sum_k c_k psi_k(x_j)
+            # backward: sum_k c_k psi_k(x_j).  Spaces whose reference backward is a series recurrence of its own
+            # (Jacobi._evaluate) supply that recurrence's table; the others the Vandermonde (orthogonal.py:117-129)
+            T = self.series_table(xj, n_coeff) if hasattr(self, "series_table") else self.vandermonde(xj)[:, :n_coeff]
             if deriv:
                 T = (float(self.domain_factor) ** deriv) * (T @ self.derivative_matrix(deriv, n_coeff))
         T = np.ascontiguousarray(T)
@@ -269,8 +271,10 @@ class OrthogonalSpace:
         X = np.atleast_1d(np.asarray(self.map_reference_domain(np.asarray(x, dtype=float))))
         n = c.shape[axis]
         assert n <= self.N, f"Coefficient length {n} exceeds N={self.N}"
-        T = np.ascontiguousarray(self.eval_basis_functions(X)[:, :n])
-        return self._run(L.OP_APPLY, c, axis, table=T, cache=False)
+        # the reference evaluates through _evaluate (orthogonal.py:102-115): Jacobi-type spaces have their own series recurrence
+        T = self.series_table(X, n) if hasattr(self, "series_table") and type(self)._dense_table is OrthogonalSpace._dense_table \
+            else self.eval_basis_functions(X)[:, :n]
+        return self._run(L.OP_APPLY, c, axis, table=np.ascontiguousarray(T), cache=False)
 
     def evaluate_mesh(self, c, kind: str = "quadrature", N: int | None = None, axis: int = -1):
         kind = getattr(kind, "value", kind)

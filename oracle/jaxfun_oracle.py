@@ -985,8 +985,15 @@ _BC_DERIV = {"D": 0, "R": 0, "N": 1, "N2": 2, "N3": 3, "N4": 4}
 class BoundaryConditions(dict):
     """composite.py:40-118.  Robin conditions ("R": u + alfa u', "W": u' + alfa u'') carry the tuple (alfa, value)."""
 
-    def __init__(self, bc):
+    def __init__(self, bc, domain=None):
         super().__init__({"left": dict(bc.get("left", {})), "right": dict(bc.get("right", {}))})
+        if not isinstance(bc, BoundaryConditions) and domain is not None:   # composite.py:66-73: dict input is normalised
+            df = 2 / (float(domain[1]) - float(domain[0]))
+            for val in self.values():
+                for k, v in val.items():
+                    if k[0] == "N":
+                        nd = int(k[1:]) if len(k) > 1 else 1
+                        val[k] = v / df**nd
 
     def orderednames(self):                                     # composite.py:75-79
         return ["L" + k for k in sorted(self["left"])] + ["R" + k for k in sorted(self["right"])]
@@ -1045,7 +1052,7 @@ class DirectSum:
 
     def __init__(self, a, bcs):
         self.a = a
-        self.bcs = BoundaryConditions(bcs)
+        self.bcs = BoundaryConditions(bcs, domain=tuple(a.domain))   # functionspace.py:134
         self.orthogonal = a.orthogonal
         self.N = a.N
         self.domain = a.domain

@@ -93,7 +93,7 @@ static void run_tiles(const Args& q, const MapDesc& mA, const MapDesc& mB, std::
             for (int lane = 0; lane < 32; ++lane) {
               double dummy[8][4][2];
               double* d0base = &dummy[0][0][0];
-              ktile<V>(stage.data(), wm, wn, lane >> 2, lane & 3, q.par_plus, dummy,
+              ktile<V>(stage.data(), frag_init<V>(wm, wn, lane >> 2, lane & 3), ktile_par(q, kt), dummy,
                        [&](double& d0, double& d1, double a, double b) {
                          assert(&d1 == &d0 + 1);
                          rec[lane].push_back(Rec{(int)((&d0 - d0base) / 2), a, b});
@@ -125,13 +125,15 @@ static void run_tiles(const Args& q, const MapDesc& mA, const MapDesc& mB, std::
 }
 
 static int g_fail = 0;
+static bool g_single = false;       // inputs = single high modes, error measured per line relative to that line's max-norm
+static double g_tol_fix = TOL_FIX;   // lowered by run_corr_case so that small synthetic asymmetries need correction
 
 // the check proper: table [rows][cols] (type / par_plus < 0: whatever analyze() finds), array [outer][cols][inner]
 static void check_table(const std::vector<double>& T, int rows, int cols, int type, int par_plus, long long outer,
                         long long inner, unsigned seed, double tol) {
   std::mt19937_64 rng(seed ^ 0x9e3779b97f4a7c15ull);
   std::uniform_real_distribution<double> U(-1.0, 1.0);
-  const FoldInfo fi = analyze(T.data(), rows, cols);
+  const FoldInfo fi = analyze(T.data(), rows, cols, 1e-12, 1e-10, g_tol_fix);
   if ((type >= 0 && fi.type != type) || (par_plus >= 0 && fi.par_plus != par_plus) || fi.type == FOLD_NONE) {
     printf("FAIL analyze: type %d par %d -> got %d %d (rows %d cols %d)\n", type, par_plus, fi.type, fi.par_plus, rows, cols);
     ++g_fail;
@@ -145,6 +147,11 @@ static void check_table(const std::vector<double>& T, int rows, int cols, int ty
   const int n_in = cols, n_out = rows;
   std::vector<double> X((size_t)outer * n_in * inner + 2), ref((size_t)outer * n_out * inner);
   for (auto& v : X) v = U(rng);
+  if (g_single) {   // line (o, i) holds the single mode n_in - 1 - ((o * inner + i) % 24)
+    for (auto& v : X) v = 0.0;
+    for (long long o = 0; o < outer; ++o)
+      for (long long i = 0; i < inner; ++i) X[((size_t)o * n_in + (n_in - 1 - (int)((o * inner + i) % 24))) * inner + i] = 1.0;
+  }
   for (long long o = 0; o < outer; ++o)
     for (int r = 0; r < n_out; ++r)
       for (long long i = 0; i < inner; ++i) {
@@ -183,6 +190,19 @@ static void check_table(const std::vector<double>& T, int rows, int cols, int ty
     nrm = std::fmax(nrm, std::fabs(ref[i]));
     if (cnt[i] != 1) ++bad_cnt;
   }
+  if (g_single) {   // worst line: error over the max-norm of that line
+    err = 0; nrm = 1;
+    for (long long o = 0; o < outer; ++o)
+      for (long long i = 0; i < inner; ++i) {
+        double e = 0, m = 0;
+        for (int r = 0; r < n_out; ++r) {
+          const size_t idx = ((size_t)o * n_out + r) * inner + i;
+          e = std::fmax(e, std::fabs(out[idx] - ref[idx]));
+          m = std::fmax(m, std::fabs(ref[idx]));
+        }
+        err = std::fmax(err, e / std::fmax(m, 1e-300));
+      }
+  }
   const bool ok = err <= tol * std::fmax(nrm, 1e-300) && bad_cnt == 0;
   printf("%s variant %d par %d n_fold %3d n_other %3d outer %4lld inner %4lld  err %.2e  miswritten %lld\n", ok ? "ok  " : "FAIL",
          q.variant, par_plus, n_fold, n_other, outer, inner, err, bad_cnt);
@@ -205,6 +225,35 @@ static void run_case(int type, int par_plus, int n_fold, int n_other, long long 
     }
   }
   check_table(T, rows, cols, type, par_plus, outer, inner, seed, 1e-13);
+}
+
+// OUT table whose highest modes are mirror images only approximately (what the reference's Gauss-Legendre nodes do to its
+// Vandermonde at n >= 320): analyze() must ask for correction k-tiles for exactly that tail and the result must again be
+// the contraction with the table AS GIVEN to rounding — while the uncorrected fold would be off by `asym`.
+static void run_corr_case(int par_plus, int n_fold, int n_other, int n_bad, double asym, long long outer, long long inner,
+                          unsigned seed) {
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  const int rows = n_fold, cols = n_other;
+  std::vector<double> T((size_t)rows * cols);
+  for (int k = 0; k < n_other; ++k) {
+    const double s = ((k & 1) == par_plus) ? 1.0 : -1.0;
+    for (int j = 0; j < n_fold / 2; ++j) {
+      const double v = U(rng);
+      T[(size_t)j * cols + k] = v;
+      T[(size_t)(n_fold - 1 - j) * cols + k] = s * v * (k >= n_other - n_bad ? 1.0 + asym * U(rng) : 1.0);
+    }
+  }
+  g_tol_fix = 1e-3 * asym;
+  const FoldInfo fi = analyze(T.data(), rows, cols, 1e-12, 1e-10, g_tol_fix);
+  const int want = (n_other - n_bad) / 2;
+  if (fi.type != FOLD_OUT || fi.kcorr0 < 0 || fi.kcorr0 > want || fi.kcorr0 < want - 1) {
+    printf("FAIL analyze (correction): type %d kcorr0 %d, expected OUT with kcorr0 ~ %d\n", fi.type, fi.kcorr0, want);
+    ++g_fail;
+    return;
+  }
+  check_table(T, rows, cols, FOLD_OUT, par_plus, outer, inner, seed, 1e-3 * asym);
+  g_tol_fix = TOL_FIX;
 }
 
 // CPLX_NT: complex interleaved rows times an arbitrary real table
@@ -280,7 +329,7 @@ static void run_tiles_scatter(const Args& q, const Scatter& sc, const MapDesc& m
           for (int lane = 0; lane < 32; ++lane) {
             double dummy[8][4][2];
             double* d0base = &dummy[0][0][0];
-            ktile<V>(stage.data(), w / WARPS_N, w % WARPS_N, lane >> 2, lane & 3, q.par_plus, dummy,
+            ktile<V>(stage.data(), frag_init<V>(w / WARPS_N, w % WARPS_N, lane >> 2, lane & 3), ktile_par(q, kt), dummy,
                      [&](double& d0, double& d1, double a, double b) { (void)d1; rec[lane].push_back(Rec{(int)((&d0 - d0base) / 2), a, b}); });
           }
           for (size_t r = 0; r < rec[0].size(); ++r)
@@ -380,6 +429,14 @@ int main(int argc, char** argv) {
     fclose(f);
     check_table(T, rows, cols, -1, -1, 2, 34, 11, 1e-12);
     check_table(T, rows, cols, -1, -1, 37, 1, 12, 1e-12);
+    if (analyze(T.data(), rows, cols).type == FOLD_OUT) {
+      // backward-type tables: single high modes, every line within 1e-12 of its own max-norm (the parity bar of BASELINE.json
+      // for the adversarial input of the fold; needs the correction k-tiles from n = 320 on)
+      g_single = true;
+      check_table(T, rows, cols, -1, -1, 2, 34, 13, 1e-12);
+      check_table(T, rows, cols, -1, -1, 37, 1, 14, 1e-12);
+      g_single = false;
+    }
     printf(g_fail ? "FOLD EMU: %d FAILURES\n" : "FOLD EMU: ALL OK\n", g_fail);
     return g_fail ? 1 : 0;
   }
@@ -431,6 +488,39 @@ int main(int argc, char** argv) {
     run_scatter_case(FOLD_OUT, 1, P, 5, 2 * P, 66, 34, seed++);
     run_scatter_case(FOLD_IN, 2, P, 2 * P, 5, 32, 16, seed++);
     run_scatter_case(FOLD_IN, 2, P, P, 24, 66, 33, seed++);
+  }
+  // asymmetric high modes: correction k-tiles (1 .. 3 tiles, ragged tails, both orders and parities)
+  for (int pp = 0; pp < 2; ++pp) {
+    run_corr_case(pp, 64, 64, 3, 5e-13, 2, 34, seed++);
+    run_corr_case(pp, 64, 64, 3, 5e-13, 37, 1, seed++);
+    run_corr_case(pp, 130, 128, 30, 5e-13, 1, 130, seed++);
+    run_corr_case(pp, 130, 128, 30, 5e-13, 129, 1, seed++);
+    run_corr_case(pp, 256, 200, 47, 5e-13, 3, 6, seed++);
+    run_corr_case(pp, 256, 200, 47, 5e-13, 260, 1, seed++);
+    run_corr_case(pp, 96, 70, 1, 5e-13, 1, 258, seed++);
+    run_corr_case(pp, 96, 70, 1, 5e-13, 5, 1, seed++);
+  }
+  // too many asymmetric modes (> 1/4): not folded at all
+  {
+    std::mt19937_64 rng(123);
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    const int n = 64;
+    std::vector<double> T(n * n);
+    for (int k = 0; k < n; ++k)
+      for (int j = 0; j < n / 2; ++j) {
+        const double v = U(rng);
+        T[j * n + k] = v;
+        T[(n - 1 - j) * n + k] = ((k & 1) ? -1.0 : 1.0) * v * (k >= 20 ? 1.0 + 1e-11 * U(rng) : 1.0);
+      }
+    if (analyze(T.data(), n, n).type != FOLD_NONE) { printf("FAIL: table with 2/3 asymmetric modes folded\n"); ++g_fail; }
+    else printf("ok   table with too many asymmetric modes refused\n");
+    // the same asymmetry on an IN table (forward): refused as well (no correction path there)
+    std::vector<double> Tt(n * n);
+    for (int k = 0; k < n; ++k)
+      for (int j = 0; j < n; ++j) Tt[k * n + j] = T[j * n + k] * (k >= 60 || k < 20 ? 1.0 : 0.0) + (k >= 20 && k < 60 ? T[std::min(j, n - 1 - j) * n + k] * ((j >= n / 2 && (k & 1)) ? -1.0 : 1.0) : 0.0);
+    const FoldInfo fi2 = analyze(Tt.data(), n, n);
+    if (fi2.type == FOLD_IN) { printf("FAIL: asymmetric IN table folded\n"); ++g_fail; }
+    else printf("ok   asymmetric IN table refused\n");
   }
   // tables without the symmetry must be refused
   {

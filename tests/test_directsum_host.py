@@ -65,6 +65,31 @@ def test_oracle_directsum_roundtrip_and_boundary_values():
     assert np.abs(D.from_orthogonal(D.to_orthogonal(c)) - c).max() < 1e-12
 
 
+@pytest.mark.parametrize("space", ["Legendre", "Chebyshev"])
+def test_inhomogeneous_neumann_on_a_mapped_domain_is_in_physical_units(space):
+    """BoundaryConditions(dict, domain) divides Neumann-type values by df**nd, df = 2 / (b - a) (composite.py:66-73 through
+    functionspace.py:134): {'N': 1} on (0, 4) prescribes du/dx = 1 at x = 4, not dU/dX = 1 in the reference coordinate."""
+    import jaxfun_b200 as jf
+    dom = (0.0, 4.0)
+    bcs = {"left": {"D": 0.5}, "right": {"N": 1.0, "N2": -3.0}}
+    D = jf.FunctionSpace(14, getattr(jf, space), bcs, domain=dom)
+    Do = O.DirectSum(O.Composite(14, getattr(O, space), D.a.stencil, domain=dom), bcs)
+    assert np.abs(D.c_b - Do.c_b).max() < 1e-13
+    V = D.orthogonal
+    df = float(V.domain_factor)                                   # = 0.5
+    for k, want in ((0, None), (1, 1.0), (2, -3.0)):
+        # k-th physical derivative of the lift at the right end: df^k sum_j c_j P_j^(k)(1)
+        got = df**k * (V.evaluate_basis_derivative(np.array([1.0]), k)[0] @ D.c_b)
+        if want is not None:
+            assert abs(got - want) < 1e-11, (k, got, want)
+    left = V.eval_basis_functions(np.array([-1.0]))[0] @ D.c_b
+    assert abs(left - 0.5) < 1e-12
+    # the reference domain leaves the values alone
+    D1 = jf.FunctionSpace(14, getattr(jf, space), bcs)
+    assert np.allclose(D1.bnd_vals(), [0.5, 1.0, -3.0])
+    assert np.allclose(D.bnd_vals(), [0.5, 1.0 / df, -3.0 / df**2])
+
+
 # ---- homogeneous stencils: numeric derivation vs the reference's symbolic get_stencil_matrix ---------------------------
 STENCILS = json.load(open(os.path.join(HERE, "golden", "reference_stencils.json")))["cases"]
 

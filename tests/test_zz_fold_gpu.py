@@ -91,7 +91,9 @@ def rel(a, b): return np.abs(a - b).max() / np.abs(b).max()
 def cplx(shape): return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
 cases = [((jf.Fourier(32), jf.Legendre(48)), (O.Fourier(32), O.Legendre(48)), (32, 48)),
          ((jf.Fourier(16), jf.Fourier(32), jf.Legendre(64)), (O.Fourier(16), O.Fourier(32), O.Legendre(64)), (16, 32, 64)),
-         ((jf.Fourier(64), jf.Jacobi(40, alpha=0.5, beta=-0.5)), (O.Fourier(64), O.Jacobi(40, alpha=0.5, beta=-0.5)), (64, 40)),
+         # (alpha = -beta != 0 is not a valid case: the reference itself raises there, Jacobi.py:84-96 indexes the int 0 that
+         #  sympy returns for a(n, n) when alpha**2 == beta**2 but alpha != beta)
+         ((jf.Fourier(64), jf.Jacobi(40, alpha=1.0, beta=0.5)), (O.Fourier(64), O.Jacobi(40, alpha=1.0, beta=0.5)), (64, 40)),
          ((jf.Fourier(8), jf.Chebyshev(36)), (O.Fourier(8), O.Chebyshev(36)), (8, 36))]
 for sp, so, shape in cases:
     T, To = jf.TensorProduct(*sp), O.TensorProductSpace(*so)
@@ -108,8 +110,6 @@ print("CPLX NT OK")
 """
 
 
-@pytest.mark.xfail(strict=False, reason="CPLX_NT (complex data on a last table axis as one NT launch, JFX_CPLX_NT=1) was written after "
-                                        "the round's GPU budget was spent: checked by the host emulator only, opt-in until this passes")
 def test_complex_last_axis_nt_variant(cuda):
     e = dict(os.environ)
     e["JFX_CPLX_NT"] = "1"
@@ -167,11 +167,7 @@ for P in (2, 4, 8):
 print("SCATTER OK")
 """
 
-_UNRUN = ("written after the round's GPU budget was spent: checked by the host emulator (tests/emu/fold_emu.cpp) only, opt-in "
-          "until this passes on a GPU")
 
-
-@pytest.mark.xfail(strict=False, reason="jfx_execute_scatter (slab exchange fused into the last contraction pass) " + _UNRUN)
 def test_scatter_execution_emulated_ranks(cuda):
     """The peer-store exchange on ONE GPU, in its own process: P emulated ranks run phase 1 with jfx_execute_scatter into P
     receive buffers; every buffer must equal what pack + tiled all-to-all (+ unpack) of the ordinary path leaves on that rank."""
@@ -181,7 +177,6 @@ def test_scatter_execution_emulated_ranks(cuda):
     assert r.returncode == 0 and "SCATTER OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-@pytest.mark.xfail(strict=False, reason="fold_check --extra (CPLX_NT and jfx_execute_scatter through the C ABI) " + _UNRUN)
 def test_fold_check_extra_c_abi(cuda):
     tool = os.path.join(ROOT, "tools", "fold_check")
     assert os.path.exists(tool)
@@ -214,8 +209,6 @@ print("GRAPH OK")
 """
 
 
-@pytest.mark.xfail(strict=False, reason="BaseIntegrator.solve(graph=True) (one CUDA graph per time step) " + _UNRUN.replace(
-    "checked by the host emulator (tests/emu/fold_emu.cpp) only", "never run"))
 def test_graphed_time_stepping_equals_eager(cuda):
     """12 ETDRK4 / RK4 steps of KdV with the step captured into a CUDA graph give bit-identical coefficients (own process:
     a failed capture must not leave the suite's stream in capture mode)."""
