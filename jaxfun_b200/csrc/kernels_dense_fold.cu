@@ -112,7 +112,7 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
   __syncthreads();
 
   const int kts = ktiles(q);
-  const long long total_tiles = (long long)q.tiles_n * q.tiles_m * q.batch;
+  const unsigned total_tiles = (unsigned)q.tiles_n * (unsigned)q.tiles_m * (unsigned)q.batch;   // < 2^31: checked by the host
 
   if (warp >= MMA_WARPS) {
     // ================================ producer warpgroup ================================
@@ -120,15 +120,15 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
 #endif
     if (warp != MMA_WARPS || lane != 0) return;
-    long long it = 0;
-    for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
-      const int tn = (int)(tl % q.tiles_n);
-      const long long r = tl / q.tiles_n;
-      const int tm = (int)(r % q.tiles_m);
-      const int z = (int)(r / q.tiles_m);
+    unsigned it = 0;
+    for (unsigned tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
+      const unsigned r = tl / (unsigned)q.tiles_n;
+      const int tn = (int)(tl - r * (unsigned)q.tiles_n);
+      const int z = (int)(r / (unsigned)q.tiles_m);
+      const int tm = (int)(r - (unsigned)z * (unsigned)q.tiles_m);
       for (int kt = 0; kt < kts; ++kt, ++it) {
         const int s = (int)(it % STAGES);
-        const unsigned ph = (unsigned)((it / STAGES) & 1);
+        const unsigned ph = (it / STAGES) & 1u;
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
         const unsigned full = bar_full + 8 * s;
         mbar_expect_tx(full, STAGE_BYTES);
@@ -158,21 +158,32 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  long long it = 0;
-  for (long long tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
+  unsigned it = 0;
+  int prev = -1;
+  for (unsigned tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
     for (int kt = 0; kt < kts; ++kt, ++it) {
       const int s = (int)(it % STAGES);
-      const unsigned ph = (unsigned)((it / STAGES) & 1);
+      const unsigned ph = (it / STAGES) & 1u;
       mbar_wait(bar_full + 8 * s, ph);
+      // Release of the PREVIOUS stage, here and not at the end of its k-tile.  ptxas schedules an arrive that follows the
+      // k-tile directly behind the last fragment loads and ahead of the MMAs that consume them; the arrive then takes
+      // effect while those LDS are still queued, and when this warp is the last of the eight the producer's refill (the
+      // table tile comes from L2 in a few hundred ns) can overwrite the 1 KB atoms they address.  Seen on the B200 as
+      // wrong minus-half accumulators in ~1e-5 of the warp k-tiles whenever the producer was not far ahead, and gone
+      // with a slowed-down producer (tools/forensic.py).  After the spin loop of the next wait every MMA of the previous
+      // k-tile has issued, i.e. every fragment register has been written: the stage is really free.
+      if (prev >= 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * prev);
+      }
+      prev = s;
       const double* S = reinterpret_cast<const double*>(gbase + (size_t)s * STAGE_BYTES);
       ktile<V>(S, fr, ktile_par(q, kt), acc, MmaOp{});
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
     }
-    const int tn = (int)(tl % q.tiles_n);
-    const long long r = tl / q.tiles_n;
-    const int tm = (int)(r % q.tiles_m);
-    const long long z = r / q.tiles_m;
+    const unsigned r = tl / (unsigned)q.tiles_n;
+    const int tn = (int)(tl - r * (unsigned)q.tiles_n);
+    const long long z = r / (unsigned)q.tiles_m;
+    const int tm = (int)(r - (unsigned)z * (unsigned)q.tiles_m);
     epi(tm, tn, z, wm, wn, g, t, acc);
 #pragma unroll
     for (int i = 0; i < 8; ++i)

@@ -180,12 +180,21 @@ dgemm_dmma_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int j = 0; j < WN / 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   long long it = 0;
+  int prev = -1;
   for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
     for (int kt = 0; kt < ktiles; ++kt, ++it) {
       if (!PW && warp == 0) load_next();   // refills the stage consumed at iteration it - 2
       const int s = (int)(it % STAGES);
       const unsigned ph = (unsigned)((it / STAGES) & 1);
       mbar_wait(bar_full + 8 * s, ph);
+      // the previous stage is released here, after the spin loop: every MMA of the previous k-tile has issued by now, so
+      // every fragment load of it has completed (an arrive placed at the end of the k-tile is scheduled behind the last
+      // LDS *issue* and can take effect before they read; see kernels_dense_fold.cu)
+      if (prev >= 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * prev);
+      }
+      prev = s;
       const double* As = reinterpret_cast<const double*>(gbase + (size_t)s * STAGE_BYTES);
       const double* Bs = As + A_TILE;
 #pragma unroll
@@ -213,8 +222,6 @@ dgemm_dmma_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < WN / 8; ++j) mma_884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
     }
     // epilogue of this tile: the ring is already being filled for the next one
     const int tn = (int)(t % q.tiles_n);
