@@ -225,6 +225,15 @@ int jfx_slab_unpack(void* stream, const void* in, void* out, const int64_t* shap
 int jfx_axpby_diag(void* stream, int n_terms, const void* const* coeff, const double* alpha,
                    const void* const* x, void* out, int64_t n, int dtype, int coeff_is_complex);
 
+/* Scattered-point evaluation (TensorProductSpace.evaluate, galerkin/tensorproductspace.py:263-321: einsum "i,j,ij" per point).
+   The last axis is contracted with the basis values of all points by an ordinary JFX_OP_APPLY plan; every remaining axis is
+   then reduced with per-point weights:   out[o, p] = sum_j y[o, j, p] * w[p, j]
+   y: [outer, n, points] (dtype), w: [points, n] values of the axis' basis functions at the points — real (float64 for
+   f64 / c128, float32 for f32 / c64), or with w_is_complex != 0 the array dtype itself (Fourier axes) —, out: [outer, points].
+   Device pointers. */
+int jfx_point_contract(void* stream, const void* y, const void* w, void* out, int64_t outer, int32_t n, int64_t points,
+                       int dtype, int w_is_complex);
+
 /* Calibration helpers used by bench.py (not on the product path). */
 int jfx_calibrate_dmma(void* stream, int iters, double* tflops);
 int jfx_calibrate_dfma(void* stream, int iters, double* tflops);

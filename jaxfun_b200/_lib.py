@@ -103,6 +103,8 @@ _SIGNATURES = {
                                   C.c_int, C.c_int, C.c_int]),
     "jfx_axpby_diag": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_double),
                                  C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int, C.c_int]),
+    "jfx_point_contract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int,
+                                   C.c_int]),
     "jfx_calibrate_dmma": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "jfx_calibrate_dfma": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
 }

@@ -835,6 +835,13 @@ int jfx_axpby_diag(void* stream, int n_terms, const void* const* coeff, const do
   JFX_REQUIRE(x && out, JFX_ERR_INVALID, "null argument");
   return launch_axpby_diag((cudaStream_t)stream, n_terms, coeff, alpha, x, out, n, dtype, coeff_is_complex);
 }
+int jfx_point_contract(void* stream, const void* y, const void* w, void* out, int64_t outer, int32_t n, int64_t points,
+                       int dtype, int w_is_complex) {
+  using namespace jfx;
+  JFX_REQUIRE(y && w && out, JFX_ERR_INVALID, "null argument");
+  JFX_REQUIRE(dtype >= JFX_F32 && dtype <= JFX_C128, JFX_ERR_INVALID, "bad dtype %d", dtype);
+  return launch_point_contract((cudaStream_t)stream, y, w, out, outer, n, points, dtype, w_is_complex);
+}
 int jfx_calibrate_dmma(void* stream, int iters, double* tflops) {
   using namespace jfx;
   JFX_REQUIRE(tflops && iters > 0, JFX_ERR_INVALID, "bad argument");

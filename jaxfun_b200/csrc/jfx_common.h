@@ -91,6 +91,8 @@ int launch_slab_pack(cudaStream_t s, const void* in, void* out, const int64_t* s
                      int split_axis, int parts, int dtype);
 int launch_slab_unpack(cudaStream_t s, const void* in, void* out, const int64_t* shape_out,
                        int ndim, int concat_axis, int parts, int dtype);
+int launch_point_contract(cudaStream_t s, const void* y, const void* w, void* out, int64_t outer, int n, int64_t P, int dtype,
+                          int w_is_complex);
 int launch_axpby_diag(cudaStream_t s, int n_terms, const void* const* coeff, const double* alpha,
                       const void* const* x, void* out, int64_t n, int dtype, int coeff_is_complex);
 // Polynomial normal form of a pointwise program:  sum_t coeff_t * prod_f x_f,  x_f = leaf or conj(leaf).

@@ -272,6 +272,70 @@ int launch_axpby_diag(cudaStream_t s, int n_terms, const void* const* coeff, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-point contraction of scattered evaluation (TensorProductSpace.evaluate, tensorproductspace.py:263-273 of the
+// reference: einsum("i,j,ij") per point).  After the last axis has been contracted with the basis values of all points
+// (a table pass), every remaining axis is reduced with weights that differ per point:
+//     out[o, p] = sum_j y[o, j, p] * w[p, j]          y: [outer, n, P] data dtype,  w: [P, n] real (double / float)
+// One thread per (o, p): consecutive threads read consecutive p of y (coalesced); w[p, :] stays in L1 / L2.
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool CPLX, bool WCPLX>
+__global__ void __launch_bounds__(256) point_contract_kernel(const void* __restrict__ y_, const void* __restrict__ w_,
+                                                             void* __restrict__ out_, int64_t outer, int n, int64_t P) {
+  const int64_t total = outer * P;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = idx / P, p = idx - o * P;
+    if (CPLX) {
+      const C2<T>* y = reinterpret_cast<const C2<T>*>(y_) + o * (int64_t)n * P + p;
+      T re = 0, im = 0;
+      for (int j = 0; j < n; ++j) {
+        const C2<T> v = y[(int64_t)j * P];
+        if (WCPLX) {
+          const C2<T> ww = reinterpret_cast<const C2<T>*>(w_)[p * n + j];
+          re += v.re * ww.re - v.im * ww.im;
+          im += v.re * ww.im + v.im * ww.re;
+        } else {
+          const T ww = reinterpret_cast<const T*>(w_)[p * n + j];
+          re += v.re * ww;
+          im += v.im * ww;
+        }
+      }
+      reinterpret_cast<C2<T>*>(out_)[idx] = C2<T>{re, im};
+    } else {
+      const T* y = reinterpret_cast<const T*>(y_) + o * (int64_t)n * P + p;
+      const T* w = reinterpret_cast<const T*>(w_);
+      T acc = 0;
+      for (int j = 0; j < n; ++j) acc += y[(int64_t)j * P] * w[p * n + j];
+      reinterpret_cast<T*>(out_)[idx] = acc;
+    }
+  }
+}
+
+int launch_point_contract(cudaStream_t s, const void* y, const void* w, void* out, int64_t outer, int n, int64_t P, int dtype,
+                          int w_is_complex) {
+  JFX_REQUIRE(outer >= 0 && n >= 0 && P >= 0, JFX_ERR_INVALID, "negative extent");
+  JFX_REQUIRE(!(w_is_complex && !dtype_is_complex(dtype)), JFX_ERR_INVALID, "complex weights on real data");
+  if (outer * P == 0) return JFX_OK;
+  int64_t blocks = (outer * P + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const unsigned b = (unsigned)blocks;
+  switch (dtype) {
+    case JFX_F32: point_contract_kernel<float, false, false><<<b, 256, 0, s>>>(y, w, out, outer, n, P); break;
+    case JFX_F64: point_contract_kernel<double, false, false><<<b, 256, 0, s>>>(y, w, out, outer, n, P); break;
+    case JFX_C64:
+      if (w_is_complex) point_contract_kernel<float, true, true><<<b, 256, 0, s>>>(y, w, out, outer, n, P);
+      else point_contract_kernel<float, true, false><<<b, 256, 0, s>>>(y, w, out, outer, n, P);
+      break;
+    case JFX_C128:
+      if (w_is_complex) point_contract_kernel<double, true, true><<<b, 256, 0, s>>>(y, w, out, outer, n, P);
+      else point_contract_kernel<double, true, false><<<b, 256, 0, s>>>(y, w, out, outer, n, P);
+      break;
+    default: set_error("bad dtype"); return JFX_ERR_INVALID;
+  }
+  JFX_CUDA_OK(cudaGetLastError());
+  return JFX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // slab pack / unpack.  Arrays are viewed as [pre, len, post] around the split / concat axis.
 // pack:   out[p][pre][len/P][post] = in[pre][p*len/P + j][post]
 // unpack: out[pre][p*len/P + j][post] = in[p][pre][len/P][post]

@@ -144,10 +144,16 @@ class Composite(OrthogonalSpace):
 
     # ---- coefficient-space maps -------------------------------------------------------------------
     def to_orthogonal(self, a, axis: int = -1):
-        return self._run(L.OP_APPLY, a, axis, table=np.ascontiguousarray(self.S.T))
+        T = self._tables.get("to_orth")
+        if T is None:
+            T = self._tables["to_orth"] = np.ascontiguousarray(self.S.T)
+        return self._run(L.OP_APPLY, a, axis, table=T, name="to_orth")
 
     def from_orthogonal(self, a, axis: int = -1):
-        return self._run(L.OP_APPLY, a, axis, table=np.ascontiguousarray(self._P_inv @ self.S))
+        T = self._tables.get("from_orth")
+        if T is None:
+            T = self._tables["from_orth"] = np.ascontiguousarray(self._P_inv @ self.S)
+        return self._run(L.OP_APPLY, a, axis, table=T, name="from_orth")
 
     def _to_orthogonal_axis(self, c, axis):
         return self.to_orthogonal(c, axis)

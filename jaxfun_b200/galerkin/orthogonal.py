@@ -30,6 +30,23 @@ class Domain(NamedTuple):
     upper: float
 
 
+def metric_weight(system, mesh):
+    """sqrt(det g) of `system` sampled on `mesh` (a tuple of coordinate arrays), or None when it is 1.
+
+    `system` follows the protocol of `jaxfun.coordinates.CoordSys` as far as the transforms use it
+    (orthogonal.py:270-276, tensorproductspace.py:376-379): `.sg` is a number or a SymPy expression in `.base_scalars()`."""
+    if system is None:
+        return None
+    import sympy as sp
+    sg = sp.sympify(system.sg)
+    if sg == 1:
+        return None
+    if sg.is_number:
+        return complex(sg) if sg.has(sp.I) else float(sg)
+    vals = sp.lambdify(tuple(system.base_scalars()), sg, modules="numpy")(*mesh)
+    return np.asarray(vals)
+
+
 class OrthogonalSpace:
     is_orthogonal = True
     #: engine basis used when a fast kernel exists for the transform length (else dense table)
@@ -170,8 +187,12 @@ class OrthogonalSpace:
 
     # ---- per-axis engine specs ---------------------------------------------------------------
     def _weights_scaled(self, n: int):
+        """Quadrature weights times sg / df (orthogonal.py:268-276): `system.sg` is the metric weight of a curvilinear 1-D
+        coordinate (a number, or a SymPy expression in the true coordinate sampled at the true-domain nodes); None = 1."""
         xj, wj = self.quad_points_and_weights(n)
-        return xj, wj * (1.0 / float(self.domain_factor))
+        wj = wj * (1.0 / float(self.domain_factor))
+        sg = metric_weight(self.system, (np.asarray(self.map_true_domain(xj), dtype=float),))
+        return xj, (wj if sg is None else wj * sg)
 
     def _dense_table(self, op: int, n_coeff: int, n_quad: int, deriv: int) -> np.ndarray:
         """Dense [n_out, n_in] table of `op` along one axis (generic Vandermonde definition)."""
@@ -221,12 +242,23 @@ class OrthogonalSpace:
                         domain_factor=float(self.domain_factor), table=T)
 
     # ---- device transforms ------------------------------------------------------------------------
+    def __getstate__(self):
+        # engine plans hold ctypes handles: copies (TensorProduct deep-copies its factors, incl. the nested orthogonal space of
+        # a Composite) start without them and build their own
+        d = dict(self.__dict__)
+        d["_plans"] = {}
+        return d
+
     def _run(self, op: int, x, axis: int, N=None, k: int = 0, table: np.ndarray | None = None,
-             cache: bool = True):
+             cache: bool = True, name=None):
+        """`table`: explicit [n_out, n_in] table of an APPLY plan; cached plans of such tables are keyed by `name` (a stable
+        label chosen by the caller), never by the identity of a temporary array."""
         x, _ = as_jfx_array(x, self.complex_data)
         axis = axis % x.ndim
         dtype = jfx_dtype(x.dtype)
-        key = (op, dtype, tuple(x.shape), axis, N, k, None if table is None else id(table))
+        if table is not None and name is None:
+            cache = False
+        key = (op, dtype, tuple(x.shape), axis, N, k, name)
         plan = self._plans.get(key) if cache else None
         if plan is None:
             if table is not None:
@@ -264,7 +296,7 @@ class OrthogonalSpace:
         if k == 0:
             return c
         n = c.shape[axis]
-        return self._run(L.OP_APPLY, c, axis, k=k, table=self.derivative_matrix(k, n))
+        return self._run(L.OP_APPLY, c, axis, k=k, table=self.derivative_matrix(k, n), name=("D", k, n))
 
     def evaluate(self, x, c, axis: int = -1):
         """sum_k c_k psi_k(x) at arbitrary true-domain points x (orthogonal.py:102-115)."""

@@ -121,8 +121,27 @@ class TensorProductSpace:
         u, _ = as_jfx_array(u, self.complex_data)
         return self._plan(L.OP_FORWARD, u)(u)
 
+    def _metric(self, like):
+        """sqrt(det g) sampled on the quadrature mesh, as an array like `like` (None for Cartesian systems)."""
+        from .orthogonal import metric_weight
+        if self.system is None:
+            return None
+        key = ("sg", getattr(like, "device", "host"), str(like.dtype))
+        if key not in self._plans:
+            sg = metric_weight(self.system, self.mesh())
+            if sg is not None and not np.isscalar(sg):
+                sg = np.ascontiguousarray(np.broadcast_to(sg, self.shape))
+                if not isinstance(like, np.ndarray):
+                    import torch
+                    sg = torch.from_numpy(sg).to(device=like.device, dtype=like.dtype)
+            self._plans[key] = sg
+        return self._plans[key]
+
     def scalar_product(self, u):
         u, _ = as_jfx_array(u, self.complex_data)
+        sg = self._metric(u)                     # tensorproductspace.py:376-379: u * sg before the separable products
+        if sg is not None:
+            u = u * sg
         return self._plan(L.OP_SCALAR_PRODUCT, u)(u)
 
     def backward_primitive(self, c, k, N=None):
@@ -140,6 +159,58 @@ class TensorProductSpace:
             axis = ax - len(self)
             c = space.evaluate_mesh(c, kind, None if N is None else N[ax], axis=axis)
         return c
+
+    def evaluate(self, x, c, group=None):
+        """Expansion evaluated at scattered points (tensorproductspace.py:263-321): x is [n_pts, d] in true coordinates,
+        result [n_pts] = einsum("pi,pj(,pk),ij(k)->p", C_0, C_1, (C_2), c) with C_ax = basis values of axis ax at the points.
+
+        The last axis is a table pass of the engine ([.., N_last] -> [.., n_pts]); every other axis is reduced by
+        `jfx_point_contract` with its per-point basis values.  With `group` (torch.distributed) the coefficient block `c` is
+        this rank's slab of a spectral array sharded along axis 0; the partial sums are all-reduced (the `psum` of :300-304)."""
+        offset = 0
+        if group is not None:                                   # this rank's modes of axis 0
+            import torch.distributed as dist
+            offset = dist.get_rank(group) * c.shape[0]
+        y = self._evaluate_partial(x, c, offset)
+        if group is not None:
+            dist.all_reduce(y, group=group)
+        return y
+
+    def _evaluate_partial(self, x, c, mode_offset: int = 0):
+        """Contribution of the coefficient block c = C[mode_offset : mode_offset + c.shape[0]] (axis 0) to evaluate(x, C)."""
+        import ctypes as C
+        import torch
+        from ..engine import current_stream_ptr
+        d = len(self)
+        x = np.atleast_2d(np.asarray(x, dtype=float))
+        assert x.shape[1] == d, f"points must be [n_pts, {d}]"
+        c, is_host = as_jfx_array(c, self.complex_data)
+        if is_host:
+            raise L.JfxError(-3, "evaluate needs a CUDA tensor; jaxfun_b200 has no CPU fallback")
+        npts = x.shape[0]
+        Cs = []
+        for ax, space in enumerate(self.basespaces):
+            X = np.asarray(space.map_reference_domain(x[:, ax]), dtype=float)
+            Cs.append(np.asarray(space.eval_basis_functions(X)))          # the Vandermonde, as the reference (:267-270)
+        Cs[0] = Cs[0][:, mode_offset:]
+        for ax in range(d):
+            assert c.shape[ax] <= Cs[ax].shape[1], f"axis {ax}: {c.shape[ax]} coefficients exceed N"
+            Cs[ax] = np.ascontiguousarray(Cs[ax][:, :c.shape[ax]])
+        # last axis: [.., N_last] x C_last^T -> [.., n_pts]
+        y = self.basespaces[-1]._run(L.OP_APPLY, c, -1, table=Cs[-1], cache=False)
+        lib = L.load()
+        dtype = jfx_dtype(y.dtype)
+        wdt = torch.float64 if dtype in (L.F64, L.C128) else torch.float32
+        for ax in range(d - 2, -1, -1):
+            w = Cs[ax]
+            wc = bool(np.iscomplexobj(w))                      # Fourier axis: complex basis values, complex data
+            wt = torch.from_numpy(w).to(device=y.device, dtype=(y.dtype if wc else wdt)).contiguous()
+            outer = int(np.prod(y.shape[:ax], dtype=np.int64))
+            out = torch.empty(tuple(y.shape[:ax]) + (npts,), dtype=y.dtype, device=y.device)
+            L.check(lib.jfx_point_contract(C.c_void_p(current_stream_ptr()), C.c_void_p(y.data_ptr()), C.c_void_p(wt.data_ptr()),
+                                           C.c_void_p(out.data_ptr()), outer, int(y.shape[ax]), npts, dtype, int(wc)))
+            y = out
+        return y
 
     def to_orthogonal(self, c):
         for ax, space in enumerate(self.basespaces):
@@ -305,4 +376,7 @@ def TensorProduct(*basespaces: OrthogonalSpace, system=None, name: str = "T") ->
             spaces.append(copy.deepcopy(s))
         finally:
             s._plans = plans
+    if system is not None:
+        for s in spaces:
+            s.system = None       # a factor sees the 1-D sub-system, whose sg is 1 (coordinates.py:1254); the product applies sg
     return TensorProductSpace(spaces, system, name)

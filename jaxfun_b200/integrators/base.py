@@ -35,12 +35,22 @@ def axpby_diag(terms, out=None):
     x_arr = (C.c_void_p * n_terms)()
     alpha = (C.c_double * n_terms)()
     ccomplex = any(c is not None and c.is_complex() for _, c, _ in terms)
+    if ccomplex and not x0.is_complex():
+        raise TypeError("complex diagonal coefficients need a complex state array")
+    # the kernel reads every coefficient array in ONE element type: the state's complex type when any coefficient is complex,
+    # else the real type of the state's precision (ETDRK4 / IMEX coefficients arrive as float64 / complex128 from numpy: a
+    # complex64 / float32 state must not have them read as if they were single precision)
+    real_dt = {torch.float32: torch.float32, torch.float64: torch.float64,
+               torch.complex64: torch.float32, torch.complex128: torch.float64}[x0.dtype]
+    want = x0.dtype if ccomplex else real_dt
     keep = []
     for i, (a, c, x) in enumerate(terms):
         assert x.shape == x0.shape and x.dtype == x0.dtype and x.is_contiguous()
         if c is not None:
-            if ccomplex and not c.is_complex():
-                c = c.to(x0.dtype)
+            if c.is_complex() and not ccomplex:
+                raise TypeError("mixed real / complex coefficient handling failed")   # unreachable: ccomplex covers it
+            if c.dtype != want:
+                c = c.to(want)
             c = c.contiguous()
             assert c.shape == x0.shape
             keep.append(c)
@@ -60,11 +70,31 @@ class BaseIntegrator:
         self.forcing = forcing
         self.has_nonlinear = nonlinear is not None
 
-    # base.py:230-236
+    # base.py:230-236: N (padded physical resolution) is forwarded to the evaluator; None = the test space's own shape
     def nonlinear_rhs(self, uh, N=None):
         if not self.has_nonlinear:
             return torch.zeros_like(uh)
-        return self.nonlinear(uh)
+        return self._nonlinear_for(N)(uh)
+
+    # base.py:238-248
+    def nonlinear_rhs_scalar_product(self, uh, N=None):
+        if not self.has_nonlinear:
+            return torch.zeros_like(uh)
+        return self._nonlinear_for(N, final="scalar_product")(uh)
+
+    def _nonlinear_for(self, N=None, final=None):
+        """The NonlinearTerm evaluated at physical resolution N (None: the term's own) with the requested final transform."""
+        term = self.nonlinear
+        if N is None and final is None:
+            return term
+        if not hasattr(term, "with_resolution"):
+            return term
+        key = (None if N is None else (tuple(N) if isinstance(N, (tuple, list)) else int(N)), final)
+        cache = self.__dict__.setdefault("_nl_variants", {})
+        t = cache.get(key)
+        if t is None:
+            t = cache[key] = term.with_resolution(N, final)
+        return t
 
     # base.py:250-255
     def linear_rhs(self, uh):
@@ -77,7 +107,7 @@ class BaseIntegrator:
     def total_rhs(self, uh, N=None):
         if not self.has_nonlinear:
             return self.linear_rhs(uh)
-        terms = [(1.0, self.Ldiag, uh), (1.0, None, self.nonlinear(uh))]
+        terms = [(1.0, self.Ldiag, uh), (1.0, None, self.nonlinear_rhs(uh, N))]
         if self.forcing is not None:
             terms.append((1.0, None, self.forcing))
         return axpby_diag(terms)

@@ -49,7 +49,9 @@ class _WeakFormMixin:
     def nonlinear_rhs_scalar_product(self, uh, N=None):
         if self._nl_sp is None:
             return torch.zeros_like(uh)
-        return self._nl_sp(uh)
+        if N is None:
+            return self._nl_sp(uh)
+        return self._nonlinear_for(N, final="scalar_product")(uh)      # base.py:238-248: N forwarded to the evaluator
 
 
 class BackwardEuler(_WeakFormMixin, BaseIntegrator):

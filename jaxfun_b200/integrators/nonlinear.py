@@ -159,6 +159,14 @@ class NonlinearTerm:
         c = self._ctor
         return NonlinearTerm(self.space, c["expr"], final=final, N=c["N"], testspace=c["testspace"], u=c["u"], coords=c["coords"])
 
+    def with_resolution(self, N=None, final=None) -> "NonlinearTerm":
+        """The same term evaluated at physical resolution N (None: keep this term's) and / or with another final transform —
+        what `BaseIntegrator.nonlinear_rhs(uh, N)` forwards to the evaluator (base.py:230-248)."""
+        c = self._ctor
+        fin = final if final is not None else ("forward" if self.final == L.OP_FORWARD else "scalar_product")
+        return NonlinearTerm(self.space, c["expr"], final=fin, N=(c["N"] if N is None else N), testspace=c["testspace"],
+                             u=c["u"], coords=c["coords"])
+
     def _spaces(self, space):
         return list(space.basespaces) if hasattr(space, "basespaces") else [space]
 

@@ -66,10 +66,13 @@ class SlabBackend:
         """[parts, .., L/parts, ..] -> [.., L, ..] contiguous."""
         raise NotImplementedError
 
+    #: process group of the exchange (None = the default group); set by SlabTensorProduct
+    group = None
+
     def all_to_all(self, send):
         """Tiled all-to-all of the leading `parts` dimension; same shape out."""
         out = torch.empty_like(send)
-        dist.all_to_all_single(out, send)
+        dist.all_to_all_single(out, send, group=self.group)
         return out
 
     def all_to_all_async(self, send):
@@ -77,7 +80,7 @@ class SlabBackend:
         exchange (NCCL runs it on its own stream, so kernels issued in between overlap it); `send` must stay
         referenced until then."""
         out = torch.empty_like(send)
-        work = dist.all_to_all_single(out, send, async_op=True)
+        work = dist.all_to_all_single(out, send, async_op=True, group=self.group)
         return out, work
 
 
@@ -255,18 +258,18 @@ class EngineSlabBackend(SlabBackend):
             bufs, hdls = [], []
             if hasattr(symm_mem, "enable_symm_mem_for_group"):      # needed by older torch releases, a no-op in newer ones
                 try:
-                    symm_mem.enable_symm_mem_for_group(dist.group.WORLD.group_name)
+                    symm_mem.enable_symm_mem_for_group((self.group or dist.group.WORLD).group_name)
                 except Exception:
                     pass
             for _ in range(2):
                 b = symm_mem.empty(recv_shape, dtype=torch.float64, device=x.device)
-                hdls.append(symm_mem.rendezvous(b, dist.group.WORLD.group_name))
+                hdls.append(symm_mem.rendezvous(b, (self.group or dist.group.WORLD).group_name))
                 bufs.append(b)
             ent = self._plans[key] = {"bufs": bufs, "hdls": hdls, "turn": 0}
         t = ent["turn"]
         ent["turn"] = t ^ 1
         hdl, buf = ent["hdls"][t], ent["bufs"][t]
-        plan.execute_scatter(x, [int(p) for p in hdl.buffer_ptrs], dist.get_rank(), split_axis)
+        plan.execute_scatter(x, [int(p) for p in hdl.buffer_ptrs], dist.get_rank(self.group), split_axis)
         hdl.barrier(channel=t)
         return buf
 
@@ -280,7 +283,7 @@ class EngineSlabBackend(SlabBackend):
         plan = self._plan_for(x, [1, 2])
         if not plan.scatter_supported(world_size, 1):
             return None
-        rank = dist.get_rank() if rank is None else rank
+        rank = dist.get_rank(self.group) if rank is None else rank
         s0, s1, s2 = plan.shape_out
         send = torch.empty((world_size, s0, s1 // world_size, s2), dtype=x.dtype, device=x.device)
         block = s0 * (s1 // world_size) * s2 * 8
@@ -328,10 +331,13 @@ class SlabTensorProduct:
         return dist.get_world_size(self.group) if dist is not None and dist.is_initialized() else 1
 
     def _backend(self, op, N=None, k=None):
+        N = None if N is None else tuple(N)
+        k = None if k is None else tuple(k)
         key = (op, N, k)
         b = self._backends.get(key)
         if b is None:
             b = self._backends[key] = EngineSlabBackend(self.space, op, N, k)
+            b.group = self.group
         return b
 
     def backward(self, c_local, N=None):

@@ -220,13 +220,24 @@ class OrthogonalSpace:
         df = float(self.domain_factor ** k)
         return df * self.backward(self.derivative_coeffs(c, k, axis), N=N, axis=axis)
 
-    # orthogonal.py:264-277 (Cartesian metric: sg == 1)
+    #: coordinate system: None = Cartesian (sg == 1); else an object with `.sg` (SymPy expression in the true coordinate)
+    #: and `.base_scalars()` (jaxfun.coordinates.CoordSys protocol)
+    system = None
+
+    # orthogonal.py:264-277
     def scalar_product(self, u, axis=-1):
         def f(um):
             N = um.shape[0]
             xj, wj = self.quad_points_and_weights(N)
             Pi = self.vandermonde(xj)
-            wj = wj * float(1 / self.domain_factor)
+            sg = (sp.Integer(1) if self.system is None else sp.sympify(self.system.sg)) / self.domain_factor   # :270
+            if sp.sympify(sg).is_number:
+                wj = wj * float(sg)
+            else:                                                                                            # :273-276
+                x = self.system.base_scalars()[0]
+                a, c, d = float(self.domain[0]), float(self.reference_domain[0]), self.domain_factor
+                sgx = sp.lambdify(x, sg.xreplace({x: a + (x - c) / d}), modules="numpy")(np.asarray(xj))        # map_expr_true_domain
+                wj = wj * sgx
             return ((um.T * wj) @ np.conj(Pi)).T
         return _along(f, u, axis)
 
@@ -712,8 +723,9 @@ class Fourier(OrthogonalSpace):
 # tensor products  (galerkin/tensorproductspace.py:330-460, sharding.py:24-40)
 # =================================================================================================
 class TensorProductSpace:
-    def __init__(self, *spaces):
+    def __init__(self, *spaces, system=None):
         self.basespaces = list(spaces)
+        self.system = system        # tensorproductspace.py:38-60; the factors keep sub-systems with sg == 1 (coordinates.py:1254)
 
     def __len__(self):
         return len(self.basespaces)
@@ -736,6 +748,9 @@ class TensorProductSpace:
 
     def scalar_product(self, u):
         u = np.asarray(u)
+        if self.system is not None and sp.sympify(self.system.sg) != 1:      # tensorproductspace.py:376-379
+            sg = sp.lambdify(self.system.base_scalars(), self.system.sg, modules="numpy")(*self.mesh())
+            u = u * sg
         for ax, axis in enumerate(self._axes(u)):
             u = self.basespaces[ax].scalar_product(u, axis=axis)
         return u
@@ -745,6 +760,13 @@ class TensorProductSpace:
         for ax, axis in enumerate(self._axes(c)):
             c = self.basespaces[ax].backward_primitive(c, k=k[ax], N=None if N is None else N[ax], axis=axis)
         return c
+
+    # tensorproductspace.py:263-273: einsum("i,j,ij") / ("i,j,k,ijk") per point
+    def evaluate(self, x, c):
+        x = np.atleast_2d(np.asarray(x, dtype=float))
+        Cs = [s.eval_basis_functions(np.asarray(s.map_reference_domain(x[:, i])))[:, : c.shape[i]] for i, s in enumerate(self.basespaces)]
+        path = "pi,pj,ij->p" if len(self) == 2 else "pi,pj,pk,ijk->p"
+        return np.einsum(path, *Cs, c)
 
     def mesh(self, N=None):
         d = len(self)

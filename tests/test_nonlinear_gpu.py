@@ -259,3 +259,49 @@ def test_three_halves_rule_padding_is_row_fused(cuda, N, M):
     assert term.launches(dev(uh, cuda)) == 1
     ref = np.stack([O.nonlinear_rhs(Vo, [0, 1], lambda a, ax: -(a * ax), r, N=M) for r in uh])
     assert relerr(got, ref) < 1e-12
+
+
+def test_integrator_forwards_N_to_the_evaluator(cuda):
+    """`nonlinear_rhs(uh, N)` / `nonlinear_rhs_scalar_product(uh, N)` evaluate at the padded resolution N
+    (base.py:230-248, pinned by tests/integrators/test_backward_euler.py:207-243); N = None is the space's own shape."""
+    from jaxfun_b200.integrators.imex_rk import BackwardEuler
+    rng = np.random.default_rng(8)
+    N, M = 32, 48
+    V, Vo = jf.Fourier(N), O.Fourier(N)
+    u, (x,) = field(V)
+    term = NonlinearTerm(V, -u * u.diff(x))
+    uh = crand(rng, (N,), 0.1)
+    k = Vo.wavenumbers().astype(float)
+    Ld = dev(-(k**2) + 0j, cuda)
+    for integ in (RK4(V, linear_diag=Ld, nonlinear=term), ETDRK4(V, linear_diag=Ld, nonlinear=term)):
+        ref_pad = O.nonlinear_rhs(Vo, [0, 1], lambda a, ax: -(a * ax), uh, N=M)
+        ref = O.nonlinear_rhs(Vo, [0, 1], lambda a, ax: -(a * ax), uh)
+        assert relerr(integ.nonlinear_rhs(dev(uh, cuda), M), ref_pad) < 1e-12
+        assert relerr(integ.nonlinear_rhs(dev(uh, cuda)), ref) < 1e-12
+        assert np.abs(ref_pad - ref).max() > 1e-6 * np.abs(ref).max()      # padding really changes the (aliased) result
+        tot = integ.total_rhs(dev(uh, cuda), M).cpu().numpy()
+        assert np.abs(tot - (ref_pad + (-(k**2)) * uh)).max() < 1e-12 * np.abs(tot).max()
+    be = BackwardEuler(V, linear_diag=Ld, nonlinear=term)
+    be.setup(1e-3)
+    ref_sp = O.nonlinear_rhs(Vo, [0, 1], lambda a, ax: -(a * ax), uh, N=M, final="scalar_product")
+    assert relerr(be.nonlinear_rhs_scalar_product(dev(uh, cuda), M), ref_sp) < 1e-12
+
+
+def test_stage_arithmetic_in_single_precision_casts_its_coefficients(cuda):
+    """ETDRK4 coefficients are built in float64 / complex128; a complex64 state must see them as complex64
+    (jfx_axpby_diag reads coefficients in the state's precision)."""
+    from jaxfun_b200.integrators.base import axpby_diag
+    rng = np.random.default_rng(9)
+    n = 1000
+    x = crand(rng, (n,)).astype(np.complex64)
+    y = crand(rng, (n,)).astype(np.complex64)
+    cz = crand(rng, (n,))                               # complex128 coefficient
+    cr = rng.standard_normal(n)                         # float64 coefficient
+    got = axpby_diag([(0.5, dev(cz, cuda), dev(x, cuda)), (2.0, dev(cr, cuda), dev(y, cuda))]).cpu().numpy()
+    ref = 0.5 * cz * x + 2.0 * cr * y
+    assert got.dtype == np.complex64 and np.abs(got - ref).max() < 1e-5 * np.abs(ref).max()
+    xr, yr = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    got = axpby_diag([(1.0, dev(cr, cuda), dev(xr, cuda)), (-1.0, None, dev(yr, cuda))]).cpu().numpy()
+    assert np.abs(got - (cr * xr - yr)).max() < 1e-5
+    with pytest.raises(TypeError):
+        axpby_diag([(1.0, dev(cz, cuda), dev(xr, cuda))])

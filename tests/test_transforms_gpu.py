@@ -233,3 +233,30 @@ def test_many_batches_on_a_middle_axis(cuda):
     ref = o.backward(c[::7000], axis=1)
     assert relerr(u[::7000], ref) < TOL64
     assert relerr(p.forward(u, axis=1), c) < 1e-11
+
+
+def test_tensor_product_evaluate_at_scattered_points(cuda):
+    """TensorProductSpace.evaluate (tensorproductspace.py:263-321): einsum over per-point basis values; incl. a Fourier
+    factor (complex basis values on a non-last axis), mapped domains, and the slab variant's partial sums (`psum`, :296-304)."""
+    import jaxfun_oracle as O
+    rng = np.random.default_rng(21)
+    cases = [((jf.Legendre(20, domain=(0, 2)), jf.Chebyshev(24)), (O.Legendre(20, domain=(0, 2)), O.Chebyshev(24)), False),
+             ((jf.Fourier(16), jf.Legendre(18)), (O.Fourier(16), O.Legendre(18)), True),
+             ((jf.Legendre(10), jf.Chebyshev(12), jf.Legendre(14, domain=(-2, 0))),
+              (O.Legendre(10), O.Chebyshev(12), O.Legendre(14, domain=(-2, 0))), False),
+             ((jf.Fourier(8), jf.Fourier(12), jf.Chebyshev(16)), (O.Fourier(8), O.Fourier(12), O.Chebyshev(16)), True)]
+    for sp, so, cplx in cases:
+        T, To = jf.TensorProduct(*sp), O.TensorProductSpace(*so)
+        shape = tuple(s.N for s in so)
+        c = rng.standard_normal(shape) + (1j * rng.standard_normal(shape) if cplx else 0)
+        pts = np.stack([rng.uniform(float(s.domain[0]), float(s.domain[1]), 37) for s in so], axis=1)
+        ref = To.evaluate(pts, c)
+        got = T.evaluate(pts, torch.from_numpy(c).to(cuda)).cpu().numpy()
+        assert got.shape == (37,)
+        assert np.abs(got - ref).max() < 1e-12 * np.abs(ref).max(), (shape, np.abs(got - ref).max())
+        # two emulated ranks: spectral slabs along axis 0, partial sums add up to the full evaluation
+        if shape[0] % 2 == 0:
+            h = shape[0] // 2
+            cd = torch.from_numpy(c).to(cuda)
+            part = T._evaluate_partial(pts, cd[:h].contiguous(), 0) + T._evaluate_partial(pts, cd[h:].contiguous(), h)
+            assert np.abs(part.cpu().numpy() - ref).max() < 1e-12 * np.abs(ref).max()
