@@ -19,7 +19,7 @@ def numpy_engine(monkeypatch):
     from jaxfun_b200.galerkin import tensorproductspace as TP
     from jaxfun_b200.galerkin.orthogonal import OrthogonalSpace
 
-    def run(self, op, x, axis, N=None, k=0, table=None, cache=True):
+    def run(self, op, x, axis, N=None, k=0, table=None, cache=True, name=None):
         x = np.asarray(x)
         axis = axis % x.ndim
         if table is None:
