@@ -208,13 +208,13 @@ def run_reference(args):
 
 def _slab_env():
     """The exchange switches of jaxfun_b200/sharding.py, read from the environment (the reference arm must not import the product)."""
-    def flag(name):
-        return os.environ.get(name, "0") == "1"
+    def flag(name, default="0"):
+        return os.environ.get(name, default) != "0"
     try:
         chunks = max(1, int(os.environ.get("JFX_SLAB_CHUNKS", "1")))
     except ValueError:
         chunks = 1
-    return {"slab_chunks": chunks, "slab_p2p": flag("JFX_SLAB_P2P"), "slab_fused_pack": flag("JFX_SLAB_FUSED_PACK")}
+    return {"slab_chunks": chunks, "slab_p2p": flag("JFX_SLAB_P2P", "1"), "slab_fused_pack": flag("JFX_SLAB_FUSED_PACK")}
 
 
 def workload_config(n, gpus):
@@ -648,7 +648,12 @@ def run_ours(args):
         line["check"] = check
         # NVLink side of the exchange: each rank sends (P-1)/P of its block in each of the two transforms of a step
         sent = 2.0 * 8.0 * n**3 / world * (world - 1) / world
-        line["exchange"] = {"bytes_sent_per_rank_per_step": sent, "mode": _slab_env()}
+        p2p_used = any(isinstance(v, dict) and "hdls" in v for be in S._backends.values() for v in be._plans.values())
+        p2p_err = next((be.p2p_error for be in S._backends.values() if getattr(be, "p2p_error", None)), None)
+        line["exchange"] = {"bytes_sent_per_rank_per_step": sent, "mode": _slab_env(),
+                            "path": ("peer stores from the epilogue of the last local pass (symmetric memory over NVLink), no NCCL "
+                                     "collective on the data path") if p2p_used else "jfx_slab_pack + NCCL all_to_all_single (+ unpack)",
+                            "p2p_fallback_reason": p2p_err}
         if rank == 0:
             # same global problem on ONE GPU: the strong-scaling denominator, measured in this run
             try:

@@ -85,10 +85,12 @@ class SlabBackend:
 
 
 def slab_p2p() -> bool:
-    """JFX_SLAB_P2P=1: the last local pass of phase 1 stores straight into the peers' receive buffers (symmetric memory
-    over NVLink) instead of pack + NCCL all-to-all (+ unpack).  Opt-in: written without multi-GPU access."""
+    """The last local pass of phase 1 stores straight into the peers' receive buffers (symmetric memory over NVLink)
+    instead of pack + NCCL all-to-all (+ unpack).  Default since it ran on real GPUs (2 x B200, 512^3: 7.3 ms per
+    backward + forward against 9.6 ms with the NCCL exchange, results identical); JFX_SLAB_P2P=0 keeps the NCCL path, which
+    is also what runs when the plan has no scatter epilogue or symmetric memory cannot be set up."""
     import os
-    return os.environ.get("JFX_SLAB_P2P", "0") == "1"
+    return os.environ.get("JFX_SLAB_P2P", "1") != "0"
 
 
 def slab_fused_pack() -> bool:
@@ -254,7 +256,27 @@ class EngineSlabBackend(SlabBackend):
         recv_shape = (world_size * s0, s1 // world_size, s2) if split_axis == 1 else (s0 // world_size, world_size * s1, s2)
         key = ("p2p", tuple(x.shape), split_axis)
         ent = self._plans.get(key)
+        if ent is False:
+            return None                     # symmetric memory could not be set up for this shape: NCCL path
         if ent is None:
+            try:
+                ent = self._p2p_setup(symm_mem, recv_shape, x)
+            except Exception as e:          # e.g. a backend / driver without symmetric memory: keep the NCCL exchange
+                self.p2p_error = f"{type(e).__name__}: {e}"
+                self._plans[key] = False
+                return None
+            self._plans[key] = ent
+        t = ent["turn"]
+        ent["turn"] = t ^ 1
+        hdl, buf = ent["hdls"][t], ent["bufs"][t]
+        plan.execute_scatter(x, [int(p) for p in hdl.buffer_ptrs], dist.get_rank(self.group), split_axis)
+        hdl.barrier(channel=t)
+        return buf
+
+    p2p_error = None
+
+    def _p2p_setup(self, symm_mem, recv_shape, x):
+        if True:
             bufs, hdls = [], []
             if hasattr(symm_mem, "enable_symm_mem_for_group"):      # needed by older torch releases, a no-op in newer ones
                 try:
@@ -265,13 +287,7 @@ class EngineSlabBackend(SlabBackend):
                 b = symm_mem.empty(recv_shape, dtype=torch.float64, device=x.device)
                 hdls.append(symm_mem.rendezvous(b, (self.group or dist.group.WORLD).group_name))
                 bufs.append(b)
-            ent = self._plans[key] = {"bufs": bufs, "hdls": hdls, "turn": 0}
-        t = ent["turn"]
-        ent["turn"] = t ^ 1
-        hdl, buf = ent["hdls"][t], ent["bufs"][t]
-        plan.execute_scatter(x, [int(p) for p in hdl.buffer_ptrs], dist.get_rank(self.group), split_axis)
-        hdl.barrier(channel=t)
-        return buf
+            return {"bufs": bufs, "hdls": hdls, "turn": 0}
 
     def packed_phase1(self, x, world_size: int, rank: int | None = None):
         """Phase 1 of spectral -> physical with the pack fused into its last pass: returns the send buffer
