@@ -92,6 +92,7 @@ struct Args {
   int vec_ok;          // 16-byte aligned vector stores allowed
   // k-tiles: kts_main tiles of the folded problem, then kts_corr asymmetry-correction tiles covering k' >= kcorr0
   int kts_main, kts_corr, kcorr0;
+  int xwide;           // NN: the X tensor map splits the contiguous axis as (8, inner / 8): one box per X tile (inner % 8 == 0)
 };
 
 // parity argument of ktile() for k-tile kt: correction tiles pair every accumulator group with the opposite parity
@@ -159,25 +160,29 @@ JFX_HD void ktile(const double* S, const Frag& fr, int par_plus, double (&acc)[8
 #pragma unroll
   for (int kk = 0; kk < BK / 4; ++kk) {
     if constexpr (V == OUT_NN || V == IN_NN) {
-      // plus half (m-tiles 0..3) then minus half (m-tiles 4..7): 8 fragment registers live at a time
+      // the X fragments of both halves first (IN: u +- u' formed ONCE per k-step), then the plus half (m-tiles 0..3)
+      // and the minus half (m-tiles 4..7) of the table
+      double bp[4], bm[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if constexpr (V == OUT_NN) {
+          bp[j] = R1[fr.q[kk & 1] + j * 128 + kk * 32];
+          bm[j] = R2[fr.q[kk & 1] + j * 128 + kk * 32];
+        } else {
+          const double u = R1[fr.q[kk & 1] + j * 128 + kk * 32], v = R2[fr.q[2 + (kk & 1)] + j * 128 + (3 - kk) * 32];
+          bp[j] = u + v;
+          bm[j] = u - v;
+        }
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        double a[4], b[4];
+        double a[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = R0[fr.p[kk] + (h * 4 + i) * 128];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if constexpr (V == OUT_NN) {
-            b[j] = (h ? R2 : R1)[fr.q[kk & 1] + j * 128 + kk * 32];
-          } else {
-            const double u = R1[fr.q[kk & 1] + j * 128 + kk * 32], v = R2[fr.q[2 + (kk & 1)] + j * 128 + (3 - kk) * 32];
-            b[j] = h ? u - v : u + v;
-          }
-        }
-#pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) mma(acc[h * 4 + i][j][0], acc[h * 4 + i][j][1], a[i], b[j]);
+          for (int j = 0; j < 4; ++j) mma(acc[h * 4 + i][j][0], acc[h * 4 + i][j][1], a[i], h ? bm[j] : bp[j]);
       }
     } else {
       double b[4];
@@ -467,9 +472,10 @@ JFX_HD void epilogue_scatter(const Args& q, const Scatter& sc, int tile_m, int t
 }
 
 // ------------------------------------------------------------------------------------------------
-// TMA copies of one pipeline stage.  issue(map, dst_offset_in_doubles, rank, c0, c1, c2, c3); map 0 = "A" tensor map
+// TMA copies of one pipeline stage.  issue(map, dst_offset_in_doubles, rank, c0, ..., c4); map 0 = "A" tensor map
 // (K-contiguous operand of the GEMM), 1 = "B" tensor map.  kt = k-tile of the folded problem.
 // ------------------------------------------------------------------------------------------------
+// issue(map, dst_offset_in_doubles, rank, c0, c1, c2, c3, c4)
 template <int V, class ISSUE>
 JFX_HD void stage_copies(const Args& q, int kt, int tile_m, int tile_n, int z, ISSUE&& issue) {
   const int m0 = tile_m * BM, n0 = tile_n * BN, k0 = kt * BK;
@@ -479,27 +485,39 @@ JFX_HD void stage_copies(const Args& q, int kt, int tile_m, int tile_n, int z, I
   const int kx = corr ? q.kcorr0 + (kt - q.kts_main) * BK : k0;
   if constexpr (V == OUT_NN) {
     const int pp = corr ? 1 - q.par_plus : q.par_plus;
-    issue(0, 0, 2, k0, m0, 0, 0);
+    issue(0, 0, 2, k0, m0, 0, 0, 0);
+    if (q.xwide) {
+      // dims (n_lo = 8, k', n_hi, parity, batch): one box = the 16 sub-tiles [16 k][8 n] of an X tile, in that order
+      issue(1, TILE, 5, 0, kx, n0 >> 3, pp, z);
+      issue(1, 2 * TILE, 5, 0, kx, n0 >> 3, 1 - pp, z);
+    } else {
 #pragma unroll
-    for (int sub = 0; sub < BN / 8; ++sub) {
-      issue(1, TILE + sub * 128, 4, n0 + 8 * sub, pp, kx, z);
-      issue(1, 2 * TILE + sub * 128, 4, n0 + 8 * sub, 1 - pp, kx, z);
+      for (int sub = 0; sub < BN / 8; ++sub) {
+        issue(1, TILE + sub * 128, 4, n0 + 8 * sub, pp, kx, z, 0);
+        issue(1, 2 * TILE + sub * 128, 4, n0 + 8 * sub, 1 - pp, kx, z, 0);
+      }
     }
   } else if constexpr (V == IN_NN) {
-    issue(0, 0, 2, k0, m0, 0, 0);
+    issue(0, 0, 2, k0, m0, 0, 0, 0);
+    if (q.xwide) {
+      // dims (n_lo = 8, k, n_hi, batch)
+      issue(1, TILE, 4, 0, k0, n0 >> 3, z, 0);
+      issue(1, 2 * TILE, 4, 0, q.n_fold - 16 - k0, n0 >> 3, z, 0);
+    } else {
 #pragma unroll
-    for (int sub = 0; sub < BN / 8; ++sub) {
-      issue(1, TILE + sub * 128, 3, n0 + 8 * sub, k0, z, 0);
-      issue(1, 2 * TILE + sub * 128, 3, n0 + 8 * sub, q.n_fold - 16 - k0, z, 0);
+      for (int sub = 0; sub < BN / 8; ++sub) {
+        issue(1, TILE + sub * 128, 3, n0 + 8 * sub, k0, z, 0, 0);
+        issue(1, 2 * TILE + sub * 128, 3, n0 + 8 * sub, q.n_fold - 16 - k0, z, 0, 0);
+      }
     }
   } else if constexpr (V == OUT_NT || V == CPLX_NT) {
-    issue(0, 0, 2, 2 * kx, m0, 0, 0);
-    issue(0, TILE, 2, 2 * kx + 16, m0, 0, 0);
-    issue(1, 2 * TILE, 2, k0, n0, 0, 0);
+    issue(0, 0, 2, 2 * kx, m0, 0, 0, 0);
+    issue(0, TILE, 2, 2 * kx + 16, m0, 0, 0, 0);
+    issue(1, 2 * TILE, 2, k0, n0, 0, 0, 0);
   } else {
-    issue(0, 0, 2, k0, m0, 0, 0);
-    issue(0, TILE, 2, q.n_fold - 16 - k0, m0, 0, 0);
-    issue(1, 2 * TILE, 2, k0, n0, 0, 0);
+    issue(0, 0, 2, k0, m0, 0, 0, 0);
+    issue(0, TILE, 2, q.n_fold - 16 - k0, m0, 0, 0, 0);
+    issue(1, 2 * TILE, 2, k0, n0, 0, 0, 0);
   }
 }
 
@@ -509,9 +527,9 @@ JFX_HD void stage_copies(const Args& q, int kt, int tile_m, int tile_n, int z, I
 struct MapDesc {
   const void* base;
   int rank;
-  unsigned long long dims[4];
-  unsigned long long strides_bytes[3];   // strides of dims 1..rank-1
-  unsigned box[4];
+  unsigned long long dims[5];
+  unsigned long long strides_bytes[4];   // strides of dims 1..rank-1
+  unsigned box[5];
   int swizzle_bytes;                     // 64 or 128
 };
 
@@ -696,14 +714,26 @@ inline bool make_launch(const FoldedTable& f, bool nn, long long outer, long lon
     a.vec_ok = al16(C) ? 1 : 0;                     // inner even -> every row / batch offset is even
     *mA = MapDesc{table, 2, {tcols, (unsigned long long)f.rows_nn, 1, 1},
                   {(unsigned long long)f.ld * 8, 0, 0}, {BK, BM, 1, 1}, 128};
+    // Wide X map (inner % 8 == 0): the contiguous axis is split as (n_lo = 8, n_hi = inner / 8) and the box order is
+    // (n_lo, k, n_hi), so ONE box copy lands as the 16 sub-tiles [16 k][8 n] the fragment loads expect — 3 copies per
+    // stage instead of 33.  Otherwise one box per sub-tile (the k tail / n tail are zero-filled by the TMA unit either way).
+    a.xwide = (inner % 8 == 0) ? 1 : 0;
+    const unsigned long long I = (unsigned long long)inner;
     if (out) {
-      // X_o[k][n] with k = 2 kk + parity: dims (n, parity, kk, batch)
-      *mB = MapDesc{X, 4, {(unsigned long long)inner, 2, (unsigned long long)(n_in / 2), (unsigned long long)outer},
-                    {(unsigned long long)inner * 8, (unsigned long long)inner * 16, (unsigned long long)n_in * inner * 8},
-                    {8, 1, BK, 1}, 64};
+      // X_o[k][n] with k = 2 kk + parity
+      if (a.xwide)
+        *mB = MapDesc{X, 5, {8, (unsigned long long)(n_in / 2), I / 8, 2, (unsigned long long)outer},
+                      {I * 16, 64, I * 8, (unsigned long long)n_in * I * 8}, {8, BK, BN / 8, 1, 1}, 64};
+      else   // dims (n, parity, kk, batch)
+        *mB = MapDesc{X, 4, {I, 2, (unsigned long long)(n_in / 2), (unsigned long long)outer, 1},
+                      {I * 8, I * 16, (unsigned long long)n_in * I * 8, 0}, {8, 1, BK, 1, 1}, 64};
     } else {
-      *mB = MapDesc{X, 3, {(unsigned long long)inner, (unsigned long long)n_in, (unsigned long long)outer, 1},
-                    {(unsigned long long)inner * 8, (unsigned long long)n_in * inner * 8, 0}, {8, BK, 1, 1}, 64};
+      if (a.xwide)
+        *mB = MapDesc{X, 4, {8, (unsigned long long)n_in, I / 8, (unsigned long long)outer, 1},
+                      {I * 8, 64, (unsigned long long)n_in * I * 8, 0}, {8, BK, BN / 8, 1, 1}, 64};
+      else
+        *mB = MapDesc{X, 3, {I, (unsigned long long)n_in, (unsigned long long)outer, 1, 1},
+                      {I * 8, (unsigned long long)n_in * I * 8, 0, 0}, {8, BK, 1, 1, 1}, 64};
     }
   } else {
     a.M = (int)outer; a.N = f.rows_nt;

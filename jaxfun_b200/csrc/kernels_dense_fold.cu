@@ -19,23 +19,14 @@ namespace jfx {
 namespace dmma {
 namespace fold {
 
-// 8 MMA warps + ONE producer warp (lane 0 works) = 288 threads.  The hardware allocates registers for the CTA rounded up
-// to 12 warps, so every thread gets 65536 / 384 -> 168 registers; with the per-lane fragment bases of frag_init() the MMA
-// code fits (a dozen local-memory accesses per k-tile in the IN variants, none in OUT_NT).
-// Round 1 gave the MMA warps 232 registers with setmaxnreg (producer warpgroup .dec 40, MMA warpgroups .inc 232).  That
-// version produced WRONG RESULTS on the B200 whenever the first TMA loads of a launch were slow (row stride >= 2 MiB, e.g.
-// the first axis of a 512^3 forward): in the first tile of some CTAs the warps of warpgroup 0 accumulated garbage in the
-// second half of their k-tile code.  Found by tests/test_at_size_gpu.py, reproduced by tools/diag_in_nn.py, gone without
-// the register hand-over; JFX_FOLD_SETMAXNREG=1 at compile time restores the old scheme for experiments.
-#ifndef JFX_FOLD_SETMAXNREG
-#define JFX_FOLD_SETMAXNREG 0
-#endif
-#if JFX_FOLD_SETMAXNREG
-constexpr int THREADS = MMA_WARPS * 32 + 128;
-constexpr int REGS_PRODUCER = 40, REGS_MMA = 232;
-#else
-constexpr int THREADS = MMA_WARPS * 32 + 32;
-#endif
+// 8 MMA warps = 256 threads, up to 255 registers each: no separate producer warp and no register hand-over.  Lane 0 of
+// warp 0 issues the TMA copies of k-tile it + AHEAD between its own k-tiles (three box copies per stage — the wide X tensor
+// map of dmma_fold.cuh — so the detour costs a few dozen instructions).
+// History: round 1 had a producer warpgroup + setmaxnreg (232 registers for the MMA warps); a ninth producer warp without
+// setmaxnreg caps every thread at 168 registers (the hardware allocates for 12 warps), which the IN variants do not fit.
+constexpr int THREADS = MMA_WARPS * 32;
+constexpr int AHEAD = STAGES - 2;      // k-tiles in flight ahead of the compute cursor (the stage refilled at iteration it was
+                                       // released by every warp at iteration it - 1: one k-tile of slack for the slowest warp)
 #define JFX_FOLD_BOUNDS __launch_bounds__(THREADS, 1)
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8;
 constexpr unsigned SPIN_LIMIT = 1u << 27;
@@ -73,6 +64,10 @@ __device__ __forceinline__ void tma_3d(unsigned dst, const CUtensorMap* tm, int 
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_5d(unsigned dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+               ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma_4d(unsigned dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned bar) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
@@ -93,8 +88,9 @@ struct GlobalStore {
   __device__ __forceinline__ void s1(long long idx, double v) const { C[idx] = v; }
 };
 
-// The whole CTA: pipeline set-up, producer warpgroup, MMA warps.  epi(tile_m, tile_n, z, wm, wn, g, t, acc) stores one warp's
-// share of a finished tile (plain epilogue into this GPU's array, or the scatter epilogue into the peers' receive buffers).
+// The whole CTA: pipeline set-up and the eight MMA warps (warp 0 also feeds the pipeline).  epi(tile_m, tile_n, z, wm, wn, g,
+// t, acc) stores one warp's share of a finished tile (plain epilogue into this GPU's array, or the scatter epilogue into the
+// peers' receive buffers).
 template <int V, class EPI>
 __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& q, EPI&& epi) {
   extern __shared__ unsigned char smem_raw[];
@@ -113,42 +109,49 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
 
   const int kts = ktiles(q);
   const unsigned total_tiles = (unsigned)q.tiles_n * (unsigned)q.tiles_m * (unsigned)q.batch;   // < 2^31: checked by the host
+  const unsigned my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+  const unsigned total_its = my_tiles * (unsigned)kts;
 
-  if (warp >= MMA_WARPS) {
-    // ================================ producer warpgroup ================================
-#if JFX_FOLD_SETMAXNREG
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
-#endif
-    if (warp != MMA_WARPS || lane != 0) return;
-    unsigned it = 0;
-    for (unsigned tl = blockIdx.x; tl < total_tiles; tl += gridDim.x) {
-      const unsigned r = tl / (unsigned)q.tiles_n;
-      const int tn = (int)(tl - r * (unsigned)q.tiles_n);
-      const int z = (int)(r / (unsigned)q.tiles_m);
-      const int tm = (int)(r - (unsigned)z * (unsigned)q.tiles_m);
-      for (int kt = 0; kt < kts; ++kt, ++it) {
-        const int s = (int)(it % STAGES);
-        const unsigned ph = (it / STAGES) & 1u;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        const unsigned full = bar_full + 8 * s;
-        mbar_expect_tx(full, STAGE_BYTES);
-        const unsigned dst0 = base + s * STAGE_BYTES;
-        stage_copies<V>(q, kt, tm, tn, z, [&](int map, int dst, int rank, int c0, int c1, int c2, int c3) {
-          const CUtensorMap* tmap = map == 0 ? &tmA : &tmB;
-          const unsigned d = dst0 + (unsigned)dst * 8u;
-          if (rank == 2) tma_2d(d, tmap, c0, c1, full);
-          else if (rank == 3) tma_3d(d, tmap, c0, c1, c2, full);
-          else tma_4d(d, tmap, c0, c1, c2, c3, full);
-        });
-      }
+  // ---- producer state (lane 0 of warp 0): cursor over the k-tiles of this CTA's tiles, AHEAD of the compute cursor ----
+  unsigned p_it = 0, p_tl = blockIdx.x;
+  int p_kt = 0, p_tm = 0, p_tn = 0, p_z = 0;
+  auto p_decode = [&]() {
+    const unsigned r = p_tl / (unsigned)q.tiles_n;
+    p_tn = (int)(p_tl - r * (unsigned)q.tiles_n);
+    p_z = (int)(r / (unsigned)q.tiles_m);
+    p_tm = (int)(r - (unsigned)p_z * (unsigned)q.tiles_m);
+  };
+  auto produce = [&]() {      // one k-tile: wait for the stage, announce the bytes, issue the box copies
+    if (p_it >= total_its) return;
+    const int s = (int)(p_it % STAGES);
+    const unsigned ph = (p_it / STAGES) & 1u;
+    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+    const unsigned full = bar_full + 8 * s;
+    mbar_expect_tx(full, STAGE_BYTES);
+    const unsigned dst0 = base + s * STAGE_BYTES;
+    stage_copies<V>(q, p_kt, p_tm, p_tn, p_z, [&](int map, int dst, int rank, int c0, int c1, int c2, int c3, int c4) {
+      const CUtensorMap* tmap = map == 0 ? &tmA : &tmB;
+      const unsigned d = dst0 + (unsigned)dst * 8u;
+      if (rank == 2) tma_2d(d, tmap, c0, c1, full);
+      else if (rank == 3) tma_3d(d, tmap, c0, c1, c2, full);
+      else if (rank == 4) tma_4d(d, tmap, c0, c1, c2, c3, full);
+      else tma_5d(d, tmap, c0, c1, c2, c3, c4, full);
+    });
+    ++p_it;
+    if (++p_kt == kts) {
+      p_kt = 0;
+      p_tl += gridDim.x;
+      if (p_it < total_its) p_decode();
     }
-    return;
+  };
+  const bool producer = tid == 0;
+  if (producer && my_tiles > 0) {
+    p_decode();
+#pragma unroll 1
+    for (int i = 0; i < AHEAD; ++i) produce();
   }
 
   // ================================ MMA warps ================================
-#if JFX_FOLD_SETMAXNREG
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_MMA));
-#endif
   const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   const int g = lane >> 2, t = lane & 3;
   const Frag fr = frag_init<V>(wm, wn, g, t);
@@ -167,16 +170,19 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
       mbar_wait(bar_full + 8 * s, ph);
       // Release of the PREVIOUS stage, here and not at the end of its k-tile.  ptxas schedules an arrive that follows the
       // k-tile directly behind the last fragment loads and ahead of the MMAs that consume them; the arrive then takes
-      // effect while those LDS are still queued, and when this warp is the last of the eight the producer's refill (the
-      // table tile comes from L2 in a few hundred ns) can overwrite the 1 KB atoms they address.  Seen on the B200 as
-      // wrong minus-half accumulators in ~1e-5 of the warp k-tiles whenever the producer was not far ahead, and gone
-      // with a slowed-down producer (tools/forensic.py).  After the spin loop of the next wait every MMA of the previous
-      // k-tile has issued, i.e. every fragment register has been written: the stage is really free.
+      // effect while those LDS are still queued, and when this warp is the last of the eight the refill (the table tile
+      // comes from L2 in a few hundred ns) can overwrite the 1 KB atoms they address.  Seen on the B200 as wrong minus-half
+      // accumulators in ~1e-5 of the warp k-tiles whenever the producer was not far ahead, and gone with a slowed-down
+      // producer (tools/forensic.py).  After the spin loop of the next wait every MMA of the previous k-tile has issued,
+      // i.e. every fragment register has been written: the stage is really free.
       if (prev >= 0) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * prev);
       }
       prev = s;
+      // k-tile it + AHEAD goes into the stage that every warp released one iteration ago
+      if (producer) produce();
+      __syncwarp();
       const double* S = reinterpret_cast<const double*>(gbase + (size_t)s * STAGE_BYTES);
       ktile<V>(S, fr, ktile_par(q, kt), acc, MmaOp{});
     }
@@ -230,9 +236,9 @@ static EncodeFn encode_fn() {
 static bool encode(CUtensorMap* tm, const MapDesc& m) {
   EncodeFn fn = encode_fn();
   if (!fn) return false;
-  cuuint64_t dims[4], strides[3];
-  cuuint32_t box[4];
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5];
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   for (int d = 0; d < m.rank; ++d) { dims[d] = m.dims[d]; box[d] = m.box[d]; }
   for (int d = 0; d + 1 < m.rank; ++d) strides[d] = m.strides_bytes[d];
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)m.rank, const_cast<void*>(m.base), dims, strides, box, estr,

@@ -20,30 +20,37 @@
 
 using namespace jfx::dmma::fold;
 
-static void tma_copy(const MapDesc& m, std::vector<double>& stage, int dst_off, int rank, const int c[4]) {
+static void tma_copy(const MapDesc& m, std::vector<double>& stage, int dst_off, int rank, const int c[5]) {
   assert(rank == m.rank);
   assert((dst_off * 8) % (m.swizzle_bytes == 128 ? 1024 : 512) == 0);
-  const unsigned b0n = m.box[0], b1n = m.box[1], b2n = rank > 2 ? m.box[2] : 1, b3n = rank > 3 ? m.box[3] : 1;
-  assert(b0n * 8 <= (unsigned)m.swizzle_bytes);   // inner box extent must fit the swizzle span
-  for (unsigned b3 = 0; b3 < b3n; ++b3)
-    for (unsigned b2 = 0; b2 < b2n; ++b2)
-      for (unsigned b1 = 0; b1 < b1n; ++b1)
-        for (unsigned b0 = 0; b0 < b0n; ++b0) {
-          const long long x[4] = {(long long)c[0] + b0, (long long)c[1] + b1, (long long)c[2] + b2, (long long)c[3] + b3};
-          bool inb = true;
-          for (int d = 0; d < rank; ++d) inb = inb && x[d] >= 0 && x[d] < (long long)m.dims[d];
-          double v = 0.0;
-          if (inb) {
-            long long off = x[0] * 8;
-            for (int d = 1; d < rank; ++d) off += x[d] * (long long)m.strides_bytes[d - 1];
-            memcpy(&v, (const char*)m.base + off, 8);
+  unsigned bn[5] = {1, 1, 1, 1, 1};
+  for (int d = 0; d < rank; ++d) bn[d] = m.box[d];
+  assert(bn[0] * 8 <= (unsigned)m.swizzle_bytes);   // inner box extent must fit the swizzle span
+  for (int d = 1; d < rank; ++d) assert(m.strides_bytes[d - 1] % 16 == 0);
+  for (unsigned b4 = 0; b4 < bn[4]; ++b4)
+    for (unsigned b3 = 0; b3 < bn[3]; ++b3)
+      for (unsigned b2 = 0; b2 < bn[2]; ++b2)
+        for (unsigned b1 = 0; b1 < bn[1]; ++b1)
+          for (unsigned b0 = 0; b0 < bn[0]; ++b0) {
+            const unsigned bb[5] = {b0, b1, b2, b3, b4};
+            long long x[5];
+            bool inb = true;
+            for (int d = 0; d < rank; ++d) {
+              x[d] = (long long)c[d] + bb[d];
+              inb = inb && x[d] >= 0 && x[d] < (long long)m.dims[d];
+            }
+            double v = 0.0;
+            if (inb) {
+              long long off = x[0] * 8;
+              for (int d = 1; d < rank; ++d) off += x[d] * (long long)m.strides_bytes[d - 1];
+              memcpy(&v, (const char*)m.base + off, 8);
+            }
+            const unsigned lin = (((b4 * bn[3] + b3) * bn[2] + b2) * bn[1] + b1) * bn[0] + b0;
+            unsigned addr = (unsigned)(dst_off + (int)lin) * 8u;
+            if (m.swizzle_bytes == 128) addr ^= ((addr >> 7) & 7u) << 4;
+            else addr ^= ((addr >> 7) & 3u) << 4;
+            stage[addr / 8] = v;
           }
-          const unsigned lin = ((b3 * b2n + b2) * b1n + b1) * b0n + b0;
-          unsigned addr = (unsigned)(dst_off + (int)lin) * 8u;
-          if (m.swizzle_bytes == 128) addr ^= ((addr >> 7) & 7u) << 4;
-          else addr ^= ((addr >> 7) & 3u) << 4;
-          stage[addr / 8] = v;
-        }
 }
 
 struct Rec { int slot; double a, b; };
@@ -78,8 +85,8 @@ static void run_tiles(const Args& q, const MapDesc& mA, const MapDesc& mB, std::
           // poison the stage so that a fragment read of a location no copy wrote is caught
           for (auto& v : stage) v = 1e300;
           unsigned bytes = 0;
-          stage_copies<V>(q, kt, tm, tn, z, [&](int map, int dst, int rank, int c0, int c1, int c2, int c3) {
-            const int c[4] = {c0, c1, c2, c3};
+          stage_copies<V>(q, kt, tm, tn, z, [&](int map, int dst, int rank, int c0, int c1, int c2, int c3, int c4) {
+            const int c[5] = {c0, c1, c2, c3, c4};
             const MapDesc& m = map == 0 ? mA : mB;
             tma_copy(m, stage, dst, rank, c);
             unsigned n = 8;
@@ -320,8 +327,8 @@ static void run_tiles_scatter(const Args& q, const Scatter& sc, const MapDesc& m
       memset(acc, 0, sizeof(acc));
       for (int kt = 0; kt < kts; ++kt) {
         for (auto& v : stage) v = 1e300;
-        stage_copies<V>(q, kt, tm, tn, 0, [&](int map, int dst, int rank, int c0, int c1, int c2, int c3) {
-          const int c[4] = {c0, c1, c2, c3};
+        stage_copies<V>(q, kt, tm, tn, 0, [&](int map, int dst, int rank, int c0, int c1, int c2, int c3, int c4) {
+          const int c[5] = {c0, c1, c2, c3, c4};
           tma_copy(map == 0 ? mA : mB, stage, dst, rank, c);
         });
         for (int w = 0; w < MMA_WARPS; ++w) {
@@ -489,9 +496,19 @@ int main(int argc, char** argv) {
     run_scatter_case(FOLD_IN, 2, P, 2 * P, 5, 32, 16, seed++);
     run_scatter_case(FOLD_IN, 2, P, P, 24, 66, 33, seed++);
   }
+  // inner extents that are multiples of 8: the wide X tensor map (one box per X tile), incl. ragged last column tiles
+  for (int pp = 0; pp < 2; ++pp) {
+    run_case(FOLD_OUT, pp, 64, 64, 2, 136, seed++);
+    run_case(FOLD_OUT, pp, 130, 128, 1, 264, seed++);
+    run_case(FOLD_OUT, pp, 34, 30, 3, 8, seed++);
+    run_case(FOLD_IN, pp, 96, 64, 1, 264, seed++);
+    run_case(FOLD_IN, pp, 66, 65, 2, 128, seed++);
+    run_case(FOLD_IN, pp, 16, 16, 3, 24, seed++);
+  }
   // asymmetric high modes: correction k-tiles (1 .. 3 tiles, ragged tails, both orders and parities)
   for (int pp = 0; pp < 2; ++pp) {
     run_corr_case(pp, 64, 64, 3, 5e-13, 2, 34, seed++);
+    run_corr_case(pp, 64, 64, 3, 5e-13, 2, 40, seed++);
     run_corr_case(pp, 64, 64, 3, 5e-13, 37, 1, seed++);
     run_corr_case(pp, 130, 128, 30, 5e-13, 1, 130, seed++);
     run_corr_case(pp, 130, 128, 30, 5e-13, 129, 1, seed++);

@@ -30,7 +30,7 @@ def test_synthetic_tables_all_variants(emu):
     r = subprocess.run([emu], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "FOLD EMU: ALL OK" in r.stdout
-    assert r.stdout.count("\nok  ") + r.stdout.startswith("ok  ") >= 178
+    assert r.stdout.count("\nok  ") + r.stdout.startswith("ok  ") >= 190
     assert r.stdout.count("variant 4 (complex last axis)") == 18
 
 
