@@ -255,8 +255,11 @@ class DirectSumTPS:
     def __init__(self, basespaces, system=None, name: str = "DSTPS") -> None:
         from .composite import DirectSum
         idx = [i for i, s in enumerate(basespaces) if isinstance(s, DirectSum)]
+        if len(idx) == 2 and len(basespaces) == 2:
+            self._init_two_directions(list(basespaces), system, name)
+            return
         if len(idx) != 1:
-            raise NotImplementedError("DirectSumTPS with two inhomogeneous directions is not part of this build")
+            raise NotImplementedError("DirectSumTPS: one inhomogeneous direction (2-D / 3-D) or two (2-D) are built")
         b, d = idx[0], len(basespaces)
         if d == 3 and b == 0:
             raise ValueError("DirectSum cannot be the first space in a 3D tensor product.")   # tensorproductspace.py:612-615
@@ -288,6 +291,79 @@ class DirectSumTPS:
             lift = np.real(lift)
         self.lift = np.ascontiguousarray(lift)
         self._cache: dict = {}
+
+    def _init_two_directions(self, basespaces, system, name) -> None:
+        """Both factors of a 2-D product carry inhomogeneous boundary values (tensorproductspace.py:620-668, 689-747): the
+        lift is the transfinite interpolant of the boundary data,
+
+            sum_b B^x_b(x) [hom. part of g_b](y) + sum_c [hom. part of h_c](x) B^y_c(y) + sum_bc C_bc B^x_b(x) B^y_c(y),
+
+        where "hom. part" is the projection onto the OTHER direction's composite space after removing that direction's own
+        lift of the corner values C_bc = (boundary functional c of y)(g_b) — the `projected_bcs` of the reference (Dirichlet:
+        the value at the corner, Neumann: the derivative / df^nd).  Boundary data must be numbers or SymPy expressions in the
+        coordinate of the other axis (x, y), as in the reference."""
+        import sympy as sp
+        Dx, Dy = basespaces
+        self.bc_axis, self.name, self.system = (0, 1), name, system
+        self.basespaces = list(basespaces)
+        self.hom = TensorProduct(Dx.a, Dy.a, system=system, name=name + "0")
+        self.orthogonal = TensorProduct(Dx.orthogonal, Dy.orthogonal, system=system, name=name + "o")
+        sym = {0: sp.Symbol("x", real=True), 1: sp.Symbol("y", real=True)}
+        from .composite import _BC_ORDER, ordered_bc_names
+
+        def as_expr(v, other):
+            e = sp.sympify(v)
+            extra = {str(f) for f in e.free_symbols} - {str(sym[other])}
+            assert not extra, f"boundary value {e} may only depend on {sym[other]}"
+            return e.xreplace({f: sym[other] for f in e.free_symbols})
+
+        def functional(D, side, kind, expr, var):
+            """Boundary functional (side, kind) of direction D applied to expr(var): value, or derivative / df^nd."""
+            a, b_ = (float(v) for v in D.a.domain)
+            z = a if side == "left" else b_
+            nd = _BC_ORDER[kind]
+            if kind not in ("D",) and kind[0] != "N":
+                raise NotImplementedError("two inhomogeneous directions: Dirichlet / Neumann conditions")
+            df = 2.0 / (b_ - a)
+            f = (expr.diff(var, nd) / df**nd if nd else expr).subs(var, z)
+            return complex(f) if sp.sympify(f).has(sp.I) else float(f)
+
+        Ds, names = {0: Dx, 1: Dy}, {ax: ordered_bc_names(Ds_.bcs) for ax, Ds_ in ((0, Dx), (1, Dy))}
+        data = {ax: [as_expr(v, 1 - ax) for v in Ds[ax].raw_vals] for ax in (0, 1)}
+        # corner values from the x-side data, as the reference (projected_bcs[0]): C[b][c] = functional_c^y (g_b)
+        C = np.array([[functional(Dy, sc, kc, g, sym[1]) for (sc, kc) in names[1]] for g in data[0]])
+        # consistency of the data at the corners: the y-side data must give the same numbers
+        C2 = np.array([[functional(Dx, sb, kb, h, sym[0]) for h in data[1]] for (sb, kb) in names[0]])
+        if not np.allclose(C, C2, rtol=1e-9, atol=1e-11):
+            raise ValueError(f"boundary data of the two directions disagree at the corners:\n{C}\nvs\n{C2}")
+        N0, N1 = Dx.N, Dy.N
+        rows = {}
+        for ax, D in Ds.items():
+            R = np.zeros((D.S_bc.shape[0], D.N))
+            R[:, :D.S_bc.shape[1]] = D.S_bc
+            rows[ax] = R                                          # lifting functions of direction ax in orthogonal coefficients
+        lift = np.einsum("bc,bi,cj->ij", C, rows[0], rows[1])      # corner block
+        for ax in (0, 1):
+            o = 1 - ax
+            Do = Ds[o]
+            orth_o, comp_o = Do.orthogonal, Do.a
+            xo = np.asarray(comp_o.mesh(), dtype=float)
+            Vo = np.asarray(orth_o.eval_basis_functions(np.asarray(orth_o.map_reference_domain(xo), dtype=float)))
+            Tf = np.asarray(comp_o._dense_table(L.OP_FORWARD, comp_o.dim, comp_o.num_quad_points, 0))
+            St = np.asarray(comp_o.S).T
+            for b, g in enumerate(data[ax]):
+                f = sp.lambdify(sym[o], g, modules="numpy")
+                samples = np.broadcast_to(np.asarray(f(xo), dtype=complex if g.has(sp.I) else float), xo.shape).copy()
+                corner = C[b] if ax == 0 else C[:, b]
+                samples = samples - Vo @ (corner @ rows[o])      # minus the other direction's lift of the corner values
+                orth_coeffs = St @ (Tf @ samples)                  # homogeneous part, in orthogonal coefficients
+                lift = lift + (np.outer(rows[0][b], orth_coeffs) if ax == 0 else np.outer(orth_coeffs, rows[1][b]))
+        if not self.orthogonal.complex_data and np.iscomplexobj(lift):
+            assert np.abs(lift.imag).max() < 1e-14 * max(1.0, np.abs(lift).max())
+            lift = lift.real
+        self.lift = np.ascontiguousarray(lift)
+        self.corner_values = C
+        self._cache = {}
 
     # ---- bookkeeping forwarded to the homogeneous product --------------------------------------------------------
     def __len__(self) -> int:

@@ -106,3 +106,51 @@ def test_unsupported_layouts_are_refused():
         jf.TensorProduct(D, D)                                    # two inhomogeneous directions
     with pytest.raises(ValueError):                               # tensorproductspace.py:612-615
         jf.TensorProduct(jf.FunctionSpace(8, jf.Legendre, {"left": {"D": 1.0}, "right": {"D": 0}}), jf.Fourier(8), jf.Fourier(8))
+
+
+@pytest.mark.parametrize("space", ["Legendre", "Chebyshev"])
+def test_two_inhomogeneous_directions(numpy_engine, space):
+    """Both directions carry boundary data (tensorproductspace.py:620-668, 689-747: corner-compatible projected boundary
+    conditions): the lift takes the prescribed Dirichlet / Neumann data on all four sides, a low-degree polynomial is
+    reproduced exactly, and free coefficients do not move the boundary values."""
+    import jaxfun_b200 as jf
+    x, y = sp.symbols("x y", real=True)
+    ue = (x**2 + 2 * x) * (y**3 - y) + 3 + x - 2 * y + sp.Rational(1, 2) * x * y + y**2 * x**3
+    domx, domy = (0.0, 2.0), (-1.0, 1.0)
+    bcx = {"left": {"D": ue.subs(x, domx[0])}, "right": {"N": ue.diff(x).subs(x, domx[1])}}          # physical-unit Neumann
+    bcy = {"left": {"D": ue.subs(y, domy[0])}, "right": {"D": ue.subs(y, domy[1])}}
+    Sp = getattr(jf, space)
+    N = 12
+    T = jf.TensorProduct(jf.FunctionSpace(N, Sp, bcx, domain=domx), jf.FunctionSpace(N, Sp, bcy, domain=domy))
+    assert type(T).__name__ == "DirectSumTPS" and T.num_dofs == (N - 2, N - 2)
+    To = T.orthogonal
+    # (1) the lift satisfies the four boundary conditions
+    ys = np.linspace(-1, 1, 7); xs = np.linspace(0, 2, 7)
+    Vx = lambda pts, k=0: np.asarray(To.basespaces[0].evaluate_basis_derivative(np.asarray(To.basespaces[0].map_reference_domain(pts)), k))
+    Vy = lambda pts, k=0: np.asarray(To.basespaces[1].evaluate_basis_derivative(np.asarray(To.basespaces[1].map_reference_domain(pts)), k))
+    f = sp.lambdify((x, y), ue, "numpy"); fx = sp.lambdify((x, y), ue.diff(x), "numpy")
+    left = Vx(np.array([0.0])) @ T.lift @ Vy(ys).T
+    assert np.abs(left[0] - f(0.0, ys)).max() < 1e-11
+    dfx = float(To.basespaces[0].domain_factor)
+    right = dfx * (Vx(np.array([2.0]), 1) @ T.lift @ Vy(ys).T)
+    assert np.abs(right[0] - fx(2.0, ys)).max() < 1e-10
+    for yb in (-1.0, 1.0):
+        row = Vx(xs) @ T.lift @ Vy(np.array([yb])).T
+        assert np.abs(row[:, 0] - f(xs, yb)).max() < 1e-11
+    # (2) exact reproduction of the polynomial
+    X, Y = T.mesh()
+    u = f(X, Y)
+    c = T.forward(u)
+    assert c.shape == (N - 2, N - 2)
+    assert rel(T.backward(c), u) < 1e-12
+    # (3) free coefficients keep the boundary values: evaluate the full expansion on the boundary
+    rng = np.random.default_rng(0)
+    cr = rng.standard_normal(c.shape)
+    a = T.to_orthogonal(cr)
+    assert np.abs((Vx(np.array([0.0])) @ a @ Vy(ys).T)[0] - f(0.0, ys)).max() < 1e-10
+    assert np.abs((Vx(xs) @ a @ Vy(np.array([1.0])).T)[:, 0] - f(xs, 1.0)).max() < 1e-10
+    assert rel(T.from_orthogonal(a), cr) < 1e-11
+    # inconsistent corner data are refused
+    bad = {"left": {"D": ue.subs(y, domy[0]) + 1}, "right": {"D": ue.subs(y, domy[1])}}
+    with pytest.raises(ValueError):
+        jf.TensorProduct(jf.FunctionSpace(N, Sp, bcx, domain=domx), jf.FunctionSpace(N, Sp, bad, domain=domy))
