@@ -169,6 +169,16 @@ int jfx_plan_executed_flops(const jfx_plan* plan, double* flops);
 /* Number of kernel launches one jfx_execute enqueues. */
 int jfx_plan_launches(const jfx_plan* plan);
 
+/* Plan registry: a SERIALISABLE handle for callers that cannot carry a pointer (XLA FFI attributes, compilation caches,
+   one program running on several devices under shard_map).  jfx_registry_register deep-copies the descriptor and its host
+   tables and returns a 64-bit key that depends only on the descriptor's contents (incl. the table values); it may be called
+   at trace time, any number of times.  jfx_registry_acquire returns the plan of that key for the CURRENT CUDA device,
+   creating it (device tables, fold analysis) on first use there — call it from an initialisation stage, not from a stream
+   callback that must not synchronise.  Plans obtained this way are owned by the registry (never jfx_plan_destroy them). */
+int jfx_registry_register(const jfx_plan_desc* desc, uint64_t* key_out);
+int jfx_registry_acquire(uint64_t key, const jfx_plan** out);
+void jfx_registry_clear(void);
+
 /* Execution: device pointers, enqueued on `stream`, no host synchronisation.
    `workspace` must hold jfx_plan_workspace_bytes() bytes (may be NULL when that is 0).
    `in` is never written; `out` must not alias `in` or `workspace`. */

@@ -75,6 +75,9 @@ _SIGNATURES = {
     "jfx_fast_path_available": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "jfx_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)]),
     "jfx_plan_destroy": (None, [C.c_void_p]),
+    "jfx_registry_register": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(C.c_uint64)]),
+    "jfx_registry_acquire": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "jfx_registry_clear": (None, []),
     "jfx_plan_ndim": (C.c_int, [C.c_void_p]),
     "jfx_plan_shape_out": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "jfx_plan_workspace_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),

@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <memory>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "jfx_common.h"
 #include "fft_common.cuh"
@@ -835,6 +837,95 @@ int jfx_axpby_diag(void* stream, int n_terms, const void* const* coeff, const do
   JFX_REQUIRE(x && out, JFX_ERR_INVALID, "null argument");
   return launch_axpby_diag((cudaStream_t)stream, n_terms, coeff, alpha, x, out, n, dtype, coeff_is_complex);
 }
+// ---- plan registry: serialisable keys instead of raw plan pointers (XLA FFI attributes) ------------------------------
+namespace {
+struct RegistryEntry {
+  jfx_plan_desc desc{};
+  std::vector<std::vector<unsigned char>> tables;     // deep copies of the host tables, one per axis (may be empty)
+  std::vector<std::pair<int, jfx_plan*>> plans;       // (device ordinal, plan)
+};
+std::mutex g_reg_mu;
+std::vector<std::pair<uint64_t, std::unique_ptr<RegistryEntry>>> g_registry;
+
+uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+size_t table_bytes(const jfx_plan_desc& d, int ax) {
+  const jfx_axis_desc& a = d.axis[ax];
+  if (!a.table || (a.basis != JFX_BASIS_TABLE && a.basis != JFX_BASIS_CTABLE)) return 0;
+  return (size_t)a.table_rows * (size_t)a.table_cols * (a.basis == JFX_BASIS_CTABLE ? 16 : 8);
+}
+}  // namespace
+
+int jfx_registry_register(const jfx_plan_desc* desc, uint64_t* key_out) {
+  using namespace jfx;
+  JFX_REQUIRE(desc && key_out, JFX_ERR_INVALID, "null argument");
+  JFX_REQUIRE(desc->ndim >= 1 && desc->ndim <= JFX_MAX_DIMS, JFX_ERR_INVALID, "ndim %d out of range", desc->ndim);
+  // key = hash of every field that defines the plan, incl. the table CONTENTS (never of a pointer value)
+  uint64_t h = 1469598103934665603ull;
+  const int32_t head[4] = {desc->abi_version, desc->op, desc->dtype, desc->ndim};
+  h = fnv1a(h, head, sizeof(head));
+  h = fnv1a(h, desc->shape_in, sizeof(int64_t) * desc->ndim);
+  for (int ax = 0; ax < desc->ndim; ++ax) {
+    const jfx_axis_desc& a = desc->axis[ax];
+    const int32_t f[6] = {a.basis, a.n_modes, a.n_quad, a.deriv, a.table_rows, a.table_cols};
+    h = fnv1a(h, f, sizeof(f));
+    h = fnv1a(h, &a.domain_factor, sizeof(double));
+    const size_t tb = table_bytes(*desc, ax);
+    if (tb) h = fnv1a(h, a.table, tb);
+  }
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  for (auto& e : g_registry)
+    if (e.first == h) { *key_out = h; return JFX_OK; }
+  std::unique_ptr<RegistryEntry> e(new (std::nothrow) RegistryEntry);
+  JFX_REQUIRE(e, JFX_ERR_NOMEM, "out of host memory");
+  e->desc = *desc;
+  e->tables.resize(JFX_MAX_DIMS);
+  for (int ax = 0; ax < desc->ndim; ++ax) {
+    const size_t tb = table_bytes(*desc, ax);
+    if (tb) {
+      e->tables[ax].assign((const unsigned char*)desc->axis[ax].table, (const unsigned char*)desc->axis[ax].table + tb);
+      e->desc.axis[ax].table = e->tables[ax].data();
+    } else {
+      e->desc.axis[ax].table = nullptr;
+    }
+  }
+  g_registry.emplace_back(h, std::move(e));
+  *key_out = h;
+  return JFX_OK;
+}
+
+int jfx_registry_acquire(uint64_t key, const jfx_plan** out) {
+  using namespace jfx;
+  JFX_REQUIRE(out, JFX_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int dev = 0;
+  JFX_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  for (auto& e : g_registry) {
+    if (e.first != key) continue;
+    for (auto& p : e.second->plans)
+      if (p.first == dev) { *out = p.second; return JFX_OK; }
+    jfx_plan* pl = nullptr;                      // first use on this device: build its tables here (may synchronise)
+    const int rc = jfx_plan_create(&e.second->desc, &pl);
+    if (rc != JFX_OK) return rc;
+    e.second->plans.emplace_back(dev, pl);
+    *out = pl;
+    return JFX_OK;
+  }
+  set_error("plan key %llu is not registered in this process (jfx_registry_register)", (unsigned long long)key);
+  return JFX_ERR_INVALID;
+}
+
+void jfx_registry_clear(void) {
+  std::lock_guard<std::mutex> lk(g_reg_mu);
+  for (auto& e : g_registry)
+    for (auto& p : e.second->plans) delete p.second;
+  g_registry.clear();
+}
+
 int jfx_point_contract(void* stream, const void* y, const void* w, void* out, int64_t outer, int32_t n, int64_t points,
                        int dtype, int w_is_complex) {
   using namespace jfx;

@@ -92,3 +92,38 @@ def test_empty_batch_and_single_line(cuda, cls):
     if cls != "Chebyshev":   # real Chebyshev data with an odd inner extent uses the dense table (still valid)
         y = V.forward(V.backward(x, axis=1), axis=1)
         assert float((y - x).abs().max()) < 1e-13
+
+
+def test_plan_registry_keys_are_content_hashes_and_plans_are_per_device(cuda):
+    """jfx_registry_register / jfx_registry_acquire (include/jfx.h): the key depends on the descriptor's CONTENTS (table values,
+    not pointers), the same key returns the same plan, an unknown key fails loudly, and a registered plan computes what a
+    directly created plan computes."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import jaxfun_b200 as jf
+    from jaxfun_b200 import _lib as L
+    from jaxfun_b200.engine import _fill_plan_desc, AxisSpec, Plan
+    lib = L.load()
+    V = jf.Legendre(48)
+    T = np.ascontiguousarray(V._dense_table(L.OP_BACKWARD, 48, 48, 0))
+    shape = (7, 48)
+    keys = []
+    for table in (T, T.copy(), T * (1 + 1e-15)):                      # same contents at another address; different contents
+        desc, keep = _fill_plan_desc(L.OP_APPLY, L.F64, shape, [None, AxisSpec(L.BASIS_TABLE, table=table)])
+        k = C.c_uint64()
+        L.check(lib.jfx_registry_register(C.byref(desc), C.byref(k)))
+        keys.append(int(k.value))
+    assert keys[0] == keys[1] and keys[0] != keys[2]
+    h1, h2 = C.c_void_p(), C.c_void_p()
+    L.check(lib.jfx_registry_acquire(C.c_uint64(keys[0]), C.byref(h1)))
+    L.check(lib.jfx_registry_acquire(C.c_uint64(keys[0]), C.byref(h2)))
+    assert h1.value == h2.value and h1.value
+    x = torch.randn(shape, dtype=torch.float64, device=cuda)
+    out = torch.empty_like(x)
+    L.check(lib.jfx_execute(h1, None, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    ref = Plan(L.OP_APPLY, L.F64, shape, [None, AxisSpec(L.BASIS_TABLE, table=T)])(x)
+    assert torch.equal(out, ref)
+    bad = C.c_void_p()
+    assert lib.jfx_registry_acquire(C.c_uint64(12345), C.byref(bad)) == -1 and b"not registered" in lib.jfx_last_error()
