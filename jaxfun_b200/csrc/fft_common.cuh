@@ -25,6 +25,10 @@ __device__ constexpr double kSin16[8] = {0.0, 0.38268343236508977173, 0.70710678
 __device__ constexpr double kCos12[6] = {1.0, 0.86602540378443864676, 0.5, 0.0, -0.5, -0.86602540378443864676};
 __device__ constexpr double kSin12[6] = {0.0, 0.5, 0.86602540378443864676, 1.0, 0.86602540378443864676, 0.5};
 
+// cos(2 pi k/20), sin(2 pi k/20), k = 0..9 (radices 10 and 20 of the 5 * 2^m lengths 80, 160, 320)
+__device__ constexpr double kCos20[10] = {1.0, 0.9510565162951535, 0.8090169943749475, 0.5877852522924731, 0.30901699437494745, 0.0, -0.30901699437494734, -0.587785252292473, -0.8090169943749473, -0.9510565162951535};
+__device__ constexpr double kSin20[10] = {0.0, 0.3090169943749474, 0.5877852522924731, 0.8090169943749475, 0.9510565162951535, 1.0, 0.9510565162951536, 0.8090169943749475, 0.5877852522924732, 0.3090169943749475};
+
 // In-register forward DFT of R points, natural order in and out (decimation in time).
 template <typename T, int R> struct Dft {
   static __device__ __forceinline__ void run(Cpx<T>* v) {
@@ -39,8 +43,8 @@ template <typename T, int R> struct Dft {
       if (k == 0) t = o[k];
       else if (4 * k == R) t = Cpx<T>{o[k].y, -o[k].x};   // * (-i)
       else {
-        const T c = (R % 3 == 0) ? (T)kCos12[k * (12 / R)] : (T)kCos16[k * (16 / R)];   // W = c - i s
-        const T s = (R % 3 == 0) ? (T)kSin12[k * (12 / R)] : (T)kSin16[k * (16 / R)];
+        const T c = (R % 5 == 0) ? (T)kCos20[k * (20 / R)] : (R % 3 == 0) ? (T)kCos12[k * (12 / R)] : (T)kCos16[k * (16 / R)];   // W = c - i s
+        const T s = (R % 5 == 0) ? (T)kSin20[k * (20 / R)] : (R % 3 == 0) ? (T)kSin12[k * (12 / R)] : (T)kSin16[k * (16 / R)];
         t = Cpx<T>{o[k].x * c + o[k].y * s, o[k].y * c - o[k].x * s};
       }
       v[k] = e[k] + t;
@@ -68,6 +72,25 @@ template <typename T> struct Dft<T, 3> {
   }
 };
 
+template <typename T> struct Dft<T, 5> {
+  static __device__ __forceinline__ void run(Cpx<T>* v) {
+    // Winograd-style radix 5: X_k = v0 + sum_m v_m W5^{mk}, with the (1,4) and (2,3) pairs combined
+    const T c1 = (T)0.30901699437494742410, c2 = (T)-0.80901699437494742410;   // cos(2 pi/5), cos(4 pi/5)
+    const T s1 = (T)0.95105651629515357212, s2 = (T)0.58778525229247312917;    // sin(2 pi/5), sin(4 pi/5)
+    const Cpx<T> a1 = v[1] + v[4], b1 = v[1] - v[4], a2 = v[2] + v[3], b2 = v[2] - v[3];
+    const Cpx<T> t1{v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y};
+    const Cpx<T> t2{v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y};
+    // -i (s1 b1 + s2 b2)  and  -i (s2 b1 - s1 b2)
+    const Cpx<T> u1{s1 * b1.y + s2 * b2.y, -(s1 * b1.x + s2 * b2.x)};
+    const Cpx<T> u2{s2 * b1.y - s1 * b2.y, -(s2 * b1.x - s1 * b2.x)};
+    v[0] = v[0] + a1 + a2;
+    v[1] = t1 + u1;
+    v[4] = t1 - u1;
+    v[2] = t2 + u2;
+    v[3] = t2 - u2;
+  }
+};
+
 // radix plans
 template <int N> struct Plan;
 template <> struct Plan<16>   { static constexpr int R0 = 4,  R1 = 4,  R2 = 1;  };
@@ -84,6 +107,11 @@ template <> struct Plan<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16; 
 template <> struct Plan<48>   { static constexpr int R0 = 4,  R1 = 12, R2 = 1;  };
 template <> struct Plan<96>   { static constexpr int R0 = 4,  R1 = 4,  R2 = 6;  };
 template <> struct Plan<192>  { static constexpr int R0 = 4,  R1 = 4,  R2 = 12; };
+template <> struct Plan<384>  { static constexpr int R0 = 4,  R1 = 8,  R2 = 12; };   // 3/2 x 256: a thread owns 24 points
+// 5 * 2^m: the factor 5 sits in the last pass (radix 20 / 10); a thread owns 20 points
+template <> struct Plan<80>   { static constexpr int R0 = 4,  R1 = 20, R2 = 1;  };
+template <> struct Plan<160>  { static constexpr int R0 = 4,  R1 = 4,  R2 = 10; };
+template <> struct Plan<320>  { static constexpr int R0 = 4,  R1 = 4,  R2 = 20; };
 
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
@@ -91,6 +119,10 @@ template <int N> struct PointsPerThread { static constexpr int value = cmax(Plan
 template <> struct PointsPerThread<48> { static constexpr int value = 12; };
 template <> struct PointsPerThread<96> { static constexpr int value = 12; };
 template <> struct PointsPerThread<192> { static constexpr int value = 12; };
+template <> struct PointsPerThread<384> { static constexpr int value = 24; };
+template <> struct PointsPerThread<80> { static constexpr int value = 20; };
+template <> struct PointsPerThread<160> { static constexpr int value = 20; };
+template <> struct PointsPerThread<320> { static constexpr int value = 20; };
 template <int N> struct Geo {
   static constexpr int RMAX = PointsPerThread<N>::value;   // points a thread owns (= largest radix for 2^m)
   static constexpr int TN = N / RMAX;                       // threads per line

@@ -279,7 +279,8 @@ fft_axis_kernel(const FftArgs a) {
 static bool supported_n(int n) {
   switch (n) {
     case 16: case 32: case 64: case 128: case 256: case 512: case 1024: case 2048: case 4096: return true;
-    case 48: case 96: case 192: return true;   // 3 * 2^m: second-generation kernel only
+    case 48: case 96: case 192: case 384: return true;   // 3 * 2^m: second-generation kernel only
+    case 80: case 160: case 320: return true;  // 5 * 2^m: second-generation kernel only
   }
   return false;
 }

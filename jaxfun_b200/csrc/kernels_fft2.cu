@@ -77,6 +77,10 @@ static int launch_t(cudaStream_t s, const FftArgs& a, int n) {
     case 48: return launch_n<T, 48>(s, a);
     case 96: return launch_n<T, 96>(s, a);
     case 192: return launch_n<T, 192>(s, a);
+    case 384: return launch_n<T, 384>(s, a);
+    case 80: return launch_n<T, 80>(s, a);
+    case 160: return launch_n<T, 160>(s, a);
+    case 320: return launch_n<T, 320>(s, a);
     case 32: return launch_n<T, 32>(s, a);
     case 64: return launch_n<T, 64>(s, a);
     case 128: return launch_n<T, 128>(s, a);

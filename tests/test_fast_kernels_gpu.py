@@ -10,7 +10,7 @@ from jaxfun_b200 import _lib as L
 from jaxfun_b200.engine import fast_path_available
 
 pytestmark = pytest.mark.gpu
-SIZES = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 48, 96, 192]
+SIZES = [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 48, 96, 192, 384, 80, 160, 320]
 
 
 def relerr(a, b):
