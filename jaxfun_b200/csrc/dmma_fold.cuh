@@ -92,6 +92,7 @@ struct Args {
   int vec_ok;          // 16-byte aligned vector stores allowed
   // k-tiles: kts_main tiles of the folded problem, then kts_corr asymmetry-correction tiles covering k' >= kcorr0
   int kts_main, kts_corr, kcorr0;
+  int tm_rot;          // the kernel visits tile_m in the order (tm + tm_rot) % tiles_m (scatter launches: see launch_dmma_fold_scatter)
   int xwide;           // NN: the X tensor map splits the contiguous axis as (8, inner / 8): one box per X tile (inner % 8 == 0)
 };
 

@@ -119,7 +119,8 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
     const unsigned r = p_tl / (unsigned)q.tiles_n;
     p_tn = (int)(p_tl - r * (unsigned)q.tiles_n);
     p_z = (int)(r / (unsigned)q.tiles_m);
-    p_tm = (int)(r - (unsigned)p_z * (unsigned)q.tiles_m);
+    p_tm = (int)(r - (unsigned)p_z * (unsigned)q.tiles_m) + q.tm_rot;
+    if (p_tm >= q.tiles_m) p_tm -= q.tiles_m;
   };
   auto produce = [&]() {      // one k-tile: wait for the stage, announce the bytes, issue the box copies
     if (p_it >= total_its) return;
@@ -189,7 +190,8 @@ __device__ __forceinline__ void fold_cta(const CUtensorMap& tmA, const CUtensorM
     const unsigned r = tl / (unsigned)q.tiles_n;
     const int tn = (int)(tl - r * (unsigned)q.tiles_n);
     const long long z = r / (unsigned)q.tiles_m;
-    const int tm = (int)(r - (unsigned)z * (unsigned)q.tiles_m);
+    int tm = (int)(r - (unsigned)z * (unsigned)q.tiles_m) + q.tm_rot;
+    if (tm >= q.tiles_m) tm -= q.tiles_m;
     epi(tm, tn, z, wm, wn, g, t, acc);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -354,6 +356,11 @@ int launch_dmma_fold_scatter(cudaStream_t s, const FoldPlan* fp, long long outer
   for (int p = 0; p < parts; ++p)
     if (!peers[p] || (reinterpret_cast<uintptr_t>(peers[p]) & 15)) return 0;
   if (!make_launch(fp->host, /*nn=*/false, outer, 1, fp->d_nt, in, peers[src], &q, &mA, &mB)) return 0;
+  // Every rank walks its rows in the same order; with split a (mode 2) the destination rank is a / (A / P), so without a
+  // rotation all P ranks would store into the SAME peer at any moment (one NVLink ingress port against P - 1 egress ports:
+  // measured at P = 8, 512^3: 0.74 ms for this pass instead of 0.31 ms with local stores).  Rank r starts at the tiles of
+  // destination r and proceeds cyclically, like the steps of a ring all-to-all.  (Mode 1 splits b, which varies fastest.)
+  q.tm_rot = (mode == 2 && q.tiles_m >= parts) ? (int)(((long long)src * q.tiles_m) / parts) : 0;
   Scatter sc{};
   sc.mode = mode; sc.parts = parts; sc.src = src; sc.A = A; sc.B = B;
   for (int p = 0; p < parts; ++p) sc.peer[p] = peers[p];
