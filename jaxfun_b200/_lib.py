@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjfx.so")
+# JFX_LIB_PATH: A/B experiments load a differently-built copy of the same library (tools/build_variant.py)
+LIB_PATH = os.environ.get("JFX_LIB_PATH") or os.path.join(_HERE, "libjfx.so")
 
 JFX_ABI_VERSION = 1
 JFX_MAX_DIMS = 4

@@ -14,13 +14,16 @@ namespace f2 {
 #ifndef JFX_FFT_REGS16
 #define JFX_FFT_REGS16 128
 #endif
+#ifndef JFX_FFT_REGS8
+#define JFX_FFT_REGS8 80
+#endif
 template <int N, int LAY> struct Cta {
   static constexpr int TN = N / Geo<N>::RMAX;
   // strided axes read LPB neighbouring lines per request: keep LPB * 16 B >= 128 B while the tile fits
   static constexpr int LPB_STRIDED = N <= 512 ? 8 : (N <= 2048 ? 4 : 2);
   static constexpr int T0 = (LAY == LAY_STRIDED) ? TN * LPB_STRIDED : TN;
   static constexpr int THREADS = T0 > 128 ? T0 : 128;
-  static constexpr int MINB = (65536 / THREADS) / (Geo<N>::RMAX >= 24 ? 168 : Geo<N>::RMAX >= 16 ? JFX_FFT_REGS16 : 80);   // register budget per thread
+  static constexpr int MINB = (65536 / THREADS) / (Geo<N>::RMAX >= 24 ? 168 : Geo<N>::RMAX >= 16 ? JFX_FFT_REGS16 : JFX_FFT_REGS8);   // register budget per thread
 };
 
 template <typename T> __device__ __forceinline__ Cpx<T> ldg(const Cpx<T>* p) { return *p; }

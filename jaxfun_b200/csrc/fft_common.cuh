@@ -97,7 +97,11 @@ template <> struct Plan<16>   { static constexpr int R0 = 4,  R1 = 4,  R2 = 1;  
 template <> struct Plan<32>   { static constexpr int R0 = 4,  R1 = 8,  R2 = 1;  };
 template <> struct Plan<64>   { static constexpr int R0 = 8,  R1 = 8,  R2 = 1;  };
 template <> struct Plan<128>  { static constexpr int R0 = 8,  R1 = 16, R2 = 1;  };
+#ifdef JFX_PLAN256_884
+template <> struct Plan<256>  { static constexpr int R0 = 8,  R1 = 8,  R2 = 4;  };   // 8 points per thread: half the registers, twice the warps
+#else
 template <> struct Plan<256>  { static constexpr int R0 = 16, R1 = 16, R2 = 1;  };
+#endif
 template <> struct Plan<512>  { static constexpr int R0 = 8,  R1 = 8,  R2 = 8;  };
 template <> struct Plan<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8;  };
 template <> struct Plan<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8;  };

@@ -242,7 +242,7 @@ def _sample_boundary_value(v, symbols, grids, shape):
 
 
 class DirectSumTPS:
-    """Tensor product with ONE DirectSum factor whose boundary values may depend on the other coordinates
+    """Tensor product with ONE DirectSum factor (2-D / 3-D) or TWO (2-D, `_init_two_directions`) whose boundary values may depend on the other coordinates
     (`DirectSumTPS`, tensorproductspace.py:575-851; the case of `examples/poisson2D_periodic.py`).
 
     The lift is a fixed element of the orthogonal tensor-product space: every boundary datum g_b(other coordinates) is
@@ -250,7 +250,7 @@ class DirectSumTPS:
     by the lifting function B_b along the DirectSum axis (tensorproductspace.py:817-830).  Its coefficients `lift` are
     built once on the host; transforms are the homogeneous tensor product's engine plans plus that constant:
     `backward(c) = hom.backward(c) + orthogonal.backward(lift)` (cached), `forward(u) = hom.from_orthogonal(
-    orthogonal.forward(u) - lift)`.  Two inhomogeneous directions (corner compatibility, :620-668) are not built."""
+    orthogonal.forward(u) - lift)`."""
 
     def __init__(self, basespaces, system=None, name: str = "DSTPS") -> None:
         from .composite import DirectSum

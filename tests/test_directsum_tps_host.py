@@ -102,8 +102,9 @@ def test_unsupported_layouts_are_refused():
     D = jf.FunctionSpace(8, jf.Legendre, {"left": {"D": sp.sin(x)}, "right": {"D": 0}})
     with pytest.raises(ValueError):
         D.backward(np.zeros(6))                                   # function-valued data need the tensor product
+    Dc = jf.FunctionSpace(8, jf.Legendre, {"left": {"D": 1.0}, "right": {"D": 0}})
     with pytest.raises(NotImplementedError):
-        jf.TensorProduct(D, D)                                    # two inhomogeneous directions
+        jf.TensorProduct(jf.Fourier(8), Dc, Dc)                   # two inhomogeneous directions in 3-D
     with pytest.raises(ValueError):                               # tensorproductspace.py:612-615
         jf.TensorProduct(jf.FunctionSpace(8, jf.Legendre, {"left": {"D": 1.0}, "right": {"D": 0}}), jf.Fourier(8), jf.Fourier(8))
 
