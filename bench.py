@@ -214,7 +214,8 @@ def _slab_env():
         chunks = max(1, int(os.environ.get("JFX_SLAB_CHUNKS", "1")))
     except ValueError:
         chunks = 1
-    return {"slab_chunks": chunks, "slab_p2p": flag("JFX_SLAB_P2P", "1"), "slab_fused_pack": flag("JFX_SLAB_FUSED_PACK")}
+    return {"slab_chunks": chunks, "slab_p2p": flag("JFX_SLAB_P2P", "1"), "slab_fused_pack": flag("JFX_SLAB_FUSED_PACK"),
+            "slab_native": flag("JFX_SLAB_NATIVE", "1")}
 
 
 def workload_config(n, gpus):
@@ -650,9 +651,19 @@ def run_ours(args):
         sent = 2.0 * 8.0 * n**3 / world * (world - 1) / world
         p2p_used = any(isinstance(v, dict) and "hdls" in v for be in S._backends.values() for v in be._plans.values())
         p2p_err = next((be.p2p_error for be in S._backends.values() if getattr(be, "p2p_error", None)), None)
-        line["exchange"] = {"bytes_sent_per_rank_per_step": sent, "mode": _slab_env(),
-                            "path": ("peer stores from the epilogue of the last local pass (symmetric memory over NVLink), no NCCL "
-                                     "collective on the data path") if p2p_used else "jfx_slab_pack + NCCL all_to_all_single (+ unpack)",
+        native = [v for be in S._backends.values() for k, v in be._plans.items()
+                  if isinstance(k, tuple) and k and k[0] == "native" and isinstance(v, dict)]
+        if native:
+            path = ("jfx_slab_execute (one C-ABI call per transform): " +
+                    ("peer stores from the epilogue of the last local pass" if all(v["fused"] for v in native)
+                     else "strided peer copies") + " + device-side flag barrier over symmetric memory (NVLink), no NCCL collective "
+                    "and no torch op on the data path")
+        elif p2p_used:
+            path = ("peer stores from the epilogue of the last local pass (symmetric memory over NVLink), barrier by "
+                    "torch symmetric memory, no NCCL collective on the data path")
+        else:
+            path = "jfx_slab_pack + NCCL all_to_all_single (+ unpack)"
+        line["exchange"] = {"bytes_sent_per_rank_per_step": sent, "mode": _slab_env(), "path": path,
                             "p2p_fallback_reason": p2p_err}
         if rank == 0:
             # same global problem on ONE GPU: the strong-scaling denominator, measured in this run

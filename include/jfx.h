@@ -230,6 +230,34 @@ int jfx_slab_pack(void* stream, const void* in, void* out, const int64_t* shape,
 int jfx_slab_unpack(void* stream, const void* in, void* out, const int64_t* shape_out, int ndim,
                     int concat_axis, int parts, int dtype);
 
+/* Slab-decomposed transform behind ONE call — `_apply_separable_spmd_shard_map` (sharding.py:43-105 of the reference) for
+   this rank's local block:  phase 1 (the unsharded axes, locally) -> exchange (lax.all_to_all(split_axis = unsharded[0],
+   concat_axis = sharded[0], tiled = True), sharding.py:83-89) -> phase 2 (the originally sharded axis).
+   `desc` describes the whole transform on the LOCAL input block (shape_in = local block, one axis entry per axis, exactly as
+   for a single-device plan) with slab_rank / slab_size set; `sharding` is the sharding of the input: JFX_SLAB_SPECTRAL =
+   axis 0 sharded (backward / backward_primitive), JFX_SLAB_PHYSICAL = axis 1 sharded (forward / scalar_product); the result
+   carries the other one (tests/galerkin/test_forward_backward_spmd.py:71-75).
+   No communication library is involved: the exchange is written by the GPUs themselves into receive buffers that every rank
+   maps from every peer (CUDA IPC / VMM / symmetric memory over NVLink) — by the contraction epilogue of phase 1 where that
+   exists (jfx_execute_scatter), by one strided 2-D peer copy per rank otherwise (any dtype, any basis; no pack / unpack
+   kernels) — followed by a device-side barrier on peer-mapped flag words.  The caller provides, per rank, TWO receive
+   buffers of `recv_bytes` and one zero-initialised flag pad of `signal_bytes`, and binds the peer-mapped pointers of all
+   ranks (index = rank) once.  jfx_slab_execute enqueues everything on `stream` and never synchronises the host; every rank
+   of the box must call it the same number of times (it contains a barrier).  `in` is not written; `out` = local block of
+   the result (shape from jfx_slab_sizes). */
+#define JFX_SLAB_SPECTRAL 0
+#define JFX_SLAB_PHYSICAL 1
+typedef struct jfx_slab jfx_slab;
+int jfx_slab_create(const jfx_plan_desc* desc, int sharding, jfx_slab** out);
+void jfx_slab_destroy(jfx_slab* slab);
+int jfx_slab_sizes(const jfx_slab* slab, size_t* recv_bytes, size_t* signal_bytes, size_t* workspace_bytes,
+                   int64_t* shape_out /* [JFX_MAX_DIMS] */);
+/* 1 when phase 1 ends in the peer-store epilogue, 0 when the exchange is done by peer copies. */
+int jfx_slab_fused(const jfx_slab* slab);
+int jfx_slab_bind(jfx_slab* slab, void* const* recv0 /* [size] */, void* const* recv1 /* [size] */,
+                  void* const* signal /* [size] */);
+int jfx_slab_execute(jfx_slab* slab, void* stream, const void* in, void* out, void* workspace);
+
 /* Stage arithmetic of the integrators (etdrk4.py:152-166, rk4.py:14-20): out = sum_i c_i * x_i with
    per-element diagonal coefficients c_i (or NULL = 1) scaled by alpha_i.  Complex or real. */
 int jfx_axpby_diag(void* stream, int n_terms, const void* const* coeff, const double* alpha,

@@ -111,6 +111,35 @@ XLA_FFI_DEFINE_HANDLER(kJfxSlabPhase1, JfxSlabPhase1Impl,
 extern "C" XLA_FFI_Error* JfxSlabTransformPhase1(XLA_FFI_CallFrame* f) { return kJfxSlabPhase1->Call(f); }
 // phase 2 is an ordinary JfxExecute on the receive buffer.
 
+// ---- the whole slab transform as ONE handler (JfxSlabTransform) ------------------------------------------------
+// `slab` is a jfx_slab created and bound by the Python glue at start-up (jfx_slab_create with slab_rank / slab_size,
+// jfx_slab_bind with the peer-mapped receive buffers and flag pads of all devices); like the nonlinear objects it is looked
+// up by a per-process integer id.  jfx_slab_execute enqueues phase 1 (peer stores from the contraction epilogue, or one
+// strided peer copy per device), a device-side flag barrier and phase 2 on XLA's stream: no NCCL call, no host
+// synchronisation, and the handler never blocks the host thread on another device (the wait happens on the GPU, bounded).
+// Every device of the mesh must run the handler the same number of times — which shard_map guarantees.  Not marked
+// command-buffer compatible: the object alternates between its two receive buffers on successive calls.
+static ffi::Error JfxSlabTransformImpl(cudaStream_t stream, ffi::ScratchAllocator scratch, ffi::AnyBuffer x,
+                                       ffi::Result<ffi::AnyBuffer> out, int64_t handle) {
+  jfx_slab* slab = reinterpret_cast<jfx_slab*>(static_cast<intptr_t>(handle));
+  size_t ws_bytes = 0;
+  if (jfx_slab_sizes(slab, nullptr, nullptr, &ws_bytes, nullptr) != JFX_OK)
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, jfx_last_error());
+  auto got = scratch.Allocate(ws_bytes ? ws_bytes : 1);
+  if (!got.has_value()) return ffi::Error(ffi::ErrorCode::kResourceExhausted, "jfx: scratch allocation failed");
+  const int rc = jfx_slab_execute(slab, stream, x.untyped_data(), out->untyped_data(), *got);
+  if (rc != JFX_OK) return ffi::Error(ffi::ErrorCode::kInternal, jfx_last_error());
+  return ffi::Error::Success();
+}
+XLA_FFI_DEFINE_HANDLER(kJfxSlabTransform, JfxSlabTransformImpl,
+                       ffi::Ffi::Bind()
+                           .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                           .Ctx<ffi::ScratchAllocator>()
+                           .Arg<ffi::AnyBuffer>()
+                           .Ret<ffi::AnyBuffer>()
+                           .Attr<int64_t>("handle"));
+extern "C" XLA_FFI_Error* JfxSlabTransform(XLA_FFI_CallFrame* f) { return kJfxSlabTransform->Call(f); }
+
 // ---- nonlinear term ---------------------------------------------------------------------------------------------------
 // jfx_nonlinear objects are created by the Python glue at trace time and looked up by an integer id it keeps per process
 // (nonlinear descriptors hold leaf plan descriptors; a registry for them follows the plan registry's pattern).

@@ -38,6 +38,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _read_deps(path: str):
+    """Repository files named by an nvcc -MD dependency file (system / CUDA headers are ignored); [] if unreadable."""
+    try:
+        txt = open(path).read()
+    except OSError:
+        return []
+    root = os.path.abspath(os.path.join(HERE, ".."))
+    out = []
+    for tok in txt.split():
+        tok = tok.rstrip(":")
+        if tok.startswith(root) and os.path.exists(tok) and not tok.endswith(".o"):
+            out.append(tok)
+    return out
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
@@ -53,11 +68,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         objs.append(obj)
-        # incremental: an object newer than its source and every header is kept (force / verbose / extra flags rebuild all)
-        if (not force and not verbose and not extra and os.path.exists(obj)
-                and os.path.getmtime(obj) > max(os.path.getmtime(os.path.join(CSRC, src)), newest_header)):
-            continue
-        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("JFX_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+        # incremental: an object newer than its source and the headers it includes (nvcc -MD dependency file; without one:
+        # every header) is kept (force / verbose / extra flags rebuild all)
+        if not force and not verbose and not extra and os.path.exists(obj):
+            deps = _read_deps(obj + ".d")
+            newest = max(os.path.getmtime(d) for d in deps) if deps else newest_header
+            if os.path.getmtime(obj) > max(os.path.getmtime(os.path.join(CSRC, src)), newest):
+                continue
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("JFX_NVCC_EXTRA", "").split(), "-MD", "-MF", obj + ".d",
+               "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -21,6 +21,8 @@ JFX_MAX_PROGRAM = 128
 F32, F64, C64, C128 = 0, 1, 2, 3
 # ops
 OP_FORWARD, OP_SCALAR_PRODUCT, OP_BACKWARD, OP_BACKWARD_PRIMITIVE, OP_NONLINEAR, OP_APPLY = range(6)
+# slab shardings (of the INPUT of a slab transform)
+SLAB_SPECTRAL, SLAB_PHYSICAL = 0, 1
 # bases
 BASIS_NONE, BASIS_TABLE, BASIS_CTABLE, BASIS_CHEBYSHEV, BASIS_FOURIER = range(5)
 # pointwise opcodes
@@ -105,6 +107,13 @@ _SIGNATURES = {
                                 C.c_int, C.c_int, C.c_int]),
     "jfx_slab_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int,
                                   C.c_int, C.c_int, C.c_int]),
+    "jfx_slab_create": (C.c_int, [C.POINTER(PlanDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    "jfx_slab_destroy": (None, [C.c_void_p]),
+    "jfx_slab_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                 C.POINTER(C.c_int64)]),
+    "jfx_slab_fused": (C.c_int, [C.c_void_p]),
+    "jfx_slab_bind": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "jfx_slab_execute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jfx_axpby_diag": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_double),
                                  C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int, C.c_int]),
     "jfx_point_contract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int,

@@ -22,7 +22,12 @@ template <int N, int LAY> struct Cta {
   // strided axes read LPB neighbouring lines per request: keep LPB * 16 B >= 128 B while the tile fits
   static constexpr int LPB_STRIDED = N <= 512 ? 8 : (N <= 2048 ? 4 : 2);
   static constexpr int T0 = (LAY == LAY_STRIDED) ? TN * LPB_STRIDED : TN;
-  static constexpr int THREADS = T0 > 128 ? T0 : 128;
+#ifdef JFX_PLAN256_884
+  static constexpr int TMIN = (N == 256) ? 256 : 128;     // the plane-fused kernel wants one CTA size for both layouts
+#else
+  static constexpr int TMIN = 128;
+#endif
+  static constexpr int THREADS = T0 > TMIN ? T0 : TMIN;
   static constexpr int MINB = (65536 / THREADS) / (Geo<N>::RMAX >= 24 ? 168 : Geo<N>::RMAX >= 16 ? JFX_FFT_REGS16 : JFX_FFT_REGS8);   // register budget per thread
 };
 

@@ -177,7 +177,7 @@ enum { K_CHEB_BWD = 0, K_CHEB_FWD = 1, K_FOUR_BWD = 2, K_FOUR_FWD = 3 };
 // configuration is outside its envelope (caller falls back to the staged kernel), < 0 on error
 int launch_fast_axis_v2(cudaStream_t s, const FftArgs& a, int n, bool dbl);
 // streaming variant (kernels_fft2_stream.cu): same return convention
-int launch_fast_axis_stream(cudaStream_t s, const FftArgs& a, int n, bool dbl);
+int launch_fast_axis_stream(cudaStream_t s, const FftArgs& a, int n, bool dbl, int mode);   // mode 1: bulk copies, 2: cp.async
 
 int make_fft_args(const AxisGeom& g, int dtype, const FastParams& p, const FastTables* t, const void* in, void* out,
                   FftArgs* out_args, bool* empty);

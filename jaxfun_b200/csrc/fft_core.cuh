@@ -17,6 +17,9 @@ __device__ __forceinline__ void fft_core(Cpx<T>* v, Cpx<T>* __restrict__ Sl, int
   constexpr bool THREE = (R2 > 1);
   constexpr int RL = THREE ? R2 : R1, NSL = N / RL;
   auto sync = [&]() { if (WARP_SYNC) __syncwarp(); else __syncthreads(); };
+#ifdef JFX_FFT_SKIP_CORE
+  return;   // timing diagnostic only (wrong results): what the loads, stores and addressing cost without the butterflies
+#endif
   {
     constexpr int BPT = E / R0;
 #pragma unroll

@@ -89,7 +89,7 @@ static int build_plan(const jfx_plan_desc* d, jfx_plan* pl) {
   JFX_REQUIRE(d->op >= JFX_OP_FORWARD && d->op <= JFX_OP_APPLY && d->op != JFX_OP_NONLINEAR, JFX_ERR_INVALID,
               "bad op %d (nonlinear terms use jfx_nonlinear_create)", d->op);
   JFX_REQUIRE(d->slab_size <= 1, JFX_ERR_UNSUPPORTED,
-              "slab plans are composed by the host from two local plans + jfx_slab_pack/unpack");
+              "a plan is a single-device object: slab transforms are jfx_slab objects (jfx_slab_create)");
   pl->desc = *d;
   pl->ndim = d->ndim;
   const bool to_physical = (d->op == JFX_OP_BACKWARD || d->op == JFX_OP_BACKWARD_PRIMITIVE);
@@ -933,6 +933,203 @@ int jfx_point_contract(void* stream, const void* y, const void* w, void* out, in
   JFX_REQUIRE(dtype >= JFX_F32 && dtype <= JFX_C128, JFX_ERR_INVALID, "bad dtype %d", dtype);
   return launch_point_contract((cudaStream_t)stream, y, w, out, outer, n, points, dtype, w_is_complex);
 }
+// ---- slab-decomposed transform behind one call (sharding.py:43-105 of the reference) ------------------------------
+}  // extern "C"
+
+struct jfx_slab {
+  int rank = 0, size = 1, sharding = 0, ndim = 0, dtype = JFX_F64;
+  jfx_plan* phase1 = nullptr;   // the unsharded axes on the local input block
+  jfx_plan* phase2 = nullptr;   // the originally sharded axis on the exchanged block
+  bool fused = false;           // phase 1 ends in the scatter epilogue (peer stores); else 2-D peer copies
+  int64_t mid[JFX_MAX_DIMS]{};  // phase-1 output shape
+  int64_t exch[JFX_MAX_DIMS]{}; // exchanged block = phase-2 input shape
+  size_t mid_bytes = 0, recv_bytes = 0, ws1_off = 0, ws2_off = 0, ws_bytes = 0;
+  std::vector<void*> recv[2];   // [turn][peer]: receive buffers, peer-mapped on this device
+  std::vector<void*> signal;    // [peer]: flag words (size * 4 bytes each, zero-initialised), peer-mapped
+  void** d_recv[2] = {nullptr, nullptr};   // device copies of the pointer tables
+  void** d_signal = nullptr;
+  int turn = 0;
+  std::mutex mu;
+  ~jfx_slab() {
+    delete phase1;
+    delete phase2;
+    for (int t = 0; t < 2; ++t) if (d_recv[t]) cudaFree(d_recv[t]);
+    if (d_signal) cudaFree(d_signal);
+  }
+};
+
+namespace jfx {
+
+// Device-side barrier over the ranks of the box (one thread per peer): raise my flag in the peer's pad, then wait for the
+// peer's flag in mine and lower it.  A flag can only be raised when it is down, so consecutive barriers cannot overtake each
+// other.  System-scope fences order the peer stores of the kernels enqueued before this one (complete, by stream order)
+// ahead of the flag, and the flag ahead of the reads of the kernels enqueued after it.  Spins are bounded (30 s, then trap).
+__device__ __forceinline__ unsigned long long slab_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__global__ void slab_barrier_kernel(unsigned* const* __restrict__ pads, int rank, int size) {
+  const int p = threadIdx.x;
+  if (p >= size) return;
+  __threadfence_system();
+  unsigned* theirs = pads[p] + rank;   // flag "rank has arrived" in p's pad
+  unsigned* mine = pads[rank] + p;     // flag "p has arrived" in my pad
+  const unsigned long long t0 = slab_now_ns(), limit = 30ull * 1000000000ull;   // a rank that never arrives: trap, no hang
+  while (atomicCAS_system(theirs, 0u, 1u) != 0u) {
+    __nanosleep(200);
+    if (slab_now_ns() - t0 > limit) __trap();
+  }
+  while (atomicCAS_system(mine, 1u, 0u) != 1u) {
+    __nanosleep(200);
+    if (slab_now_ns() - t0 > limit) __trap();
+  }
+  __threadfence_system();
+}
+
+}  // namespace jfx
+
+extern "C" {
+
+int jfx_slab_create(const jfx_plan_desc* desc, int sharding, jfx_slab** out) {
+  using namespace jfx;
+  JFX_REQUIRE(desc && out, JFX_ERR_INVALID, "null argument");
+  *out = nullptr;
+  JFX_REQUIRE(desc->abi_version == JFX_ABI_VERSION, JFX_ERR_INVALID, "ABI version %d != %d", desc->abi_version, JFX_ABI_VERSION);
+  JFX_REQUIRE(sharding == JFX_SLAB_SPECTRAL || sharding == JFX_SLAB_PHYSICAL, JFX_ERR_INVALID, "bad sharding %d", sharding);
+  JFX_REQUIRE(desc->ndim >= 2 && desc->ndim <= JFX_MAX_DIMS, JFX_ERR_INVALID, "slab transforms need 2..%d axes", JFX_MAX_DIMS);
+  const int P = desc->slab_size, rank = desc->slab_rank;
+  JFX_REQUIRE(P >= 1 && rank >= 0 && rank < P, JFX_ERR_INVALID, "slab rank %d / size %d", rank, P);
+  std::unique_ptr<jfx_slab> sl(new (std::nothrow) jfx_slab);
+  JFX_REQUIRE(sl, JFX_ERR_NOMEM, "out of host memory");
+  sl->rank = rank; sl->size = P; sl->sharding = sharding; sl->ndim = desc->ndim; sl->dtype = desc->dtype;
+  const int sh = sharding == JFX_SLAB_SPECTRAL ? 0 : 1;   // sharded axis of the input; the other of {0, 1} is split
+  const int split = 1 - sh;
+  // phase 1: every axis but the sharded one
+  jfx_plan_desc d1 = *desc;
+  d1.slab_rank = 0; d1.slab_size = 1;
+  d1.axis[sh] = jfx_axis_desc{};
+  d1.axis[sh].basis = JFX_BASIS_NONE;
+  int rc = jfx_plan_create(&d1, &sl->phase1);
+  if (rc != JFX_OK) return rc;
+  for (int i = 0; i < desc->ndim; ++i) sl->mid[i] = sl->exch[i] = sl->phase1->shape_out[i];
+  JFX_REQUIRE(sl->mid[split] % P == 0, JFX_ERR_INVALID, "split axis %d has extent %lld, not divisible by %d devices", split,
+              (long long)sl->mid[split], P);   // sharding.py:59-63
+  sl->exch[split] = sl->mid[split] / P;
+  sl->exch[sh] = sl->mid[sh] * P;
+  // phase 2: the sharded axis alone, on the exchanged block
+  jfx_plan_desc d2 = *desc;
+  d2.slab_rank = 0; d2.slab_size = 1;
+  for (int i = 0; i < desc->ndim; ++i) {
+    d2.shape_in[i] = sl->exch[i];
+    if (i != sh) { d2.axis[i] = jfx_axis_desc{}; d2.axis[i].basis = JFX_BASIS_NONE; }
+  }
+  rc = jfx_plan_create(&d2, &sl->phase2);
+  if (rc != JFX_OK) return rc;
+  const size_t es = dtype_size(desc->dtype);
+  sl->mid_bytes = align_up((size_t)prod(sl->mid, 0, sl->ndim) * es, 256);
+  sl->recv_bytes = (size_t)prod(sl->exch, 0, sl->ndim) * es;
+  sl->fused = P > 1 && desc->ndim == 3 && jfx_plan_scatter_supported(sl->phase1, P, split) == 1;
+  {
+    static const bool no_fuse = [] { const char* e = getenv("JFX_SLAB_P2P"); return e && e[0] == '0'; }();
+    if (no_fuse) sl->fused = false;
+  }
+  // workspace: [phase-1 result (copy route only)] [phase-1 workspace] [phase-2 workspace]
+  sl->ws1_off = sl->fused ? 0 : sl->mid_bytes;
+  sl->ws2_off = sl->ws1_off + align_up(sl->phase1->ws_bytes, 256);
+  sl->ws_bytes = sl->ws2_off + align_up(sl->phase2->ws_bytes, 256);
+  *out = sl.release();
+  return JFX_OK;
+}
+
+void jfx_slab_destroy(jfx_slab* s) { delete s; }
+
+int jfx_slab_sizes(const jfx_slab* s, size_t* recv_bytes, size_t* signal_bytes, size_t* workspace_bytes,
+                   int64_t* shape_out /* [JFX_MAX_DIMS] */) {
+  using namespace jfx;
+  JFX_REQUIRE(s, JFX_ERR_INVALID, "null argument");
+  if (recv_bytes) *recv_bytes = s->recv_bytes;
+  if (signal_bytes) *signal_bytes = (size_t)s->size * sizeof(unsigned);
+  if (workspace_bytes) *workspace_bytes = s->ws_bytes;
+  if (shape_out) for (int i = 0; i < JFX_MAX_DIMS; ++i) shape_out[i] = i < s->ndim ? s->phase2->shape_out[i] : 1;
+  return JFX_OK;
+}
+
+int jfx_slab_fused(const jfx_slab* s) { return s && s->fused ? 1 : 0; }
+
+int jfx_slab_bind(jfx_slab* s, void* const* recv0, void* const* recv1, void* const* signal) {
+  using namespace jfx;
+  JFX_REQUIRE(s && recv0 && recv1 && signal, JFX_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(s->mu);
+  const int P = s->size;
+  for (int p = 0; p < P; ++p)
+    JFX_REQUIRE(recv0[p] && recv1[p] && signal[p], JFX_ERR_INVALID, "peer %d: null buffer", p);
+  s->recv[0].assign(recv0, recv0 + P);
+  s->recv[1].assign(recv1, recv1 + P);
+  s->signal.assign(signal, signal + P);
+  for (int t = 0; t < 2; ++t) {
+    if (!s->d_recv[t]) JFX_CUDA_OK(cudaMalloc((void**)&s->d_recv[t], sizeof(void*) * P));
+    JFX_CUDA_OK(cudaMemcpy(s->d_recv[t], s->recv[t].data(), sizeof(void*) * P, cudaMemcpyHostToDevice));
+  }
+  if (!s->d_signal) JFX_CUDA_OK(cudaMalloc((void**)&s->d_signal, sizeof(void*) * P));
+  JFX_CUDA_OK(cudaMemcpy(s->d_signal, s->signal.data(), sizeof(void*) * P, cudaMemcpyHostToDevice));
+  JFX_CUDA_OK(cudaDeviceSynchronize());   // binding may synchronise (like plan creation); execution never does
+  s->turn = 0;
+  return JFX_OK;
+}
+
+int jfx_slab_execute(jfx_slab* s, void* stream, const void* in, void* out, void* workspace) {
+  using namespace jfx;
+  JFX_REQUIRE(s && in && out, JFX_ERR_INVALID, "null argument");
+  JFX_REQUIRE(s->ws_bytes == 0 || workspace, JFX_ERR_INVALID, "slab transform needs a %zu byte workspace", s->ws_bytes);
+  std::lock_guard<std::mutex> lk(s->mu);
+  const int P = s->size, rank = s->rank;
+  JFX_REQUIRE((int)s->signal.size() == P, JFX_ERR_INVALID, "jfx_slab_bind has not been called");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const int t = s->turn;
+  s->turn ^= 1;
+  const int sh = s->sharding == JFX_SLAB_SPECTRAL ? 0 : 1, split = 1 - sh;
+  int rc;
+  if (s->fused) {
+    rc = jfx_execute_scatter(s->phase1, stream, in, s->recv[t].data(), P, rank, split, ws + s->ws1_off);
+    if (rc != JFX_OK) return rc;
+  } else {
+    // phase 1 into the workspace (or straight through when it has no pass), then one strided 2-D copy per peer:
+    // the exchange of lax.all_to_all(split_axis, concat_axis, tiled=True) (sharding.py:83-89) without pack / unpack kernels
+    const void* mid = in;
+    if (!s->phase1->passes.empty()) {
+      rc = jfx_execute(s->phase1, stream, in, ws, ws + s->ws1_off);
+      if (rc != JFX_OK) return rc;
+      mid = ws;
+    }
+    const size_t es = dtype_size(s->dtype);
+    const size_t rest = (size_t)prod(s->mid, 2, s->ndim) * es;      // bytes of one (axis 0, axis 1) element
+    const int64_t s0 = s->mid[0], s1 = s->mid[1];
+    for (int q = 0; q < P; ++q) {
+      const int p = (rank + q) % P;                                   // start with myself, then round the ring
+      if (sh == 0) {
+        // spectral -> physical: peer p receives mid[:, p*s1/P:(p+1)*s1/P] as block `rank` of its [P, s0, s1/P, ...] buffer
+        const size_t row = (size_t)(s1 / P) * rest;
+        JFX_CUDA_OK(cudaMemcpy2DAsync((char*)s->recv[t][p] + (size_t)rank * s0 * row, row,
+                                      (const char*)mid + (size_t)p * row, (size_t)s1 * rest, row, (size_t)s0,
+                                      cudaMemcpyDeviceToDevice, st));
+      } else {
+        // physical -> spectral: peer p receives mid[p*s0/P:(p+1)*s0/P] as columns rank*s1.. of its [s0/P, P*s1, ...] buffer
+        const size_t row = (size_t)s1 * rest;
+        JFX_CUDA_OK(cudaMemcpy2DAsync((char*)s->recv[t][p] + (size_t)rank * row, (size_t)P * row,
+                                      (const char*)mid + (size_t)p * (s0 / P) * row, row, row, (size_t)(s0 / P),
+                                      cudaMemcpyDeviceToDevice, st));
+      }
+    }
+  }
+  if (P > 1) {
+    slab_barrier_kernel<<<1, 32 * ((P + 31) / 32), 0, st>>>((unsigned* const*)s->d_signal, rank, P);
+    JFX_CUDA_OK(cudaGetLastError());
+  }
+  return jfx_execute(s->phase2, stream, s->recv[t][rank], out, ws + s->ws2_off);
+}
+
 int jfx_calibrate_dmma(void* stream, int iters, double* tflops) {
   using namespace jfx;
   JFX_REQUIRE(tflops && iters > 0, JFX_ERR_INVALID, "bad argument");

@@ -465,8 +465,8 @@ int launch_fast_axis(cudaStream_t s, const AxisGeom& g, int dtype, const FastPar
   // Opt-in (JFX_FFT_STREAM=1, read per call): measured 2x slower on strided axes (n bulk copies of 128 B
   // per tile) and within +-7 % of the plain kernel on contiguous axes — see DESIGN.md.
   const char* stream_env = getenv("JFX_FFT_STREAM");
-  if (!force_v1 && stream_env && stream_env[0] == '1') {
-    const int rc = launch_fast_axis_stream(s, a, p.n_quad, dtype_is_double(dtype));
+  if (!force_v1 && stream_env && (stream_env[0] == '1' || stream_env[0] == '2')) {
+    const int rc = launch_fast_axis_stream(s, a, p.n_quad, dtype_is_double(dtype), stream_env[0] - '0');
     if (rc != 0) return rc < 0 ? rc : JFX_OK;
   }
   if (!force_v1) {

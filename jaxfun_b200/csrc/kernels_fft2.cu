@@ -72,6 +72,10 @@ static int launch_n(cudaStream_t s, const FftArgs& a) {
 
 template <typename T>
 static int launch_t(cudaStream_t s, const FftArgs& a, int n) {
+#ifdef JFX_FFT2_ONLY   /* A/B variant builds (tools/build_variant.py): instantiate one length, everything else falls back */
+  if (n == JFX_FFT2_ONLY) return launch_n<T, JFX_FFT2_ONLY>(s, a);
+  return 0;
+#endif
   switch (n) {
     case 16: return launch_n<T, 16>(s, a);
     case 48: return launch_n<T, 48>(s, a);

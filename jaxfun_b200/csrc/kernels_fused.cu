@@ -19,6 +19,8 @@
 // keeps the occupancy of the plain FFT kernel.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "fft_common.cuh"
 #include "fft_core.cuh"
 #include "pointwise.cuh"
@@ -30,9 +32,21 @@ namespace jfx {
 #endif
 constexpr int FUSED_THREADS = 128;
 
-template <typename T, int N, bool PAD, int DEPTH>
+// MODE: where the leaf lines live between their inverse transform and the pointwise evaluation
+//   PARK_ALL_L2  every leaf and the pointwise result go through the CTA's L2-resident scratch (general programs: the stack
+//                machine indexes its operands at run time)
+//   PARK_L2 / PARK_SMEM  polynomial programs: the LAST leaf never leaves the registers, the pointwise result is formed in
+//                registers and handed to the forward transform by a compile-time register permutation (the bins a thread
+//                holds after an inverse transform are exactly the pass-0 inputs it needs next); only leaves 0 .. L-2 are
+//                parked — in shared memory when they fit beside the exchange buffer, else in the L2 scratch.  KdV -u u_x:
+//                one parked line per row instead of six scratch transits.
+enum { PARK_ALL_L2 = 0, PARK_L2 = 1, PARK_SMEM = 2 };
+
+// PARK_SMEM variants are limited to three CTAs per SM by shared memory: their register budget is sized for 384 threads
+template <typename T, int N, bool PAD, int DEPTH, int MODE>
 __global__ void __launch_bounds__((N / Geo<N>::RMAX) > FUSED_THREADS ? (N / Geo<N>::RMAX) : FUSED_THREADS,
-                                  JFX_FUSED_TPS / ((N / Geo<N>::RMAX) > FUSED_THREADS ? (N / Geo<N>::RMAX) : FUSED_THREADS))
+                                  (MODE == PARK_SMEM && (N / Geo<N>::RMAX) <= FUSED_THREADS ? 384 : JFX_FUSED_TPS) /
+                                      ((N / Geo<N>::RMAX) > FUSED_THREADS ? (N / Geo<N>::RMAX) : FUSED_THREADS))
 fused_rows_kernel(const __grid_constant__ FusedRowArgs a) {
   using P = Plan<N>;
   constexpr int R0 = P::R0;
@@ -53,9 +67,11 @@ fused_rows_kernel(const __grid_constant__ FusedRowArgs a) {
   // Leaf lines: a CTA-private slice of the scratch (L2-resident: gridDim * LPB * n_leaves lines in all).
   // A thread only ever reads back the points it wrote itself (the bins a thread holds after the last FFT
   // pass, j + k*TN, are exactly the points whose pass-0 inputs it needs next), so no barrier guards them.
-  Cpx<T>* __restrict__ Lb = reinterpret_cast<Cpx<T>*>(a.scratch) +
-                            ((size_t)blockIdx.x * LPB + ll) * (size_t)a.n_leaves * N;
+  Cpx<T>* __restrict__ Lb = (MODE == PARK_SMEM)
+      ? S + (size_t)LPB * PITCH + (size_t)ll * (size_t)(a.n_leaves - 1) * N          // parked leaves behind the exchange buffer
+      : reinterpret_cast<Cpx<T>*>(a.scratch) + ((size_t)blockIdx.x * LPB + ll) * (size_t)a.n_leaves * N;
   const long long ntiles = (a.rows + LPB - 1) / LPB;
+  const int last_leaf = a.n_leaves - 1;
 
   Cpx<T> v[E];
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -87,17 +103,51 @@ fused_rows_kernel(const __grid_constant__ FusedRowArgs a) {
         }
       }
       fft_core<T, N, false>(v, Sl, j, tw);
-      Cpx<T>* __restrict__ dst = Lb + (size_t)l * N;
+      if (MODE == PARK_ALL_L2 || l < last_leaf) {
+        Cpx<T>* __restrict__ dst = Lb + (size_t)l * N;
 #pragma unroll
-      for (int bf = 0; bf < BPTL; ++bf)
+        for (int bf = 0; bf < BPTL; ++bf)
 #pragma unroll
-        for (int r = 0; r < RL; ++r) {
-          Cpx<T> z = v[bf * RL + r];
-          z.y = -z.y;
-          dst[j + bf * TN + r * NSL] = z;
-        }
+          for (int r = 0; r < RL; ++r) {
+            Cpx<T> z = v[bf * RL + r];
+            z.y = -z.y;
+            dst[j + bf * TN + r * NSL] = z;
+          }
+      }
       __syncthreads();                                   // exchange buffer is reused by the next transform
     }
+    if (MODE != PARK_ALL_L2) {
+      // ---- polynomial program on registers: last leaf = v, the others from the parked lines (own points only) -------
+      static_assert(E % 4 == 0, "points per thread");
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e].y = -v[e].y;      // conjugate: inverse DFT = conj(FFT(conj(.)))
+#pragma unroll
+      for (int e0 = 0; e0 < E; e0 += 4) {
+        auto leaf4 = [&](int l, int c) -> C2<T> {
+          const int e = e0 + c, m = j + (e / RL) * TN + (e % RL) * NSL;   // the bin register e holds
+          if (l == last_leaf) return C2<T>{v[e].x, v[e].y};
+          const Cpx<T> z = Lb[(size_t)l * N + m];
+          return C2<T>{z.x, z.y};
+        };
+        C2<T> r4[4];
+        poly_eval_vec<T, 4>(a.poly, leaf4, r4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[e0 + c] = Cpx<T>{r4[c].re, r4[c].im};
+      }
+      // ---- register permutation: bin order of the last pass -> input order of pass 0 ----------------------------------
+      {
+        Cpx<T> w[E];
+#pragma unroll
+        for (int bf = 0; bf < BPT0; ++bf)
+#pragma unroll
+          for (int r = 0; r < R0; ++r) {
+            const int k = bf + r * BPT0;                 // point j + k * TN
+            w[bf * R0 + r] = v[(k % BPTL) * RL + k / BPTL];
+          }
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = w[e];
+      }
+    } else
     // ---- pointwise program over the thread's own points, in place over the line of leaf 0 ------------
     if (a.poly.n_terms > 0) {
       // polynomial normal form, four points at a time (their scratch loads overlap)
@@ -129,10 +179,12 @@ fused_rows_kernel(const __grid_constant__ FusedRowArgs a) {
         Lb[m] = Cpx<T>{r.re, r.im};
       }
     }
+    if (MODE == PARK_ALL_L2) {
 #pragma unroll
-    for (int bf = 0; bf < BPT0; ++bf)
+      for (int bf = 0; bf < BPT0; ++bf)
 #pragma unroll
-      for (int r = 0; r < R0; ++r) v[bf * R0 + r] = Lb[j + bf * TN + r * STR0];
+        for (int r = 0; r < R0; ++r) v[bf * R0 + r] = Lb[j + bf * TN + r * STR0];
+    }
     // ---- forward transform, scale, wavenumber gather (Fourier.py:150-180) ---------------------------
     fft_core<T, N, false>(v, Sl, j, tw);
     {
@@ -161,20 +213,39 @@ fused_rows_kernel(const __grid_constant__ FusedRowArgs a) {
 }
 
 // Geometry of one launch: persistent grid (CTAs resident at once), scratch bytes it needs.
-template <typename T, int N, bool PAD, int DEPTH>
+// shared memory of one CTA: the exchange buffer, plus (PARK_SMEM) the parked lines of leaves 0 .. L-2
+template <typename T, int N>
+static size_t fused_smem(int n_leaves, int mode) {
+  constexpr int E = Geo<N>::RMAX, TN = N / E;
+  constexpr int THREADS = TN > FUSED_THREADS ? TN : FUSED_THREADS;
+  constexpr int LPB = THREADS / TN;
+  size_t smem = (size_t)LPB * Geo<N>::PITCH * sizeof(Cpx<T>);
+  if (mode == PARK_SMEM) smem += (size_t)LPB * (size_t)(n_leaves - 1) * N * sizeof(Cpx<T>);
+  return smem;
+}
+
+template <typename T, int N, bool PAD, int DEPTH, int MODE>
 static int fused_geometry(const FusedRowArgs& a, int* grid_out, size_t* smem_out, size_t* scratch_out) {
   constexpr int E = Geo<N>::RMAX, TN = N / E;
   constexpr int THREADS = TN > FUSED_THREADS ? TN : FUSED_THREADS;
   constexpr int LPB = THREADS / TN;
-  const size_t smem = (size_t)LPB * Geo<N>::PITCH * sizeof(Cpx<T>);
-  static int per_sm = -1, sms = 0;
+  const size_t smem = fused_smem<T, N>(a.n_leaves, MODE);
+  // occupancy depends on the leaf count in PARK_SMEM mode: cached per leaf count
+  static int per_sm_l[JFX_MAX_LEAVES + 1], sms = 0;
+  static bool init = false;
+  if (!init) { for (int& v : per_sm_l) v = -1; init = true; }
+  int& per_sm = per_sm_l[a.n_leaves];
   if (per_sm < 0) {
-    JFX_CUDA_OK(cudaFuncSetAttribute(fused_rows_kernel<T, N, PAD, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      JFX_CUDA_OK(cudaFuncSetAttribute(fused_rows_kernel<T, N, PAD, DEPTH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
+    }
     int dev = 0;
     JFX_CUDA_OK(cudaGetDevice(&dev));
     JFX_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int nb = 0;
-    JFX_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_rows_kernel<T, N, PAD, DEPTH>, THREADS, smem));
+    JFX_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_rows_kernel<T, N, PAD, DEPTH, MODE>, THREADS, smem));
     per_sm = nb < 1 ? 1 : nb;
   }
   const long long ntiles = (a.rows + LPB - 1) / LPB;
@@ -188,16 +259,16 @@ static int fused_geometry(const FusedRowArgs& a, int* grid_out, size_t* smem_out
   return JFX_OK;
 }
 
-template <typename T, int N, bool PAD, int DEPTH>
+template <typename T, int N, bool PAD, int DEPTH, int MODE>
 static int launch_fused_v(cudaStream_t s, const FusedRowArgs& a, size_t* scratch_query) {
   constexpr int E = Geo<N>::RMAX, TN = N / E;
   constexpr int THREADS = TN > FUSED_THREADS ? TN : FUSED_THREADS;
   int grid;
   size_t smem, scratch;
-  int rc = fused_geometry<T, N, PAD, DEPTH>(a, &grid, &smem, &scratch);
+  int rc = fused_geometry<T, N, PAD, DEPTH, MODE>(a, &grid, &smem, &scratch);
   if (rc != JFX_OK) return rc;
   if (scratch_query) { *scratch_query = scratch; return 1; }
-  fused_rows_kernel<T, N, PAD, DEPTH><<<grid, THREADS, smem, s>>>(a);
+  fused_rows_kernel<T, N, PAD, DEPTH, MODE><<<grid, THREADS, smem, s>>>(a);
   JFX_CUDA_OK(cudaGetLastError());
   return 1;
 }
@@ -207,8 +278,16 @@ static int launch_fused_n(cudaStream_t s, const FusedRowArgs& a, size_t* q) {
   // PAD: zero padding on the way in or truncation on the way out; DEPTH: operand stack of the program
   const bool pad = (a.n_coeff != N) || (a.n_out != N);
   const bool deep = a.depth > 4;
-  if (pad) return deep ? launch_fused_v<T, N, true, 8>(s, a, q) : launch_fused_v<T, N, true, 4>(s, a, q);
-  return deep ? launch_fused_v<T, N, false, 8>(s, a, q) : launch_fused_v<T, N, false, 4>(s, a, q);
+  // polynomial programs keep the last leaf and the result in registers (JFX_NL_REG=0: the round-1 scratch route, for A/B runs)
+  static const bool reg_off = [] { const char* e = getenv("JFX_NL_REG"); return e && e[0] == '0'; }();
+  if (a.poly.n_terms > 0 && !reg_off) {
+    // parked leaves in shared memory while at least three CTAs still fit on an SM (227 KB), else in the L2 scratch
+    const bool in_smem = a.n_leaves >= 1 && fused_smem<T, N>(a.n_leaves, PARK_SMEM) <= 75 * 1024;
+    if (in_smem) return pad ? launch_fused_v<T, N, true, 4, PARK_SMEM>(s, a, q) : launch_fused_v<T, N, false, 4, PARK_SMEM>(s, a, q);
+    return pad ? launch_fused_v<T, N, true, 4, PARK_L2>(s, a, q) : launch_fused_v<T, N, false, 4, PARK_L2>(s, a, q);
+  }
+  if (pad) return deep ? launch_fused_v<T, N, true, 8, PARK_ALL_L2>(s, a, q) : launch_fused_v<T, N, true, 4, PARK_ALL_L2>(s, a, q);
+  return deep ? launch_fused_v<T, N, false, 8, PARK_ALL_L2>(s, a, q) : launch_fused_v<T, N, false, 4, PARK_ALL_L2>(s, a, q);
 }
 
 template <typename T>

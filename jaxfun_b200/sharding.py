@@ -93,6 +93,14 @@ def slab_p2p() -> bool:
     return os.environ.get("JFX_SLAB_P2P", "1") != "0"
 
 
+def slab_native() -> bool:
+    """The whole slab transform is ONE C-ABI call (`jfx_slab_execute`: phase 1 with peer stores or strided peer copies,
+    device-side barrier on peer-mapped flags, phase 2) — no NCCL collective, no torch op on the data path; torch only
+    provides the symmetric-memory allocation the peers map.  Default; JFX_SLAB_NATIVE=0 keeps the Python orchestration."""
+    import os
+    return os.environ.get("JFX_SLAB_NATIVE", "1") != "0"
+
+
 def slab_fused_pack() -> bool:
     """JFX_SLAB_FUSED_PACK=1: spectral -> physical keeps the NCCL all-to-all, but the last local pass writes the packed send
     buffer itself (the scatter epilogue of jfx_execute_scatter aimed at this rank's own buffer) — no jfx_slab_pack launch."""
@@ -170,6 +178,10 @@ def apply_separable_slab(x, sharding: str, backend: SlabBackend, world_size: int
     Returns the local block of the result, which carries the transposed sharding.  chunks > 1 (default: JFX_SLAB_CHUNKS)
     selects the overlapped exchange."""
     chunks = slab_chunks() if chunks is None else chunks
+    if world_size > 1 and chunks == 1 and slab_native() and not slab_fused_pack() and hasattr(backend, "native_transform"):
+        y = backend.native_transform(x, sharding, world_size)
+        if y is not None:                      # None: symmetric memory unavailable -> host-composed routes below
+            return y
     if world_size > 1 and slab_p2p() and hasattr(backend, "scatter_exchange"):
         y = backend.scatter_exchange(x, sharding, world_size)
         if y is not None:                      # None: this plan / shape has no fused path -> ordinary exchange below
@@ -233,6 +245,43 @@ class EngineSlabBackend(SlabBackend):
 
     def apply_axes(self, x, axes):
         return self._plan_for(x, axes)(x)
+
+    # ---- the whole transform as one jfx_slab call ---------------------------------------------------
+    def native_transform(self, x, sharding: str, world_size: int):
+        """jfx_slab_create / bind / execute (include/jfx.h): returns the local block of the result, or None when the peers'
+        buffers cannot be mapped (no symmetric memory) — the caller then uses the host-composed exchange."""
+        key = ("native", tuple(x.shape), x.dtype, sharding)
+        ent = self._plans.get(key)
+        if ent is False:
+            return None
+        if ent is None:
+            slab = NativeSlab(self.space, self.op, tuple(x.shape), x.dtype, sharding, dist.get_rank(self.group), world_size,
+                              self.N, self.k)
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = (self.group or dist.group.WORLD).group_name
+                if hasattr(symm_mem, "enable_symm_mem_for_group"):
+                    try:
+                        symm_mem.enable_symm_mem_for_group(grp)
+                    except Exception:
+                        pass
+                bufs, hdls = [], []
+                for nbytes in (slab.recv_bytes, slab.recv_bytes, max(slab.signal_bytes, 256)):
+                    b = symm_mem.empty((max(nbytes, 8) + 7) // 8, dtype=torch.int64, device=x.device)
+                    b.zero_()
+                    hdls.append(symm_mem.rendezvous(b, grp))
+                    bufs.append(b)
+                torch.cuda.synchronize(x.device)
+                hdls[2].barrier(channel=0)          # every pad is zero before anybody raises a flag
+                torch.cuda.synchronize(x.device)
+            except Exception as e:
+                self.p2p_error = f"{type(e).__name__}: {e}"
+                slab.close()
+                self._plans[key] = False
+                return None
+            slab.bind(*[[int(p) for p in hd.buffer_ptrs] for hd in hdls])
+            ent = self._plans[key] = {"slab": slab, "bufs": bufs, "hdls": hdls, "fused": slab.fused}
+        return ent["slab"](x)
 
     # ---- exchange fused into the last pass of phase 1 (peer stores) ---------------------------------
     def scatter_exchange(self, x, sharding: str, world_size: int):
@@ -328,6 +377,71 @@ class EngineSlabBackend(SlabBackend):
         shp = list(blocks.shape[1:])
         shp[concat_axis] *= parts
         return self._repack("jfx_slab_unpack", blocks, shp, shp, concat_axis, parts)
+
+
+class NativeSlab:
+    """One rank's `jfx_slab` (include/jfx.h): the whole slab transform of a local block as one C-ABI call.
+
+    The caller allocates two receive buffers of `recv_bytes` and a zeroed flag pad of `signal_bytes` per rank in memory
+    every rank can map, and binds the pointers of all ranks (index = rank) once."""
+
+    def __init__(self, space, op: int, local_shape, torch_dtype, sharding: str, rank: int, world_size: int, N=None, k=None):
+        from . import _lib as L
+        from .engine import _fill_plan_desc, jfx_dtype
+        self._lib = lib = L.load()
+        dtype = jfx_dtype(torch_dtype)
+        sh = sharded_axis(sharding)
+        shape = [int(v) for v in local_shape]
+        specs = []
+        for ax in range(len(shape)):
+            sp = space.basespaces[ax]
+            n_in = shape[ax] * world_size if ax == sh else shape[ax]   # the sharded axis is transformed at its global extent
+            inner = int(np.prod(shape[ax + 1:], dtype=np.int64))
+            if ax == sh == 0:
+                inner //= world_size                                   # phase 2 sees the split axis at 1/P of its extent
+            specs.append(sp.axis_spec(op, n_in, dtype, None if N is None else N[ax], 0 if k is None else k[ax], inner=inner))
+        desc, keep = _fill_plan_desc(op, dtype, shape, specs)
+        desc.slab_rank, desc.slab_size = int(rank), int(world_size)
+        h = C.c_void_p()
+        L.check(lib.jfx_slab_create(C.byref(desc), L.SLAB_SPECTRAL if sharding == SPECTRAL else L.SLAB_PHYSICAL, C.byref(h)))
+        del keep
+        self._h = h
+        rb, sb, wb = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        so = (C.c_int64 * L.JFX_MAX_DIMS)()
+        L.check(lib.jfx_slab_sizes(h, C.byref(rb), C.byref(sb), C.byref(wb), so))
+        self.recv_bytes, self.signal_bytes, self.workspace_bytes = rb.value, sb.value, wb.value
+        self.shape_out = tuple(int(v) for v in so[:len(shape)])
+        self.fused = bool(lib.jfx_slab_fused(h))
+        self.world_size, self.dtype, self._ws = int(world_size), torch_dtype, None
+
+    def bind(self, recv0, recv1, signal):
+        from . import _lib as L
+        P = self.world_size
+        arrs = [(C.c_void_p * P)(*[int(p) for p in ptrs]) for ptrs in (recv0, recv1, signal)]
+        L.check(self._lib.jfx_slab_bind(self._h, *arrs))
+
+    def __call__(self, x, out=None):
+        from . import _lib as L
+        from .engine import current_stream_ptr
+        x = x.contiguous()
+        if self._ws is None:
+            self._ws = torch.empty(max(self.workspace_bytes, 8), dtype=torch.uint8, device=x.device)
+        if out is None:
+            out = torch.empty(self.shape_out, dtype=x.dtype, device=x.device)
+        L.check(self._lib.jfx_slab_execute(self._h, C.c_void_p(current_stream_ptr()), C.c_void_p(x.data_ptr()),
+                                           C.c_void_p(out.data_ptr()), C.c_void_p(self._ws.data_ptr())))
+        return out
+
+    def close(self):
+        if self._h:
+            self._lib.jfx_slab_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class SlabTensorProduct:

@@ -78,3 +78,19 @@ def test_pack_unpack_roundtrip(cuda, P):
         assert torch.equal(packed, torch.stack(torch.chunk(x, P, dim=ax), dim=0).contiguous())
         assert torch.equal(be.unpack(packed, ax, P), x)
 
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_native_slab_c_abi_emulated_ranks(cuda, P):
+    """`jfx_slab_create / bind / execute` (include/jfx.h; the reference's `_apply_separable_spmd_shard_map`,
+    sharding.py:43-105, as ONE call per rank): P ranks emulated on one GPU, one stream per rank, against the single-device
+    transform — peer stores from the contraction epilogue (Legendre^3) and strided peer copies (Chebyshev^3, mixed complex,
+    2-D), flag barrier included.  Own process: the barrier needs the ranks' kernels co-resident."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "slab_native_one_gpu.py"), str(P)], capture_output=True,
+                       text=True, timeout=300, cwd=root)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "SLAB NATIVE ONE GPU OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

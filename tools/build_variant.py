@@ -9,12 +9,19 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, HERE)
-from jaxfun_b200 import _build as B  # noqa: E402
+import importlib.util  # noqa: E402
+_spec = importlib.util.spec_from_file_location("jfx_build", os.path.join(HERE, "jaxfun_b200", "_build.py"))
+B = importlib.util.module_from_spec(_spec)      # the build script alone: importing the package would load libjfx.so
+_spec.loader.exec_module(B)
 
 
 def main():
     tag, flags = sys.argv[1], sys.argv[2:]
+    only = None                      # --only=a.cu,b.cu: recompile these, link the rest from the main build directory
+    for f in list(flags):
+        if f.startswith("--only="):
+            only = f[len("--only="):].split(",")
+            flags.remove(f)
     bdir = os.path.join(B.HERE, "build_" + tag)
     odir = os.path.join(B.HERE, "variants")
     os.makedirs(bdir, exist_ok=True)
@@ -22,6 +29,9 @@ def main():
     nvcc = B._nvcc()
     procs, objs = [], []
     for src in B.SOURCES:
+        if only is not None and src not in only:
+            objs.append(os.path.join(B.HERE, "build", src.replace(".cu", ".o")))
+            continue
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
         objs.append(obj)
         procs.append((src, subprocess.Popen([nvcc, *B.NVCC_FLAGS, *flags, "-c", os.path.join(B.CSRC, src), "-o", obj],

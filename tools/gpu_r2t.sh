@@ -6,7 +6,7 @@ NP=${NP:-2}
 for mode in ${MODES:-JFX_SLAB_P2P=0 JFX_SLAB_P2P=1}; do
   tag=${mode}
   env $mode timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29533 \
-      tools/check_slab_ranks.py 256 2>&1 | grep -E "SLAB CHECK|Error|error" | tail -3
+      tools/check_slab_ranks.py 256 2>&1 | grep -E "SLAB CHECK|Error|error|route" | tail -12
   env $mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29531 \
       bench.py --gpus $NP --steps 10 --warmup 3 > "gpurun_out/scale${NP}_${tag}.json" 2> "gpurun_out/scale${NP}_${tag}.err"
   echo "mode=$tag rc=$?"
