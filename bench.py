@@ -278,11 +278,20 @@ def run_legs(jf, L, torch, dev, fp64_peak, hbm):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    def hbm_entry(ms, nbytes, launches=None):
+    def hbm_entry(ms, nbytes, launches=None, fft_flops=None):
         gbs = nbytes / (ms * 1e-3) / 1e9
         d = {"ms": ms, "compulsory_bytes": nbytes, "achieved_gbs": gbs, "frac_of_hbm": gbs / hbm}
         if launches is not None:
             d["launches"] = launches
+        if fft_flops is not None:
+            # second bound of the fused nonlinear terms: the butterflies themselves (5 n log2 n real operations per 1-D FFT
+            # line).  They are additions and multiplications, hardly any fused multiply-adds, so the FP64 pipe retires at
+            # most HALF of its FMA peak on them; the floor printed here is flops / (peak / 2) beside bytes / HBM peak.
+            tf = fft_flops / (ms * 1e-3) / 1e12
+            d["fft"] = {"flops": fft_flops, "achieved_tflops": tf, "frac_of_fp64_peak": tf / fp64_peak,
+                        "floor_ms_fp64_non_fma": fft_flops / (fp64_peak * 0.5e12) * 1e3,
+                        "floor_ms_hbm": nbytes / (hbm * 1e9) * 1e3,
+                        "binding": "fp64" if fft_flops / (fp64_peak * 0.5e12) > nbytes / (hbm * 1e9) else "hbm"}
         return d
 
     legs = {}
@@ -301,7 +310,8 @@ def run_legs(jf, L, torch, dev, fp64_peak, hbm):
         u, (x,) = field(F)
         term = NonlinearTerm(F, -u * u.diff(x))
         term(cF)
-        c3["kdv_nonlinear"] = hbm_entry(timed(lambda: term(cF)), bF, term.launches(cF))
+        c3["kdv_nonlinear"] = hbm_entry(timed(lambda: term(cF)), bF, term.launches(cF),
+                                        fft_flops=3 * rows * 5.0 * n3 * np.log2(n3))      # 2 inverse + 1 forward FFT per line
         c3["kdv_nonlinear"]["note"] = "forward(-(u u_x)): one coefficient read + one coefficient write are compulsory (8d)"
         del term, cF
         torch.cuda.empty_cache()
@@ -337,7 +347,9 @@ def run_legs(jf, L, torch, dev, fp64_peak, hbm):
         uh = uh / (1.0 + k2 / (2 * np.pi) ** 2) ** 1.5            # smooth field (as tests/test_at_size_gpu.py)
         term4(uh)
         b4 = 2.0 * 16 * n4 * n4
-        c4 = {"shape": [n4, n4], "nonlinear_N": hbm_entry(timed(lambda: term4(uh)), b4, term4.launches(uh))}
+        c4 = {"shape": [n4, n4], "nonlinear_N": hbm_entry(timed(lambda: term4(uh)), b4, term4.launches(uh),
+                                                        # 5 inverse + 1 forward 2-D FFT = 12 x 4096 lines of n = 4096
+                                                        fft_flops=6 * 2 * n4 * 5.0 * n4 * np.log2(n4))}
         c4["nonlinear_N"]["note"] = "-(6u(ux^2+uy^2)+3u^2(uxx+uyy)), 5 leaves: one coefficient read + one write are compulsory (8d)"
         Ld = (-(k2 * k2) * 1e-4 - 0 * k2).to(torch.complex128)   # -gamma k^4 - alpha... diagonal linear operator of the example
         integ = ETDRK4(T4, linear_diag=Ld, nonlinear=term4)
@@ -354,6 +366,21 @@ def run_legs(jf, L, torch, dev, fp64_peak, hbm):
         del term4, integ, uh, T4, Ld, k2
     except Exception as e:  # pragma: no cover
         legs["c4_cahn_hilliard"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+    # ---- mixed product (complex data on a polynomial axis): Fourier x Fourier x Legendre 256^3 c128 ------------
+    try:
+        nm = 256
+        Tm = jf.TensorProduct(jf.Fourier(nm), jf.Fourier(nm), jf.Legendre(nm))
+        cm = torch.view_as_complex(torch.randn(nm, nm, nm, 2, dtype=torch.float64, device=dev, generator=g))
+        um = Tm.backward(cm)
+        msb, msf = timed(lambda: Tm.backward(cm)), timed(lambda: Tm.forward(um))
+        legs["mixed_FxFxLeg_256"] = {"shape": [nm] * 3, "dtype": "c128", "backward_ms": msb, "forward_ms": msf,
+                                     "launches": [p.launches for p in Tm._plans.values()],
+                                     "note": "two FFT passes (HBM-bound, 537 MB each) + one real-table contraction of complex lines "
+                                             "(CPLX_NT: 2 x 8.59 GFLOP algorithmic, unfolded) per transform"}
+        del Tm, cm, um
+    except Exception as e:  # pragma: no cover
+        legs["mixed_FxFxLeg_256"] = {"error": f"{type(e).__name__}: {e}"}
     torch.cuda.empty_cache()
     # ---- C5 on ONE GPU: the strong-scaling denominator of the N > 1 runs -------------------------------------------------
     try:

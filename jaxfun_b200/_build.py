@@ -54,8 +54,6 @@ def _read_deps(path: str):
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
     nvcc = _nvcc()
     objs = []
     build_dir = os.path.join(HERE, "build")
@@ -80,6 +78,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    if not procs and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(o) for o in objs):
+        return LIB                       # every object is newer than its sources and the library newer than every object
     failed = False
     for src, p in procs:
         out, _ = p.communicate()

@@ -20,7 +20,10 @@ namespace f2 {
 template <int N, int LAY> struct Cta {
   static constexpr int TN = N / Geo<N>::RMAX;
   // strided axes read LPB neighbouring lines per request: keep LPB * 16 B >= 128 B while the tile fits
-  static constexpr int LPB_STRIDED = N <= 512 ? 8 : (N <= 2048 ? 4 : 2);
+#ifndef JFX_LPB4096
+#define JFX_LPB4096 2
+#endif
+  static constexpr int LPB_STRIDED = N <= 512 ? 8 : (N <= 2048 ? 4 : JFX_LPB4096);
   static constexpr int T0 = (LAY == LAY_STRIDED) ? TN * LPB_STRIDED : TN;
 #ifdef JFX_PLAN256_884
   static constexpr int TMIN = (N == 256) ? 256 : 128;     // the plane-fused kernel wants one CTA size for both layouts

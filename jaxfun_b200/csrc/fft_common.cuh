@@ -134,6 +134,22 @@ template <int N> struct Geo {
   static constexpr int PITCH = N + (N >> LOGSK) + 1;        // odd -> conflict-free across lines
 };
 
+// Layout of the twiddle table behind the N base entries (host: fast_tables_create, device: fft_core)
+//   middle pass of a three-pass plan (radix R1, butterfly index k < R0, twiddle stride TS = N / (R0 R1)):
+//       tw[OFF_MID  + (r - 1) * R0      + k] = W_N^(r k TS)      r = 1 .. R1 - 1
+//   last pass (radix RL, k < N / RL):
+//       tw[OFF_LAST + (r - 1) * (N/RL)  + k] = W_N^(r k)         r = 1 .. RL - 1
+template <int N> struct TwLayout {
+  using P = Plan<N>;
+  static constexpr bool THREE = P::R2 > 1;
+  static constexpr int RL = THREE ? P::R2 : P::R1;
+  static constexpr int OFF_MID = N;
+  static constexpr int MID = THREE ? (P::R1 - 1) * P::R0 : 0;
+  static constexpr int OFF_LAST = N + MID;
+  static constexpr int LAST = (RL - 1) * (N / RL);
+  static constexpr int TOTAL = N + MID + LAST;
+};
+
 template <int LOGSK> __device__ __forceinline__ int sk(int i) { return i + (i >> LOGSK); }
 
 

@@ -7,6 +7,10 @@ namespace jfx {
 // Forward DFT of one line of length N spread over TN = N/E threads (E = Geo<N>::RMAX points each).
 //   in : v[bf * R0 + r] = x[jj + r * (N / R0)],  jj = j + bf * TN          (pass-0 input stride)
 //   out: v[bf * RL + r] = X[jj + r * (N / RL)],  RL = radix of the last pass
+// tw is the table of fast_tables_create: [0, N) the base twiddles W^m, then the per-pass tables of TwLayout<N>, in which the
+// twiddles of one butterfly leg are stored by butterfly index: the lanes of a warp (consecutive k) read consecutive 16-byte
+// words, where indexing the base table with r * k * TS is a gather with a stride of up to r * TS words per lane (one L1
+// wavefront per lane instead of four per warp).
 // Sl is the line's exchange buffer (Geo<N>::PITCH elements, skew-padded).  The caller must put a
 // barrier between the return of this function and its next write to Sl.
 template <typename T, int N, bool WARP_SYNC>
@@ -46,9 +50,10 @@ __device__ __forceinline__ void fft_core(Cpx<T>* v, Cpx<T>* __restrict__ Sl, int
 #pragma unroll
     for (int bf = 0; bf < BPT; ++bf) {
       const int jj = j + bf * TN, k = jj % NS;
-      const Cpx<T>* w = tw + k * TS;
+      (void)TS;
+      const Cpx<T>* w = tw + TwLayout<N>::OFF_MID + k;     // Wm[(r-1) * NS + k] = W^(r k TS): neighbouring lanes, neighbouring words
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[bf * R + r] = cmul(v[bf * R + r], w[(r - 1) * k * TS]);
+      for (int r = 1; r < R; ++r) v[bf * R + r] = cmul(v[bf * R + r], w[(r - 1) * NS]);
       Dft<T, R>::run(&v[bf * R]);
       Cpx<T>* dst = Sl + sk<LOGSK>((jj / NS) * NS * R + k);
 #pragma unroll
@@ -69,9 +74,9 @@ __device__ __forceinline__ void fft_core(Cpx<T>* v, Cpx<T>* __restrict__ Sl, int
 #pragma unroll
     for (int bf = 0; bf < BPT; ++bf) {
       const int k = j + bf * TN;                         // jj < NS: k = jj
-      const Cpx<T>* w = tw + k;
+      const Cpx<T>* w = tw + TwLayout<N>::OFF_LAST + k;    // Wl[(r-1) * NS + k] = W^(r k)
 #pragma unroll
-      for (int r = 1; r < R; ++r) v[bf * R + r] = cmul(v[bf * R + r], w[(r - 1) * k]);
+      for (int r = 1; r < R; ++r) v[bf * R + r] = cmul(v[bf * R + r], w[(r - 1) * NS]);
       Dft<T, R>::run(&v[bf * R]);
     }
   }

@@ -324,6 +324,19 @@ static void expmipi(long long num, long long den, long double* c, long double* s
   *s = -sgn_s * ss;  // exp(-i theta) = cos - i sin
 }
 
+template <int N> static void radices_of(int* r0, int* r1, int* r2) {
+  *r0 = Plan<N>::R0; *r1 = Plan<N>::R1; *r2 = Plan<N>::R2;
+}
+static bool plan_radices(int n, int* r0, int* r1, int* r2) {
+  switch (n) {
+#define JFX_R(N) case N: radices_of<N>(r0, r1, r2); return true;
+    JFX_R(16) JFX_R(32) JFX_R(64) JFX_R(128) JFX_R(256) JFX_R(512) JFX_R(1024) JFX_R(2048) JFX_R(4096)
+    JFX_R(48) JFX_R(96) JFX_R(192) JFX_R(384) JFX_R(80) JFX_R(160) JFX_R(320)
+#undef JFX_R
+  }
+  return false;
+}
+
 int fast_tables_create(const FastParams& p, int dtype, FastTables** out) {
   *out = nullptr;
   const int n = p.n_quad;
@@ -336,7 +349,24 @@ int fast_tables_create(const FastParams& p, int dtype, FastTables** out) {
   t->dbl = dtype_is_double(dtype);
   std::vector<long double> re(n), im(n);
   for (int m = 0; m < n; ++m) expmipi(2LL * m, n, &re[m], &im[m]);
-  int rc = t->dbl ? upload_complex<double>(re, im, &t->d_tw) : upload_complex<float>(re, im, &t->d_tw);
+  {
+    // per-pass tables behind the base entries (TwLayout<N>, fft_common.cuh): the same values, stored by butterfly index
+    int R0 = 0, R1 = 0, R2 = 0;
+    JFX_REQUIRE(plan_radices(n, &R0, &R1, &R2), JFX_ERR_UNSUPPORTED, "no radix plan for n=%d", n);
+    const bool three = R2 > 1;
+    const int RL = three ? R2 : R1;
+    std::vector<long double> wr(re), wi(im);
+    if (three) {
+      const int TS = n / (R0 * R1);
+      for (int r = 1; r < R1; ++r)
+        for (int k = 0; k < R0; ++k) { wr.push_back(re[(size_t)r * k * TS]); wi.push_back(im[(size_t)r * k * TS]); }
+    }
+    for (int r = 1; r < RL; ++r)
+      for (int k = 0; k < n / RL; ++k) { wr.push_back(re[(size_t)r * k]); wi.push_back(im[(size_t)r * k]); }
+    const int rc0 = t->dbl ? upload_complex<double>(wr, wi, &t->d_tw) : upload_complex<float>(wr, wi, &t->d_tw);
+    if (rc0 != JFX_OK) { delete t; return rc0; }
+  }
+  int rc = JFX_OK;
   if (rc == JFX_OK && cheb) {
     for (int k = 0; k < n; ++k) expmipi(k, 2LL * n, &re[k], &im[k]);
     rc = t->dbl ? upload_complex<double>(re, im, &t->d_half) : upload_complex<float>(re, im, &t->d_half);

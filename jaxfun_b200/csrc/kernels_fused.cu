@@ -30,7 +30,10 @@ namespace jfx {
 #ifndef JFX_FUSED_TPS
 #define JFX_FUSED_TPS 512   /* resident threads per SM the register budget is sized for */
 #endif
-constexpr int FUSED_THREADS = 128;
+#ifndef JFX_FUSED_THREADS
+#define JFX_FUSED_THREADS 64   /* one 1024-point line per CTA: barriers span two warps (round 2: KdV 1.38 -> 1.33 ms) */
+#endif
+constexpr int FUSED_THREADS = JFX_FUSED_THREADS;
 
 // MODE: where the leaf lines live between their inverse transform and the pointwise evaluation
 //   PARK_ALL_L2  every leaf and the pointwise result go through the CTA's L2-resident scratch (general programs: the stack
@@ -282,7 +285,11 @@ static int launch_fused_n(cudaStream_t s, const FusedRowArgs& a, size_t* q) {
   static const bool reg_off = [] { const char* e = getenv("JFX_NL_REG"); return e && e[0] == '0'; }();
   if (a.poly.n_terms > 0 && !reg_off) {
     // parked leaves in shared memory while at least three CTAs still fit on an SM (227 KB), else in the L2 scratch
-    const bool in_smem = a.n_leaves >= 1 && fused_smem<T, N>(a.n_leaves, PARK_SMEM) <= 75 * 1024;
+    // (JFX_NL_PARK=l2 / smem overrides the choice for A/B runs)
+    static const int park_env = [] { const char* e = getenv("JFX_NL_PARK"); return !e ? 0 : (e[0] == 'l' ? 1 : 2); }();
+    bool in_smem = a.n_leaves >= 1 && fused_smem<T, N>(a.n_leaves, PARK_SMEM) <= 75 * 1024;
+    if (park_env == 1) in_smem = false;
+    if (park_env == 2) in_smem = fused_smem<T, N>(a.n_leaves, PARK_SMEM) <= 200 * 1024;
     if (in_smem) return pad ? launch_fused_v<T, N, true, 4, PARK_SMEM>(s, a, q) : launch_fused_v<T, N, false, 4, PARK_SMEM>(s, a, q);
     return pad ? launch_fused_v<T, N, true, 4, PARK_L2>(s, a, q) : launch_fused_v<T, N, false, 4, PARK_L2>(s, a, q);
   }
