@@ -284,12 +284,12 @@ static int launch_fused_n(cudaStream_t s, const FusedRowArgs& a, size_t* q) {
   // polynomial programs keep the last leaf and the result in registers (JFX_NL_REG=0: the round-1 scratch route, for A/B runs)
   static const bool reg_off = [] { const char* e = getenv("JFX_NL_REG"); return e && e[0] == '0'; }();
   if (a.poly.n_terms > 0 && !reg_off) {
-    // parked leaves in shared memory while at least three CTAs still fit on an SM (227 KB), else in the L2 scratch
-    // (JFX_NL_PARK=l2 / smem overrides the choice for A/B runs)
-    static const int park_env = [] { const char* e = getenv("JFX_NL_PARK"); return !e ? 0 : (e[0] == 'l' ? 1 : 2); }();
-    bool in_smem = a.n_leaves >= 1 && fused_smem<T, N>(a.n_leaves, PARK_SMEM) <= 75 * 1024;
-    if (park_env == 1) in_smem = false;
-    if (park_env == 2) in_smem = fused_smem<T, N>(a.n_leaves, PARK_SMEM) <= 200 * 1024;
+    // parked leaves: the L2-resident scratch by default — measured on the B200 (KdV 65 536 x 1024: 0.92 ms against 1.06 ms with
+    // shared-memory parking, Cahn-Hilliard 1024^2 0.103 against 0.125 ms): the parked lines cost a third of the resident
+    // warps (12 instead of 16 per SM), which hurts more than the L2 round trip of ONE line per row.  JFX_NL_PARK=smem selects
+    // shared-memory parking where it fits.
+    static const int park_env = [] { const char* e = getenv("JFX_NL_PARK"); return !e ? 0 : (e[0] == 's' ? 2 : 1); }();
+    const bool in_smem = park_env == 2 && a.n_leaves >= 1 && fused_smem<T, N>(a.n_leaves, PARK_SMEM) <= 200 * 1024;
     if (in_smem) return pad ? launch_fused_v<T, N, true, 4, PARK_SMEM>(s, a, q) : launch_fused_v<T, N, false, 4, PARK_SMEM>(s, a, q);
     return pad ? launch_fused_v<T, N, true, 4, PARK_L2>(s, a, q) : launch_fused_v<T, N, false, 4, PARK_L2>(s, a, q);
   }

@@ -6,7 +6,9 @@ import collections, csv, io, json, re, subprocess, sys, os
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r1d"
 RD = sys.argv[2] if len(sys.argv) > 2 else "r1"          # prefix of the files written under profiles/ (r1, r2, ...)
-G, P = "gpurun_out", "profiles"
+# JFX_PROF_IN / JFX_PROF_OUT: run on the GPU box right after the captures (the .ncu-rep files are too large to travel back)
+G, P = os.environ.get("JFX_PROF_IN", "gpurun_out"), os.environ.get("JFX_PROF_OUT", "profiles")
+os.makedirs(P, exist_ok=True)
 
 # ---- launch list -------------------------------------------------------------------------------------
 rows = list(csv.reader(open(f"{G}/launches_{tag}.csv")))
