@@ -255,8 +255,14 @@ class EngineSlabBackend(SlabBackend):
         if ent is False:
             return None
         if ent is None:
-            slab = NativeSlab(self.space, self.op, tuple(x.shape), x.dtype, sharding, dist.get_rank(self.group), world_size,
-                              self.N, self.k)
+            from ._lib import JfxError
+            try:
+                slab = NativeSlab(self.space, self.op, tuple(x.shape), x.dtype, sharding, dist.get_rank(self.group), world_size,
+                                  self.N, self.k)
+            except JfxError as e:
+                if "not divisible" in str(e):
+                    raise ValueError(str(e)) from None      # the reference's error for this case (sharding.py:59-63)
+                raise
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 grp = (self.group or dist.group.WORLD).group_name
