@@ -19,7 +19,8 @@ def test_header_declares_the_contract_entry_points():
     syms = header_symbols()
     for must in ("jfx_plan_create", "jfx_plan_destroy", "jfx_plan_workspace_bytes", "jfx_execute",
                  "jfx_last_error", "jfx_execute_host", "jfx_nonlinear_create", "jfx_nonlinear_execute",
-                 "jfx_slab_pack", "jfx_slab_unpack"):
+                 "jfx_slab_pack", "jfx_slab_unpack", "jfx_slab_create", "jfx_slab_bind", "jfx_slab_execute",
+                 "jfx_slab_sizes", "jfx_slab_destroy", "jfx_execute_scatter", "jfx_registry_register"):
         assert must in syms
 
 
@@ -61,6 +62,30 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.JfxError) as e:
         jf.Legendre(8).forward(np.zeros(8))
     assert e.value.code == -3
+
+
+def test_slab_object_argument_checks_and_no_cpu_fallback():
+    """jfx_slab_create validates its arguments before touching a device and, without one, fails with JFX_ERR_CUDA like a
+    plan (the slab transform has no host route either)."""
+    import torch
+    from jaxfun_b200 import _lib
+    lib = _lib.load()
+    d = _lib.PlanDesc()
+    d.abi_version, d.op, d.dtype, d.ndim = _lib.JFX_ABI_VERSION, _lib.OP_BACKWARD, _lib.F64, 3
+    for i in range(3):
+        d.shape_in[i] = 8
+    h = C.c_void_p()
+    d.slab_rank, d.slab_size = 2, 2                                   # rank outside 0 .. size - 1
+    assert lib.jfx_slab_create(C.byref(d), _lib.SLAB_SPECTRAL, C.byref(h)) == -1 and not h.value
+    assert b"slab rank" in lib.jfx_last_error()
+    d.slab_rank = 0
+    assert lib.jfx_slab_create(C.byref(d), 7, C.byref(h)) == -1          # unknown sharding
+    d.ndim = 1
+    assert lib.jfx_slab_create(C.byref(d), _lib.SLAB_SPECTRAL, C.byref(h)) == -1   # a slab needs two axes to exchange
+    d.ndim = 3
+    assert lib.jfx_slab_execute(None, None, None, None, None) == -1      # null arguments are refused, not dereferenced
+    if not torch.cuda.is_available():
+        assert lib.jfx_slab_create(C.byref(d), _lib.SLAB_SPECTRAL, C.byref(h)) == -3 and not h.value
 
 
 def test_product_does_not_import_oracle():
