@@ -314,7 +314,7 @@ template <typename T, int N, int KIND, int LAY, bool GEN>
 __global__ void __launch_bounds__(Cta<N, LAY>::THREADS, Cta<N, LAY>::MINB)
 fft2_kernel(const FftArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  fft2_tile<T, N, KIND, LAY, GEN>(a, blockIdx.x, reinterpret_cast<Cpx<T>*>(smem_raw));
+  fft2_tile<T, N, KIND, LAY, GEN>(a, a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x, reinterpret_cast<Cpx<T>*>(smem_raw));
 }
 
 }  // namespace f2

@@ -168,6 +168,7 @@ struct FftArgs {
   int real_pair;
   int lpb;
   int log_lpb;
+  int reverse;        // tile order last-to-first (L2 reuse between consecutive passes)
   double scale;
 };
 

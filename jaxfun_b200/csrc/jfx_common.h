@@ -76,6 +76,7 @@ struct FastParams {
   int n_quad;    // n (transform length)
   int deriv;     // k
   double domain_factor;
+  int reverse;   // walk the tiles last-to-first: the pass starts on what the previous pass wrote last (still in L2)
 };
 bool fast_available(int basis, int n, int dtype);
 bool fast_geometry_ok(const AxisGeom& g, int dtype);

@@ -455,7 +455,7 @@ int make_fft_args(const AxisGeom& g, int dtype, const FastParams& p, const FastT
   *empty = false;
   a.in = in; a.out = out;
   a.tw = t->d_tw; a.half = t->d_half; a.pre = t->d_pre;
-  a.n_in = g.n_in; a.n_out = g.n_out; a.n_modes = p.n_modes; a.kind = p.kind;
+  a.n_in = g.n_in; a.n_out = g.n_out; a.n_modes = p.n_modes; a.kind = p.kind; a.reverse = p.reverse;
   const double n = (double)p.n_quad;
   const double PI = 3.14159265358979323846;
   switch (p.kind) {
