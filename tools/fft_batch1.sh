@@ -1,5 +1,11 @@
 #!/bin/bash
-# A/B batch of the FFT / DCT axis-pass variants on one GPU (timing only; see tools/build_variant.py)
+# A/B batch of the FFT / DCT axis-pass variants on one GPU (timing only; see tools/build_variant.py).  Build the variants first:
+#   F=kernels_fft.cu,kernels_fft2.cu,kernels_fft2_pair.cu,kernels_fft2_stream.cu,kernels_fused.cu; O="--only=$F -DJFX_FFT2_ONLY=256"
+#   python tools/build_variant.py p884    $O -DJFX_PLAN256_884 -DJFX_FFT_REGS8=64
+#   python tools/build_variant.py p884r80 $O -DJFX_PLAN256_884
+#   python tools/build_variant.py skip    $O -DJFX_FFT_SKIP_CORE
+#   python tools/build_variant.py skip884 $O -DJFX_FFT_SKIP_CORE -DJFX_PLAN256_884 -DJFX_FFT_REGS8=64
+# (recorded run: profiles/r2_fft_variants.txt)
 set -u
 mkdir -p gpurun_out
 V=jaxfun_b200/variants

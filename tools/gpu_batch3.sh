@@ -1,4 +1,7 @@
 #!/bin/bash
+# build first:  python tools/build_variant.py lpb1 --only=kernels_fft2.cu -DJFX_FFT2_ONLY=4096 -DJFX_LPB4096=1
+#               python tools/build_variant.py ft64 --only=kernels_fused.cu -DJFX_FUSED_THREADS=64   (64 is the default now)
+# (recorded run: profiles/r2_fused_kdv_ncu.txt)
 # round-2 batch 3: strided n = 4096 with one line per CTA (two CTAs per SM), 64-thread CTAs in the fused nonlinear kernel, ncu of the KdV kernel
 set -u
 mkdir -p gpurun_out
