@@ -272,6 +272,42 @@ int jfx_axpby_diag(void* stream, int n_terms, const void* const* coeff, const do
 int jfx_point_contract(void* stream, const void* y, const void* w, void* out, int64_t outer, int32_t n, int64_t points,
                        int dtype, int w_is_complex);
 
+/* Wavenumber-batched banded solves of Fourier x polynomial tensor-product systems — `tpmats_wavenumber_factor` /
+   `TPMatricesWavenumberSolver.solve` (la/tpmatrix.py:1236-1354, 686-1014 of the reference) with the no-pivot banded LU of
+   la/diamatrix.py:1937-1973.  System s (one per combination of Fourier wavenumbers, C order over the Fourier axes) has the
+   banded matrix  B_s = sum_t weights[t][s] * P_t  on the polynomial axis (tpmatrix.py:1306-1347: W[t, s] = scale_t * product of
+   the Fourier-axis diagonals at s; P_t = polynomial-axis matrix of term t in DIA form on the union `offsets`).
+   jfx_banded_create assembles all B_s on the device, factors them in place (L unit lower, U upper; no pivoting) and
+   fails with JFX_ERR_UNSUPPORTED when a pivot is zero or not finite (diamatrix.py:461-471 raises there).  It may synchronise.
+   jfx_banded_solve solves every system for one right-hand-side array addressed as [outer, n, inner] (row-major; system
+   s = o * inner + i, outer * inner = n_sys), i.e. the polynomial axis may be any axis of the array and nothing is
+   transposed; `rhs` and `out` are device pointers of the descriptor's dtype and may be the same buffer.  It enqueues one
+   launch on `stream`, allocates nothing and never synchronises. */
+#define JFX_BANDED_MAX_TERMS 8
+typedef struct {
+  int32_t abi_version;   /* JFX_ABI_VERSION                                                                 */
+  int32_t dtype;         /* jfx_dtype of the right-hand sides; the factors are kept in its precision        */
+  int32_t band_complex;  /* 0: weights / diags are float64, 1: complex128 (needs a complex dtype)            */
+  int32_t n_terms;       /* 1 .. JFX_BANDED_MAX_TERMS                                                       */
+  int64_t n;             /* length of the polynomial axis = order of every banded system                    */
+  int64_t n_sys;         /* number of systems = product of the Fourier extents                              */
+  int32_t n_diags;       /* number of diagonals in `offsets`                                                */
+  int32_t reserved0;
+  const int32_t* offsets;/* host, [n_diags], strictly increasing, must contain 0                            */
+  const void* weights;   /* host, [n_terms][n_sys]                                                          */
+  const void* diags;     /* host, [n_terms][n_diags][n], column-aligned DIA: diags[t][d][j] = P_t[j - offsets[d], j] */
+  int32_t reserved[8];
+} jfx_banded_desc;
+typedef struct jfx_banded jfx_banded;
+int jfx_banded_create(const jfx_banded_desc* desc, jfx_banded** out);
+void jfx_banded_destroy(jfx_banded* b);
+/* lower / upper bandwidth and the bytes of device memory the factors occupy */
+int jfx_banded_info(const jfx_banded* b, int32_t* p, int32_t* q, size_t* factor_bytes);
+/* copy the factored band to the host: [p + q + 1][n][n_sys] elements (row p - s = multipliers of sub-diagonal s, rows
+   p .. p + q = U; band[p + off][j] = entry (j - off, j)), real or complex of the dtype's precision.  Synchronises. */
+int jfx_banded_factors(const jfx_banded* b, void* lu_host);
+int jfx_banded_solve(const jfx_banded* b, void* stream, const void* rhs, void* out, int64_t outer, int64_t inner);
+
 /* Calibration helpers used by bench.py (not on the product path). */
 int jfx_calibrate_dmma(void* stream, int iters, double* tflops);
 int jfx_calibrate_dfma(void* stream, int iters, double* tflops);

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjfx.so")
-SOURCES = ["jfx_api.cu", "kernels_dense.cu", "kernels_dense_tma.cu", "kernels_dense_fold.cu", "kernels_fft.cu", "kernels_fft2.cu", "kernels_fft2_pair.cu", "kernels_fft2_stream.cu", "kernels_fused.cu", "kernels_pointwise.cu"]
+SOURCES = ["jfx_api.cu", "kernels_dense.cu", "kernels_dense_tma.cu", "kernels_dense_fold.cu", "kernels_fft.cu", "kernels_fft2.cu", "kernels_fft2_pair.cu", "kernels_fft2_stream.cu", "kernels_fused.cu", "kernels_pointwise.cu", "kernels_banded.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -64,6 +64,18 @@ class NonlinearDesc(C.Structure):
     ]
 
 
+JFX_BANDED_MAX_TERMS = 8
+
+
+class BandedDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("dtype", C.c_int32), ("band_complex", C.c_int32), ("n_terms", C.c_int32),
+        ("n", C.c_int64), ("n_sys", C.c_int64), ("n_diags", C.c_int32), ("reserved0", C.c_int32),
+        ("offsets", C.POINTER(C.c_int32)), ("weights", C.c_void_p), ("diags", C.c_void_p),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
 class JfxError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"jfx error {code}: {message}")
@@ -118,6 +130,11 @@ _SIGNATURES = {
                                  C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int, C.c_int]),
     "jfx_point_contract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int,
                                    C.c_int]),
+    "jfx_banded_create": (C.c_int, [C.POINTER(BandedDesc), C.POINTER(C.c_void_p)]),
+    "jfx_banded_destroy": (None, [C.c_void_p]),
+    "jfx_banded_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_size_t)]),
+    "jfx_banded_factors": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "jfx_banded_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]),
     "jfx_calibrate_dmma": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "jfx_calibrate_dfma": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
 }

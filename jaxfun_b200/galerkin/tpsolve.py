@@ -81,6 +81,184 @@ class KroneckerSumSolver:
         return pv(g)
 
 
-def poisson_solver(T) -> KroneckerSumSolver:
-    """Solver of the weak Laplace operator  (v, div grad u)_w  on the tensor-product space T."""
+# =====================================================================================================================
+# Fourier x polynomial systems: one banded solve per Fourier wavenumber combination
+# =====================================================================================================================
+def dia_from_dense(A, tol: float = 1e-10):
+    """(offsets, data) of a square matrix in column-aligned DIA form, data[d][j] = A[j - offsets[d], j] — the layout of
+    `DiaMatrix.data` the reference's banded LU works on (la/diamatrix.py:1944).  Diagonals whose largest entry is below
+    tol * max|A| are dropped (quadrature round-off of structurally zero diagonals)."""
+    A = np.asarray(A)
+    n = A.shape[0]
+    scale = float(np.abs(A).max()) if A.size else 0.0
+    offs, rows = [], []
+    for off in range(-(n - 1), n):
+        dg = np.diagonal(A, off)
+        if np.abs(dg).max(initial=0.0) > tol * scale:
+            row = np.zeros(n, dtype=A.dtype)
+            if off >= 0:
+                row[off:] = dg
+            else:
+                row[:n + off] = dg
+            offs.append(off)
+            rows.append(row)
+    return tuple(offs), np.array(rows)
+
+
+class SolverNotApplicable(ValueError):
+    """The operator does not have the Fourier x polynomial structure (la/tpmatrix.py: `SolverNotApplicable`)."""
+
+
+class WavenumberBandedSolver:
+    """`TPMatricesWavenumberSolver` (la/tpmatrix.py:686-1014 of the reference) on the device.
+
+    The systems are given in the separable form `tpmats_wavenumber_factor` derives (tpmatrix.py:1306-1347):
+    B_s = sum_t weights[t, s] * P_t with `diags[t]` the DIA data of P_t on the union `offsets`; s runs over the Fourier axes
+    of `shape` in C order.  Assembly, LU without pivoting and both substitution sweeps run in libjfx.so (`jfx_banded_*`,
+    csrc/kernels_banded.cu); `solve` takes the right-hand side in its natural layout (polynomial axis = `poly_axis`)."""
+
+    def __init__(self, poly_axis: int, shape, weights, diags, offsets):
+        self.poly_axis, self.shape = int(poly_axis) % len(shape), tuple(int(v) for v in shape)
+        self.offsets = tuple(int(o) for o in offsets)
+        n = self.shape[self.poly_axis]
+        n_sys = int(np.prod([v for a, v in enumerate(self.shape) if a != self.poly_axis], dtype=np.int64))
+        cplx = np.iscomplexobj(weights) or np.iscomplexobj(diags)
+        want = np.complex128 if cplx else np.float64
+        self.weights = np.ascontiguousarray(weights, dtype=want)
+        self.diags = np.ascontiguousarray(diags, dtype=want)
+        if self.weights.ndim != 2 or self.weights.shape[1] != n_sys:
+            raise ValueError(f"weights must be [n_terms, {n_sys}] (one column per Fourier wavenumber combination)")
+        if self.diags.shape != (self.weights.shape[0], len(self.offsets), n):
+            raise ValueError(f"diags must be [n_terms, n_diags, n] = {(self.weights.shape[0], len(self.offsets), n)}")
+        self.band_complex = bool(cplx)
+        self.n, self.n_sys = n, n_sys
+        self._lib = L.load()
+        self._handles: dict = {}
+
+    def _handle(self, dtype: int):
+        h = self._handles.get(dtype)
+        if h is None:
+            import ctypes as C
+            d = L.BandedDesc()
+            d.abi_version, d.dtype, d.band_complex = L.JFX_ABI_VERSION, int(dtype), int(self.band_complex)
+            d.n_terms, d.n, d.n_sys, d.n_diags = self.weights.shape[0], self.n, self.n_sys, len(self.offsets)
+            offs = (C.c_int32 * len(self.offsets))(*self.offsets)
+            d.offsets = offs
+            d.weights, d.diags = self.weights.ctypes.data, self.diags.ctypes.data
+            h = C.c_void_p()
+            rc = self._lib.jfx_banded_create(C.byref(d), C.byref(h))
+            if rc == -2:      # zero / non-finite pivot: the reference raises ValueError (la/diamatrix.py:461-471)
+                raise ValueError(self._lib.jfx_last_error().decode())
+            L.check(rc)
+            self._handles[dtype] = h
+        return h
+
+    def __del__(self):
+        try:
+            for h in self._handles.values():
+                self._lib.jfx_banded_destroy(h)
+            self._handles = {}
+        except Exception:
+            pass
+
+    def bandwidths(self, dtype: int = L.C128):
+        import ctypes as C
+        p, q, nb = C.c_int32(), C.c_int32(), C.c_size_t()
+        L.check(self._lib.jfx_banded_info(self._handle(dtype), C.byref(p), C.byref(q), C.byref(nb)))
+        return int(p.value), int(q.value), int(nb.value)
+
+    def factors(self, dtype: int = L.C128) -> np.ndarray:
+        """The factored band [n_sys, p + q + 1, n] (the reference's `band_lu` layout, la/tpmatrix.py:765-767) on the host."""
+        p, q, _ = self.bandwidths(dtype)
+        real = np.float64 if dtype in (L.F64, L.C128) else np.float32
+        et = (np.complex128 if real is np.float64 else np.complex64) if self.band_complex else real
+        buf = np.empty((p + q + 1, self.n, self.n_sys), dtype=et)
+        L.check(self._lib.jfx_banded_factors(self._handle(dtype), buf.ctypes.data))
+        return np.ascontiguousarray(np.transpose(buf, (2, 0, 1)))
+
+    def solve(self, rhs, out=None):
+        import ctypes as C
+
+        from ..engine import current_stream_ptr
+        if tuple(rhs.shape) != self.shape:
+            raise ValueError(f"right-hand side has shape {tuple(rhs.shape)}, the solver was built for {self.shape}")
+        if not getattr(rhs, "is_cuda", False):
+            raise L.JfxError(-3, "device path needs a CUDA tensor; jaxfun_b200 has no CPU fallback")
+        dt = jfx_dtype(rhs.dtype)
+        if self.band_complex and dt in (L.F32, L.F64):
+            raise TypeError("complex systems need a complex right-hand side")
+        rhs = rhs.contiguous()
+        if out is None:
+            import torch
+            out = torch.empty_like(rhs)
+        elif tuple(out.shape) != self.shape or out.dtype != rhs.dtype or out.device != rhs.device or not out.is_contiguous():
+            raise ValueError("out must be a contiguous array of the right-hand side's shape, dtype and device")
+        outer = int(np.prod(self.shape[:self.poly_axis], dtype=np.int64))
+        inner = int(np.prod(self.shape[self.poly_axis + 1:], dtype=np.int64))
+        L.check(self._lib.jfx_banded_solve(self._handle(dt), C.c_void_p(current_stream_ptr()), C.c_void_p(rhs.data_ptr()),
+                                           C.c_void_p(out.data_ptr()), outer, inner))
+        return out
+
+
+def tpmats_wavenumber_factor(terms) -> WavenumberBandedSolver:
+    """`tpmats_wavenumber_factor` (la/tpmatrix.py:1236-1354): `terms` = [(scale, [M_0, .., M_{d-1}]), ...] describes
+    sum_t scale_t * (M_0 x .. x M_{d-1}); a 1-D array M_a stands for a diagonal matrix.  Axes on which every term is
+    diagonal are the Fourier axes; exactly one other (banded) axis is required."""
+    if not isinstance(terms, (list, tuple)) or not terms or not all(isinstance(t, (list, tuple)) and len(t) == 2 for t in terms):
+        raise TypeError(f"tpmats_wavenumber_factor expects a list of (scale, matrices) terms, got {type(terms).__name__!r}.")
+    terms = [(complex(sc) if np.iscomplexobj(sc) else float(sc), [np.asarray(m) for m in mats]) for sc, mats in terms]
+    ndim = len(terms[0][1])
+
+    def diagonal(m):
+        return m.ndim == 1 or not np.any(m - np.diag(np.diagonal(m)))
+
+    diag_axes = [a for a in range(ndim) if all(diagonal(mats[a]) for _, mats in terms)]
+    poly_axes = [a for a in range(ndim) if a not in diag_axes]
+    if len(poly_axes) != 1:
+        raise SolverNotApplicable(f"tpmats_wavenumber_factor requires exactly 1 polynomial (non-diagonal) axis; found "
+                                  f"{len(poly_axes)}: {poly_axes}. Use KroneckerSumSolver for fully polynomial problems.")
+    pa = poly_axes[0]
+    shape = tuple(int(m.shape[0]) for m in terms[0][1])
+    W = []
+    for sc, mats in terms:                                   # tpmatrix.py:1306-1316: C order over the Fourier axes
+        w = np.array([sc])
+        for a in diag_axes:
+            dg = mats[a] if mats[a].ndim == 1 else np.diagonal(mats[a])
+            w = np.outer(w, dg).ravel()
+        W.append(w)
+    dias = [dia_from_dense(mats[pa]) for _, mats in terms]
+    offsets = tuple(sorted({o for offs, _ in dias for o in offs}))
+    P = np.zeros((len(terms), len(offsets), shape[pa]), dtype=np.result_type(*[d.dtype for _, d in dias]))
+    for t, (offs, data) in enumerate(dias):                  # tpmatrix.py:1330-1343: aligned to the union of offsets
+        for o, row in zip(offs, data):
+            P[t, offsets.index(o)] = row
+    return WavenumberBandedSolver(pa, shape, np.array(W), P, offsets)
+
+
+def _axis_matrices(space):
+    """(stiffness, mass) of one axis; Fourier axes give their diagonals (orthogonal exponentials: (e_l, e_k) = 2 pi / df,
+    second derivative -(k df)^2)."""
+    if getattr(space, "complex_data", False):
+        df = float(space.domain_factor)
+        k = np.asarray(space.wavenumbers(), dtype=float)
+        m = np.full(space.N, 2 * np.pi / df)
+        return -(k * df) ** 2 * m, m
+    return stiffness_matrix(space, 2), mass_matrix(space)
+
+
+def laplace_terms(T, alpha: float = 0.0):
+    """Terms of  (v, div grad u)_w + alpha (v, u)_w  on T: one Kronecker product per axis (+ the mass term)."""
+    mats = [_axis_matrices(s) for s in T.basespaces]
+    terms = [(1.0, [mats[j][0] if j == i else mats[j][1] for j in range(len(mats))]) for i in range(len(mats))]
+    if alpha:
+        terms.append((float(alpha), [m[1] for m in mats]))
+    return terms
+
+
+def poisson_solver(T):
+    """Solver of the weak Laplace operator  (v, div grad u)_w  on the tensor-product space T: per-wavenumber banded LU when
+    all axes but one are Fourier (`TPMatrices.lu_factor` dispatch, la/tpmatrix.py:396-427), per-axis diagonalisation otherwise."""
+    fourier = [bool(getattr(s, "complex_data", False)) for s in T.basespaces]
+    if any(fourier) and fourier.count(False) == 1:
+        return tpmats_wavenumber_factor(laplace_terms(T))
     return KroneckerSumSolver([(stiffness_matrix(s, 2), mass_matrix(s)) for s in T.basespaces])

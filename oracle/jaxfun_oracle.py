@@ -1167,3 +1167,102 @@ class DirectSumTPS:
 
     def forward(self, u):                                        # :788-790
         return self.from_orthogonal(self.orth.forward(u))
+
+
+# =================================================================================================
+# Wavenumber-batched banded solves of Fourier x polynomial systems  (la/tpmatrix.py, la/diamatrix.py)
+# Pinned: tests/golden/reference_banded.npz is produced by executing the reference's own
+# `_lu_banded_no_pivot_kernel` and `_make_wavenumber_vmap_solve` (function bodies taken from where they lie, on the numpy
+# stand-in for jax) — tests/golden/make_golden_banded.py; tests/test_banded_host.py replays it against these functions.
+# =================================================================================================
+def dia_from_dense(A, tol=0.0):
+    """(offsets, data) of a square matrix in the reference's column-aligned DIA form: data[d][j] = A[j - offsets[d], j]
+    (the band convention of la/diamatrix.py:1944: band[center + off, j] = A[j - off, j])."""
+    A = np.asarray(A)
+    n = A.shape[0]
+    scale = np.abs(A).max() if A.size else 0.0
+    offs, rows = [], []
+    for off in range(-(n - 1), n):
+        dg = np.diagonal(A, off)
+        if np.abs(dg).max(initial=0.0) > tol * scale:
+            row = np.zeros(n, dtype=A.dtype)
+            if off >= 0:
+                row[off:] = dg           # entry (j - off, j) for j = off .. n-1
+            else:
+                row[:n + off] = dg       # entry (j - off, j) for j = 0 .. n-1+off
+            offs.append(off)
+            rows.append(row)
+    return tuple(offs), np.array(rows)
+
+
+def wavenumber_band_data(W, P):
+    """B_data_batch[k, d, :] = sum_t W[t, k] * P[t, d, :]   (la/tpmatrix.py:1345-1347)."""
+    return np.einsum("tf,tdp->fdp", np.asarray(W), np.asarray(P))
+
+
+def banded_lu_no_pivot(data, offsets):
+    """Batched LU without pivoting of banded matrices given as DIA data [n_sys, n_diags, n] on `offsets`
+    (la/tpmatrix.py:743-768 -> la/diamatrix.py:1937-1973).  Returns (band_lu [n_sys, p + q + 1, n], p, q) with
+    band[center + off, j] = entry (j - off, j), center = p: rows below center = multipliers of L, rows >= center = U."""
+    data = np.asarray(data)
+    n_sys, _, n = data.shape
+    p = max((-o for o in offsets if o < 0), default=0)
+    q = max((o for o in offsets if o > 0), default=0)
+    center = p
+    band = np.zeros((n_sys, p + q + 1, n), dtype=data.dtype)
+    for d, off in enumerate(offsets):
+        band[:, center + off, :] = data[:, d, :]
+    for k in range(n):
+        pivot = band[:, center, k]
+        for s in range(1, p + 1):
+            if k + s >= n:
+                continue
+            with np.errstate(divide="ignore", invalid="ignore"):
+                f = band[:, center - s, k] / pivot        # a zero pivot is reported by the caller (WavenumberSolver)
+            band[:, center - s, k] = f
+            for u in range(1, q + 1):
+                j = k + u
+                if j < n:
+                    band[:, center + u - s, j] -= f * band[:, center + u, j]
+    return band, p, q
+
+
+def banded_solve(band_lu, p, q, rhs):
+    """Forward elimination and back substitution for every system (la/tpmatrix.py:637-680): band_lu [n_sys, p + q + 1, n],
+    rhs [n_sys, n] -> x [n_sys, n]."""
+    n_sys, _, n = band_lu.shape
+    y = np.zeros((n_sys, n), dtype=np.result_type(band_lu.dtype, rhs.dtype))
+    for i in range(n):
+        acc = np.zeros(n_sys, dtype=y.dtype)
+        for s in range(1, min(p, i) + 1):
+            acc += band_lu[:, p - s, i - s] * y[:, i - s]        # L[i, i-s] at band[center - s][i - s]
+        y[:, i] = rhs[:, i] - acc
+    x = np.zeros_like(y)
+    for i in range(n - 1, -1, -1):
+        acc = np.zeros(n_sys, dtype=y.dtype)
+        for s in range(1, min(q, n - 1 - i) + 1):
+            acc += band_lu[:, p + s, i + s] * x[:, i + s]        # U[i, i+s] at band[center + s][i + s]
+        x[:, i] = (y[:, i] - acc) / band_lu[:, p, i]
+    return x
+
+
+class WavenumberSolver:
+    """`TPMatricesWavenumberSolver` (la/tpmatrix.py:686-1014) from the separable form of `tpmats_wavenumber_factor`
+    (:1236-1354): systems flattened in C order over the Fourier axes, polynomial axis = `poly_axis` of `shape`."""
+
+    def __init__(self, poly_axis, shape, W, P, offsets):
+        self.poly_axis, self.shape, self.offsets = int(poly_axis), tuple(shape), tuple(int(o) for o in offsets)
+        self.band_lu, self.p, self.q = banded_lu_no_pivot(wavenumber_band_data(W, P), self.offsets)
+        d = np.abs(self.band_lu[:, self.p, :])
+        if not np.all(np.isfinite(self.band_lu[:, self.p, :])) or d.min() == 0.0:
+            raise ValueError("Matrix is singular or has a zero/non-finite pivot in LU factorisation without pivoting.")
+
+    def solve(self, rhs):
+        rhs = np.asarray(rhs)
+        nd = rhs.ndim
+        order = [a for a in range(nd) if a != self.poly_axis] + [self.poly_axis]      # tpmatrix.py:931-939
+        inv = np.argsort(order)
+        r2 = np.transpose(rhs, order)
+        fshape = r2.shape[:-1]
+        x = banded_solve(self.band_lu, self.p, self.q, r2.reshape(-1, rhs.shape[self.poly_axis]))
+        return np.transpose(x.reshape(fshape + (rhs.shape[self.poly_axis],)), inv)

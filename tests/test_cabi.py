@@ -39,7 +39,8 @@ def test_struct_layout_matches_header():
     import tempfile
     from jaxfun_b200 import _lib
     code = ('#include "jfx.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(jfx_axis_desc),'
-            'sizeof(jfx_plan_desc), sizeof(jfx_nonlinear_desc), sizeof(jfx_pw_instr));return 0;}\n')
+            'sizeof(jfx_plan_desc), sizeof(jfx_nonlinear_desc), sizeof(jfx_pw_instr));'
+            'printf("%zu\\n", sizeof(jfx_banded_desc));return 0;}\n')
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "s.c")
         open(src, "w").write(code)
@@ -47,7 +48,7 @@ def test_struct_layout_matches_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
     assert sizes == [C.sizeof(_lib.AxisDesc), C.sizeof(_lib.PlanDesc), C.sizeof(_lib.NonlinearDesc),
-                     C.sizeof(_lib.PwInstr)]
+                     C.sizeof(_lib.PwInstr), C.sizeof(_lib.BandedDesc)]
 
 
 def test_no_cpu_fallback():
