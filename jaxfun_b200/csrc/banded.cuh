@@ -12,6 +12,22 @@
 #define JFX_HD inline
 #endif
 
+// Optional software prefetch of the sweeps (build switch, OFF by default): every chunk asks for the lines it will need
+// JFX_BANDED_PF steps later (prefetch.global.L2: no register, no dependency).  Measured on the B200 (profiles/r2_banded.txt):
+// distances 32 / 64 / 128 and the L1 variant are 10-25 % SLOWER than no prefetch on every shape but 4096 x 4094 (5 % faster).
+// On the host (emulation) it is a no-op.
+#ifndef JFX_BANDED_PF
+#define JFX_BANDED_PF 0
+#endif
+#ifndef JFX_BANDED_PF_INSTR
+#define JFX_BANDED_PF_INSTR "prefetch.global.L2"
+#endif
+#if defined(__CUDA_ARCH__)
+#define JFX_BANDED_PREFETCH(ptr) asm volatile(JFX_BANDED_PF_INSTR " [%0];" ::"l"(ptr))
+#else
+#define JFX_BANDED_PREFETCH(ptr) ((void)(ptr))
+#endif
+
 namespace jfx {
 namespace banded {
 
@@ -50,6 +66,16 @@ struct BA {
       acc.re -= l.re * w.re - l.im * w.im;
       acc.im -= l.re * w.im + l.im * w.re;
     }
+  }
+  static JFX_HD E recip(const E& d) {
+    if constexpr (!EC) return R(1) / d;
+    else return cx_div(Cx<R>{R(1), R(0)}, d);
+  }
+  // a * r
+  static JFX_HD X mul(const X& a, const E& r) {
+    if constexpr (!XC) return a * r;
+    else if constexpr (!EC) return X{a.re * r, a.im * r};
+    else return X{a.re * r.re - a.im * r.im, a.re * r.im + a.im * r.re};
   }
   static JFX_HD X div(const X& a, const E& d) {
     if constexpr (!XC) return a / d;
@@ -120,7 +146,7 @@ JFX_HD bool factor_system(BandElem<R, EC>* lu, int64_t n, int64_t n_sys, int p, 
 // [outer, n, inner] with s = o * inner + i.  W > 0: p, q <= W, window in registers, the loads of U consecutive steps are
 // issued before their dependent arithmetic.  W == 0: any bandwidth, earlier unknowns are read back from `out`.
 // `rhs` may equal `out` (every step reads its right-hand-side entries before it writes them).
-template <typename R, bool EC, bool XC, int W, int U>
+template <typename R, bool EC, bool XC, int W, int U, bool DB = true>
 JFX_HD void solve_system(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>::X* rhs, typename BA<R, EC, XC>::X* out,
                          int64_t n, int64_t n_sys, int64_t inner, int p, int q, int64_t s) {
   using A = BA<R, EC, XC>;
@@ -133,13 +159,27 @@ JFX_HD void solve_system(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>
   auto ld = [&](int row, int64_t j) -> E { return Ls[((int64_t)row * n + j) * n_sys]; };
 
   if constexpr (W > 0) {
+    // The loads of a chunk (U steps: right-hand side and matrix entries) do not depend on the recurrence.  Two register
+    // buffers alternate: the loads of chunk c + 1 are issued before the dependent arithmetic of chunk c, so they are in flight
+    // while it runs.  The reciprocal of the U diagonal is formed in the load phase, off the dependent chain (the sweep
+    // multiplies by it: one rounding more than the reference's division, far inside the 1e-12 bar).
     X win[W];
 #pragma unroll
     for (int t = 0; t < W; ++t) win[t] = A::xzero();
     // forward elimination: y_j = b_j - sum_{t=1..p} L[j, j-t] y_{j-t},   L[j, j-t] = band[p - t][j - t]
-    for (int64_t j0 = 0; j0 < n; j0 += U) {
-      X bv[U];
-      E lv[U][W];
+    auto load_fwd = [&](int64_t j0, X (&bv)[U], E (&lv)[U][W]) {
+      if constexpr (JFX_BANDED_PF > 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t j = j0 + u + JFX_BANDED_PF;
+          if (j < n) {
+            JFX_BANDED_PREFETCH(b + j * inner);
+#pragma unroll
+            for (int t = 1; t <= W; ++t)
+              if (t <= p) JFX_BANDED_PREFETCH(Ls + ((int64_t)(p - t) * n + (j - t)) * n_sys);
+          }
+        }
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t j = j0 + u;
@@ -153,6 +193,8 @@ JFX_HD void solve_system(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>
             if (t <= p && j - t >= 0) lv[u][t - 1] = ld(p - t, j - t);
         }
       }
+    };
+    auto run_fwd = [&](int64_t j0, const X (&bv)[U], const E (&lv)[U][W]) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t j = j0 + u;
@@ -166,28 +208,65 @@ JFX_HD void solve_system(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>
           x[j * inner] = y;
         }
       }
+    };
+    if constexpr (DB) {
+      X bva[U], bvb[U];
+      E lva[U][W], lvb[U][W];
+      load_fwd(0, bva, lva);
+      for (int64_t j0 = 0; j0 < n; j0 += 2 * U) {
+        load_fwd(j0 + U, bvb, lvb);
+        run_fwd(j0, bva, lva);
+        load_fwd(j0 + 2 * U, bva, lva);
+        run_fwd(j0 + U, bvb, lvb);
+      }
+    } else {
+      X bva[U];
+      E lva[U][W];
+      for (int64_t j0 = 0; j0 < n; j0 += U) {
+        load_fwd(j0, bva, lva);
+        run_fwd(j0, bva, lva);
+      }
     }
-    // back substitution: x_j = (y_j - sum_{t=1..q} U[j, j+t] x_{j+t}) / U[j, j],   U[j, j+t] = band[p + t][j + t]
+    // back substitution: x_j = (y_j - sum_{t=1..q} U[j, j+t] x_{j+t}) / U[j, j],   U[j, j+t] = band[p + t][j + t];
+    // a chunk covers j = j1 - 1 down to j1 - U
 #pragma unroll
     for (int t = 0; t < W; ++t) win[t] = A::xzero();
-    for (int64_t j1 = n; j1 > 0; j1 -= U) {
-      X yv[U];
-      E uv[U][W], dv[U];
+    auto load_bwd = [&](int64_t j1, X (&yv)[U], E (&uv)[U][W], E (&rd)[U]) {
+      if constexpr (JFX_BANDED_PF > 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t j = j1 - 1 - u - JFX_BANDED_PF;
+          if (j >= 0) {
+            JFX_BANDED_PREFETCH(x + j * inner);
+            JFX_BANDED_PREFETCH(Ls + ((int64_t)p * n + j) * n_sys);
+#pragma unroll
+            for (int t = 1; t <= W; ++t)
+              if (t <= q) JFX_BANDED_PREFETCH(Ls + ((int64_t)(p + t) * n + (j + t)) * n_sys);
+          }
+        }
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t j = j1 - 1 - u;
         yv[u] = A::xzero();
-        dv[u] = A::ezero();
+        rd[u] = A::ezero();
 #pragma unroll
         for (int t = 1; t <= W; ++t) uv[u][t - 1] = A::ezero();
         if (j >= 0) {
           yv[u] = x[j * inner];
-          dv[u] = ld(p, j);
+          rd[u] = ld(p, j);
 #pragma unroll
           for (int t = 1; t <= W; ++t)
             if (t <= q && j + t < n) uv[u][t - 1] = ld(p + t, j + t);
         }
       }
+      // reciprocals only after EVERY load of the chunk has been issued: the first one waits for its diagonal entry, and the
+      // issue is in order (with the reciprocal inside the loop above each step paid its own DRAM latency)
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (j1 - 1 - u >= 0) rd[u] = A::recip(rd[u]);
+    };
+    auto run_bwd = [&](int64_t j1, const X (&yv)[U], const E (&uv)[U][W], const E (&rd)[U]) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int64_t j = j1 - 1 - u;
@@ -195,12 +274,30 @@ JFX_HD void solve_system(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>
           X v = yv[u];
 #pragma unroll
           for (int t = 1; t <= W; ++t) A::msub(v, uv[u][t - 1], win[t - 1]);
-          v = A::div(v, dv[u]);
+          v = A::mul(v, rd[u]);
 #pragma unroll
           for (int t = W - 1; t > 0; --t) win[t] = win[t - 1];
           win[0] = v;
           x[j * inner] = v;
         }
+      }
+    };
+    if constexpr (DB) {
+      X yva[U], yvb[U];
+      E uva[U][W], uvb[U][W], rda[U], rdb[U];
+      load_bwd(n, yva, uva, rda);
+      for (int64_t j1 = n; j1 > 0; j1 -= 2 * U) {
+        load_bwd(j1 - U, yvb, uvb, rdb);
+        run_bwd(j1, yva, uva, rda);
+        load_bwd(j1 - 2 * U, yva, uva, rda);
+        run_bwd(j1 - U, yvb, uvb, rdb);
+      }
+    } else {
+      X yva[U];
+      E uva[U][W], rda[U];
+      for (int64_t j1 = n; j1 > 0; j1 -= U) {
+        load_bwd(j1, yva, uva, rda);
+        run_bwd(j1, yva, uva, rda);
       }
     }
   } else {
@@ -219,12 +316,24 @@ JFX_HD void solve_system(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>
   }
 }
 
-// register-window width and chunk length for a bandwidth: (W, U) = (2, 8), (4, 4), (8, 2), else the generic path (0, 1)
+// register-window width W and chunk length U for a bandwidth; wider than 8: the generic path (0, 1)
+#ifndef JFX_BANDED_U2
+#define JFX_BANDED_U2 12   /* measured 8 / 12 / 16: 12 is fastest on every shape but 4096 x 4094 (profiles/r2_banded.txt) */
+#endif
+#ifndef JFX_BANDED_U4
+#define JFX_BANDED_U4 4
+#endif
+#ifndef JFX_BANDED_U8
+#define JFX_BANDED_U8 2
+#endif
+#ifndef JFX_BANDED_DB
+#define JFX_BANDED_DB 0   /* measured: a second register buffer does not hide a DRAM latency (profiles/r2_banded.txt) */
+#endif
 template <typename F> inline void dispatch_window(int p, int q, F&& f) {
   const int w = p > q ? p : q;
-  if (w <= 2) f(std::integral_constant<int, 2>{}, std::integral_constant<int, 8>{});
-  else if (w <= 4) f(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{});
-  else if (w <= 8) f(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
+  if (w <= 2) f(std::integral_constant<int, 2>{}, std::integral_constant<int, JFX_BANDED_U2>{});
+  else if (w <= 4) f(std::integral_constant<int, 4>{}, std::integral_constant<int, JFX_BANDED_U4>{});
+  else if (w <= 8) f(std::integral_constant<int, 8>{}, std::integral_constant<int, JFX_BANDED_U8>{});
   else f(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});
 }
 

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) banded_solve_kernel(const BandElem<R, EC>
                                                            int64_t inner, int p, int q) {
   const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (s >= n_sys) return;
-  banded::solve_system<R, EC, XC, W, U>(lu, rhs, out, n, n_sys, inner, p, q, s);
+  banded::solve_system<R, EC, XC, W, U, (JFX_BANDED_DB != 0)>(lu, rhs, out, n, n_sys, inner, p, q, s);
 }
 
 template <typename R, bool EC, bool XC>

@@ -169,6 +169,13 @@ class Plan:
         x = x.contiguous()
         if out is None:
             out = torch.empty(self.shape_out, dtype=x.dtype, device=x.device)
+        elif (tuple(out.shape) != self.shape_out or out.dtype != x.dtype or out.device != x.device
+              or not out.is_contiguous()):
+            # the kernels write shape_out elements of the plan's dtype through a raw pointer: anything else would be silent
+            # memory corruption
+            raise ValueError(f"out must be a contiguous {x.dtype} array of shape {self.shape_out} on {x.device}")
+        elif out.data_ptr() == x.data_ptr():
+            raise ValueError("a transform cannot run in place: out must not alias the input")
         ws = self.workspace(x.device)
         L.check(self._lib.jfx_execute(self._h, C.c_void_p(current_stream_ptr()), C.c_void_p(x.data_ptr()),
                                       C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr() if ws is not None else 0)))

@@ -35,7 +35,7 @@ static int run(int n_terms, int64_t n, int64_t n_sys, int n_diags, const int* of
   if (flag) return 1;
   dispatch_window(p, q, [&](auto w, auto u) {
     for (int64_t s = 0; s < n_sys; ++s)
-      solve_system<R, EC, XC, decltype(w)::value, decltype(u)::value>(lu.data(), static_cast<const X*>(rhs), static_cast<X*>(out),
+      solve_system<R, EC, XC, decltype(w)::value, decltype(u)::value, (JFX_BANDED_DB != 0)>(lu.data(), static_cast<const X*>(rhs), static_cast<X*>(out),
                                                                       n, n_sys, inner, p, q, s);
   });
   return 0;
