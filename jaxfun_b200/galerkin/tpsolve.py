@@ -135,6 +135,21 @@ class WavenumberBandedSolver:
         self._lib = L.load()
         self._handles: dict = {}
 
+    def shard(self, rank: int, size: int) -> "WavenumberBandedSolver":
+        """The solver of rank `rank`'s block of a coefficient array slab-sharded along axis 0 into `size` equal blocks — the
+        multi-device mode of the reference (la/tpmatrix.py:786-812, 985-1013): axis 0 must be a Fourier axis, every device
+        keeps the factors of its own contiguous block of wavenumbers and the solve needs no communication."""
+        if self.poly_axis == 0:
+            raise ValueError(f"Multi-process solve requires axis 0 to be a Fourier axis (poly_axis=0 not supported). "
+                             f"Got shape={self.shape}, poly_axis={self.poly_axis}.")
+        n0 = self.shape[0]
+        if not 0 <= rank < size or n0 % size:
+            raise ValueError(f"axis 0 of extent {n0} cannot be split into {size} equal blocks (rank {rank})")
+        per = self.n_sys // size                     # C order over the Fourier axes: a block of axis 0 is a contiguous range
+        local_shape = (n0 // size,) + self.shape[1:]
+        return WavenumberBandedSolver(self.poly_axis, local_shape, self.weights[:, rank * per:(rank + 1) * per], self.diags,
+                                      self.offsets)
+
     def _handle(self, dtype: int):
         h = self._handles.get(dtype)
         if h is None:

@@ -72,6 +72,16 @@ def test_banded_zero_pivot_is_refused(cuda):
             torch.ones(3, 6, dtype=torch.float64, device=cuda))
 
 
+def test_banded_sharded_blocks_reproduce_the_global_solve(cuda):
+    """la/tpmatrix.py:985-1013: every rank solves its own block of axis 0 with its own factors, no communication."""
+    shape, pa, offsets, W, P, rhs = make_case("3d_last")
+    S0 = S.WavenumberBandedSolver(pa, shape, W, P, offsets)
+    full = S0.solve(dev(rhs, cuda))
+    size = 3
+    parts = [S0.shard(r, size).solve(dev(rhs[r * 2:(r + 1) * 2], cuda)) for r in range(size)]
+    assert torch.equal(torch.cat(parts, dim=0), full)
+
+
 def test_banded_in_cuda_graph(cuda):
     """jfx_banded_solve only enqueues one launch: it can be captured and replayed."""
     shape, pa, offsets, W, P, rhs = make_case("2d_last_penta")

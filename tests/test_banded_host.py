@@ -115,6 +115,32 @@ def test_wavenumber_factor_assembly_matches_kron():
     assert isinstance(S.poisson_solver(jf.TensorProduct(jf.Fourier(6), D)), S.WavenumberBandedSolver)
 
 
+def test_sharded_solver_blocks():
+    """`shard(rank, size)`: the blocks of the reference's multi-device mode (la/tpmatrix.py:786-812) — contiguous wavenumber
+    ranges of axis 0; together they reproduce the global solve (checked with the oracle); poly_axis = 0 is refused."""
+    from jaxfun_b200.galerkin.tpsolve import WavenumberBandedSolver
+    rng = np.random.default_rng(4)
+    shape, pa, offsets = (8, 6, 11), 2, (-2, 0, 2)
+    P = rng.standard_normal((2, 3, 11))
+    P[0, 1] += 12
+    W = np.abs(rng.standard_normal((2, 48))) + 1
+    S = WavenumberBandedSolver(pa, shape, W, P, offsets)
+    rhs = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    full = O.WavenumberSolver(pa, shape, W, P, offsets).solve(rhs)
+    for size in (2, 4):
+        parts = []
+        for r in range(size):
+            Sr = S.shard(r, size)
+            assert Sr.shape == (8 // size, 6, 11) and Sr.n_sys == 48 // size
+            blk = slice(r * 8 // size, (r + 1) * 8 // size)
+            parts.append(O.WavenumberSolver(pa, Sr.shape, Sr.weights, Sr.diags, Sr.offsets).solve(rhs[blk]))
+        assert np.allclose(np.concatenate(parts, axis=0), full, rtol=0, atol=1e-14)
+    with pytest.raises(ValueError, match="axis 0"):
+        WavenumberBandedSolver(0, (11, 6), W[:, :6], P, offsets).shard(0, 2)
+    with pytest.raises(ValueError):
+        S.shard(0, 3)
+
+
 def test_banded_cabi_argument_checks_and_no_cpu_fallback():
     import torch
     from jaxfun_b200 import _lib
