@@ -164,3 +164,25 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(JfxNonlinear, JfxNonlinearImpl,
                                   .Ret<ffi::AnyBuffer>()
                                   .Attr<int64_t>("nonlinear"),
                               {xla::ffi::Traits::kCmdBufferCompatible});
+
+// ---- wavenumber-batched banded solve (la/tpmatrix.py:982-1013: TPMatricesWavenumberSolver.solve) ---------------------------
+// The jfx_banded object (assembled and factored on this device by jfx_banded_create when the solver object is built on the
+// Python side, from W / P_data_stack / poly_offsets of tpmats_wavenumber_factor) travels as a per-process handle like the
+// nonlinear objects.  `outer` / `inner` place the polynomial axis inside the array (outer * n * inner elements): the
+// transposes of tpmatrix.py:963-977 do not exist here.  One launch, no allocation, no synchronisation.
+static ffi::Error JfxBandedSolveImpl(cudaStream_t stream, ffi::AnyBuffer rhs, ffi::Result<ffi::AnyBuffer> out, int64_t handle,
+                                     int64_t outer, int64_t inner) {
+  const jfx_banded* b = reinterpret_cast<const jfx_banded*>(static_cast<intptr_t>(handle));
+  const int rc = jfx_banded_solve(b, stream, rhs.untyped_data(), out->untyped_data(), outer, inner);
+  if (rc != JFX_OK) return ffi::Error(rc == JFX_ERR_INVALID ? ffi::ErrorCode::kInvalidArgument : ffi::ErrorCode::kInternal, jfx_last_error());
+  return ffi::Error::Success();
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JfxBandedSolve, JfxBandedSolveImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int64_t>("handle")
+                                  .Attr<int64_t>("outer")
+                                  .Attr<int64_t>("inner"),
+                              {xla::ffi::Traits::kCmdBufferCompatible});
