@@ -316,6 +316,162 @@ JFX_HD void solve_system(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>
   }
 }
 
+// ---- polynomial axis LAST (inner == 1): one WARP owns 32 consecutive systems = 32 consecutive rows of the array --------
+// With one thread per row every warp load touches 32 different 128-byte lines (measured: 0.35 of HBM against 0.67 for the
+// coalesced layouts, the load / store unit is the limit).  Here the warp moves a [32 rows x C steps] tile between global and
+// shared memory with row-contiguous accesses (128 bytes per row and chunk for complex128, 64 for the narrower types), each
+// lane sweeps its own row inside the tile, and the tile goes back the same way.  The matrix entries are loaded directly (they
+// are coalesced across systems already).  The phases are separated by __syncwarp only.
+// Host emulation: the lane loop replaces the 32 threads, per-lane state is an array.
+#if defined(__CUDA_ARCH__)
+#define JFX_BANDED_FOR_LANES(lane) for (int lane = (int)(threadIdx.x & 31u), once_ = 1; once_; once_ = 0)
+#define JFX_BANDED_LI(lane) 0
+#define JFX_BANDED_NSTATE 1
+#define JFX_BANDED_SYNC() __syncwarp()
+#else
+#define JFX_BANDED_FOR_LANES(lane) for (int lane = 0; lane < 32; ++lane)
+#define JFX_BANDED_LI(lane) (lane)
+#define JFX_BANDED_NSTATE 32
+#define JFX_BANDED_SYNC() ((void)0)
+#endif
+
+template <typename R, bool EC, bool XC> constexpr int rows_chunk() {
+  return sizeof(typename BA<R, EC, XC>::X) >= 8 ? 8 : 16;   // 128-byte row segments for complex128, 64 bytes otherwise (registers)
+}
+template <typename R, bool EC, bool XC> constexpr int rows_pitch() { return rows_chunk<R, EC, XC>() + 1; }   // conflict-free
+
+template <typename R, bool EC, bool XC, int W>
+JFX_HD void solve_rows_warp(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>::X* rhs, typename BA<R, EC, XC>::X* out,
+                            int64_t n, int64_t n_sys, int p, int q, int64_t s0, typename BA<R, EC, XC>::X* tile) {
+  using A = BA<R, EC, XC>;
+  using E = typename A::E;
+  using X = typename A::X;
+  constexpr int C = rows_chunk<R, EC, XC>();
+  constexpr int LD = rows_pitch<R, EC, XC>();
+  const int64_t nchunks = (n + C - 1) / C;
+  X win[JFX_BANDED_NSTATE][W];
+  JFX_BANDED_FOR_LANES(lane) {
+#pragma unroll
+    for (int t = 0; t < W; ++t) win[JFX_BANDED_LI(lane)][t] = A::xzero();
+  }
+  auto tile_in = [&](const X* src, int64_t j0) {
+    JFX_BANDED_FOR_LANES(lane) {
+#pragma unroll
+      for (int it = 0; it < C; ++it) {
+        const int e = it * 32 + lane, row = e / C, col = e % C;
+        const int64_t s = s0 + row, j = j0 + col;
+        if (s < n_sys && j < n) tile[row * LD + col] = src[s * n + j];
+      }
+    }
+    JFX_BANDED_SYNC();
+  };
+  auto tile_out = [&](int64_t j0) {
+    JFX_BANDED_SYNC();
+    JFX_BANDED_FOR_LANES(lane) {
+#pragma unroll
+      for (int it = 0; it < C; ++it) {
+        const int e = it * 32 + lane, row = e / C, col = e % C;
+        const int64_t s = s0 + row, j = j0 + col;
+        if (s < n_sys && j < n) out[s * n + j] = tile[row * LD + col];
+      }
+    }
+    JFX_BANDED_SYNC();
+  };
+  // forward elimination
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t j0 = c * C;
+    tile_in(rhs, j0);
+    JFX_BANDED_FOR_LANES(lane) {
+      const int64_t s = s0 + lane;
+      if (s < n_sys) {
+        const E* Ls = lu + s;
+        X* w = win[JFX_BANDED_LI(lane)];
+        E lv[C][W];
+#pragma unroll
+        for (int u = 0; u < C; ++u) {
+          const int64_t j = j0 + u;
+#pragma unroll
+          for (int t = 1; t <= W; ++t) {
+            lv[u][t - 1] = A::ezero();
+            if (j < n && t <= p && j - t >= 0) lv[u][t - 1] = Ls[((int64_t)(p - t) * n + (j - t)) * n_sys];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < C; ++u) {
+          if (j0 + u < n) {
+            X y = tile[lane * LD + u];
+#pragma unroll
+            for (int t = 1; t <= W; ++t) A::msub(y, lv[u][t - 1], w[t - 1]);
+#pragma unroll
+            for (int t = W - 1; t > 0; --t) w[t] = w[t - 1];
+            w[0] = y;
+            tile[lane * LD + u] = y;
+          }
+        }
+      }
+    }
+    tile_out(j0);
+  }
+  // back substitution, chunks from the top, steps inside a chunk from the top
+  JFX_BANDED_FOR_LANES(lane) {
+#pragma unroll
+    for (int t = 0; t < W; ++t) win[JFX_BANDED_LI(lane)][t] = A::xzero();
+  }
+  for (int64_t c = nchunks - 1; c >= 0; --c) {
+    const int64_t j0 = c * C;
+    tile_in(out, j0);
+    JFX_BANDED_FOR_LANES(lane) {
+      const int64_t s = s0 + lane;
+      if (s < n_sys) {
+        const E* Ls = lu + s;
+        X* w = win[JFX_BANDED_LI(lane)];
+        E uv[C][W], rd[C];
+#pragma unroll
+        for (int u = 0; u < C; ++u) {
+          const int64_t j = j0 + u;
+          rd[u] = A::ezero();
+          if (j < n) rd[u] = Ls[((int64_t)p * n + j) * n_sys];
+#pragma unroll
+          for (int t = 1; t <= W; ++t) {
+            uv[u][t - 1] = A::ezero();
+            if (j < n && t <= q && j + t < n) uv[u][t - 1] = Ls[((int64_t)(p + t) * n + (j + t)) * n_sys];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < C; ++u)
+          if (j0 + u < n) rd[u] = A::recip(rd[u]);
+#pragma unroll
+        for (int u = C - 1; u >= 0; --u) {
+          if (j0 + u < n) {
+            X v = tile[lane * LD + u];
+#pragma unroll
+            for (int t = 1; t <= W; ++t) A::msub(v, uv[u][t - 1], w[t - 1]);
+            v = A::mul(v, rd[u]);
+#pragma unroll
+            for (int t = W - 1; t > 0; --t) w[t] = w[t - 1];
+            w[0] = v;
+            tile[lane * LD + u] = v;
+          }
+        }
+      }
+    }
+    tile_out(j0);
+  }
+}
+
+// The row-tile variant serves bandwidths up to 4 on arrays whose polynomial axis is last, when there are enough systems to fill
+// the GPU with warps (its chunks are 8 steps, so with few warps it is MORE latency-bound than one thread per system: measured
+// 470 vs 292 us for 1024 systems, 456 vs 518 us for 65 536).  Build switches: JFX_BANDED_ROWS=0 off, JFX_BANDED_ROWS_MIN.
+#ifndef JFX_BANDED_ROWS
+#define JFX_BANDED_ROWS 1
+#endif
+#ifndef JFX_BANDED_ROWS_MIN
+#define JFX_BANDED_ROWS_MIN (148 * 128)
+#endif
+inline bool rows_variant_applies(int64_t inner, int p, int q, int64_t n_sys) {
+  return JFX_BANDED_ROWS && inner == 1 && (p > q ? p : q) <= 4 && n_sys >= JFX_BANDED_ROWS_MIN;
+}
+
 // register-window width W and chunk length U for a bandwidth; wider than 8: the generic path (0, 1)
 #ifndef JFX_BANDED_U2
 #define JFX_BANDED_U2 12   /* measured 8 / 12 / 16: 12 is fastest on every shape but 4096 x 4094 (profiles/r2_banded.txt) */

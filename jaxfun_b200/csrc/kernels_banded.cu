@@ -67,11 +67,39 @@ __global__ void __launch_bounds__(128) banded_solve_kernel(const BandElem<R, EC>
   banded::solve_system<R, EC, XC, W, U, (JFX_BANDED_DB != 0)>(lu, rhs, out, n, n_sys, inner, p, q, s);
 }
 
+// polynomial axis last: one warp per 32 consecutive rows, tiles staged through shared memory (banded.cuh: solve_rows_warp)
+template <typename R, bool EC, bool XC, int W>
+__global__ void __launch_bounds__(128) banded_solve_rows_kernel(const BandElem<R, EC>* __restrict__ lu,
+                                                                const typename BA<R, EC, XC>::X* rhs,
+                                                                typename BA<R, EC, XC>::X* out, int64_t n, int64_t n_sys,
+                                                                int p, int q) {
+  using X = typename BA<R, EC, XC>::X;
+  constexpr int TILE = 32 * banded::rows_pitch<R, EC, XC>();
+  __shared__ X tiles[4 * TILE];
+  const int warp = (int)(threadIdx.x >> 5);
+  const int64_t s0 = (blockIdx.x * (int64_t)(blockDim.x >> 5) + warp) * 32;
+  if (s0 >= n_sys) return;
+  banded::solve_rows_warp<R, EC, XC, W>(lu, rhs, out, n, n_sys, p, q, s0, tiles + warp * TILE);
+}
+
 template <typename R, bool EC, bool XC>
 int launch_solve_t(cudaStream_t st, const jfx_banded* b, const void* rhs, void* out, int64_t inner) {
   using A = BA<R, EC, XC>;
   using E = typename A::E;
   using X = typename A::X;
+  if (banded::rows_variant_applies(inner, b->p, b->q, b->n_sys)) {
+    const int wpc = 4;   // 4 warps of 32 rows per CTA
+    const unsigned nb = (unsigned)((b->n_sys + 32 * wpc - 1) / (32 * wpc));
+    const E* lu_ = static_cast<const E*>(b->lu);
+    if (b->p <= 2 && b->q <= 2)
+      banded_solve_rows_kernel<R, EC, XC, 2><<<nb, 32 * wpc, 0, st>>>(lu_, static_cast<const X*>(rhs), static_cast<X*>(out), b->n,
+                                                                    b->n_sys, b->p, b->q);
+    else
+      banded_solve_rows_kernel<R, EC, XC, 4><<<nb, 32 * wpc, 0, st>>>(lu_, static_cast<const X*>(rhs), static_cast<X*>(out), b->n,
+                                                                    b->n_sys, b->p, b->q);
+    JFX_CUDA_OK(cudaGetLastError());
+    return JFX_OK;
+  }
   // few systems: small CTAs so that they spread over the SMs; many: 128 threads
   const int threads = b->n_sys >= 148 * 128 ? 128 : (b->n_sys >= 148 * 64 ? 64 : 32);
   const unsigned blocks = (unsigned)((b->n_sys + threads - 1) / threads);

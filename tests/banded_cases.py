@@ -20,6 +20,10 @@ CASES = {
     "lower_only":         ((6, 12), 1, (-3, -1, 0), 1, False, "complex128"),
     "diagonal":           ((6, 12), 1, (0,), 2, False, "complex128"),
     "n_one":              ((9, 1), 1, (0,), 1, False, "float64"),
+    "rows_kernel_w2":     ((19000, 21), 1, (-2, 0, 2), 2, False, "complex128"),     # enough systems for the row-tile kernel on the GPU
+    "rows_kernel_w4":     ((593, 33, 13), 2, (-4, -1, 0, 3), 2, True, "complex128"),
+    "rows_kernel_f64":    ((19010, 19), 1, (-1, 0, 1), 1, False, "float64"),
+    "rows_kernel_c64":    ((19010, 18), 1, (-2, 0, 2), 2, False, "complex64"),
     "many_systems":       ((300, 20), 1, (-2, 0, 2), 2, False, "complex128"),      # several CTAs, ragged last one
 }
 

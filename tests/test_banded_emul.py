@@ -25,11 +25,11 @@ def emul(tmp_path_factory):
     lib = C.CDLL(so)
     lib.banded_emul.restype = C.c_int
     lib.banded_emul.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int32), C.c_void_p,
-                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
     return lib
 
 
-def run_emul(lib, shape, pa, offsets, W, P, rhs, inplace=False):
+def run_emul(lib, shape, pa, offsets, W, P, rhs, inplace=False, rows=0):
     n = shape[pa]
     n_sys = int(np.prod(shape)) // n
     inner = int(np.prod(shape[pa + 1:], dtype=np.int64))
@@ -45,21 +45,24 @@ def run_emul(lib, shape, pa, offsets, W, P, rhs, inplace=False):
     out = rhs if inplace else np.empty_like(rhs)
     offs = (C.c_int32 * len(offsets))(*offsets)
     rc = lib.banded_emul(DT[str(rhs.dtype)], int(cband), W.shape[0], n, n_sys, len(offsets), offs, Wc.ctypes.data, Pc.ctypes.data,
-                         rhs.ctypes.data, out.ctypes.data, inner, lu.ctypes.data)
+                         rhs.ctypes.data, out.ctypes.data, inner, lu.ctypes.data, int(rows))
     return rc, out, np.transpose(lu, (2, 0, 1))
 
 
+@pytest.mark.parametrize("rows", [0, 1], ids=["thread-per-system", "row-tiles"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_device_code_on_host_matches_oracle(emul, name):
+def test_device_code_on_host_matches_oracle(emul, name, rows):
     shape, pa, offsets, W, P, rhs = make_case(name)
+    if rows and (pa != len(shape) - 1 or max(abs(o) for o in offsets) > 4):
+        pytest.skip("the row-tile variant serves a last polynomial axis with bandwidth <= 4")
     S = O.WavenumberSolver(pa, shape, W, P, offsets)
     want = S.solve(rhs.astype(np.complex128 if np.iscomplexobj(rhs) else np.float64))
     tol = tolerance(str(rhs.dtype))
-    rc, x, lu = run_emul(emul, shape, pa, offsets, W, P, rhs)
+    rc, x, lu = run_emul(emul, shape, pa, offsets, W, P, rhs, rows=rows)
     assert rc == 0
     assert np.abs(lu - S.band_lu).max() <= tol * np.abs(S.band_lu).max()
     assert np.abs(x - want).max() <= tol * np.abs(want).max()
-    rc, x2, _ = run_emul(emul, shape, pa, offsets, W, P, rhs.copy(), inplace=True)        # rhs == out
+    rc, x2, _ = run_emul(emul, shape, pa, offsets, W, P, rhs.copy(), inplace=True, rows=rows)        # rhs == out
     assert rc == 0 and np.array_equal(x2, x)
 
 
@@ -70,6 +73,8 @@ def test_device_code_on_host_matches_reference_vectors(emul):
         offsets = tuple(int(o) for o in gold[name + "/offsets"])
         rc, x, lu = run_emul(emul, rhs.shape, 1, offsets, W, P, rhs)
         assert rc == 0
+        if max(abs(o) for o in offsets) <= 4:
+            assert np.array_equal(run_emul(emul, rhs.shape, 1, offsets, W, P, rhs, rows=1)[1], x), name
         assert np.abs(lu - gold[name + "/band_lu"]).max() <= 1e-13 * np.abs(gold[name + "/band_lu"]).max(), name
         assert np.abs(x - gold[name + "/x"]).max() <= 1e-12 * np.abs(gold[name + "/x"]).max(), name
 
