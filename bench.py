@@ -382,6 +382,34 @@ def run_legs(jf, L, torch, dev, fp64_peak, hbm):
     except Exception as e:  # pragma: no cover
         legs["mixed_FxFxLeg_256"] = {"error": f"{type(e).__name__}: {e}"}
     torch.cuda.empty_cache()
+    # ---- Fourier x Fourier x polynomial Helmholtz solve: 65 536 pentadiagonal-type systems of n = 254 ---
+    try:
+        from jaxfun_b200.galerkin.tpsolve import WavenumberBandedSolver
+        nb, nsys = 254, 256 * 256
+        Pb = np.zeros((2, 3, nb))
+        Pb[0, 1] = 4.0 + 0.01 * np.arange(nb)
+        Pb[1, 0, :nb - 2], Pb[1, 1], Pb[1, 2, 2:] = -0.2, 1.0, -0.2
+        Wb = np.stack([np.ones(nsys), 1.0 + np.random.default_rng(6).random(nsys)])
+        out_b = {}
+        for tag, shape, pa in (("poly_axis_last", (256, 256, nb), 2), ("poly_axis_middle", (256, nb, 256), 1)):
+            Sb = WavenumberBandedSolver(pa, shape, Wb, Pb, (-2, 0, 2))
+            rb = [torch.view_as_complex(torch.randn(*shape, 2, dtype=torch.float64, device=dev, generator=g)) for _ in range(2)]
+            ob = torch.empty_like(rb[0])
+            cnt = [0]
+
+            def solve_once():
+                cnt[0] += 1
+                Sb.solve(rb[cnt[0] % 2], out=ob)          # two 266 MB inputs alternate: nothing of the input is L2-resident
+            ms = timed(solve_once, reps=6)
+            nbytes = 2 * rb[0].numel() * 16 + 5 * 8 * nb * nsys
+            out_b[tag] = dict(hbm_entry(ms, nbytes, launches=1), shape=list(shape))
+            del Sb, rb, ob
+        out_b["note"] = ("jfx_banded_solve, complex128 right-hand sides, real factors with offsets (-2, 0, 2): compulsory bytes = "
+                         "right-hand side in + solution out + factored band read once (the y round trip of L y = b is extra traffic)")
+        legs["banded_FxFxPoly_256"] = out_b
+    except Exception as e:  # pragma: no cover
+        legs["banded_FxFxPoly_256"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
     # ---- C5 on ONE GPU: the strong-scaling denominator of the N > 1 runs -------------------------------------------------
     try:
         n5 = 512
