@@ -12,22 +12,6 @@
 #define JFX_HD inline
 #endif
 
-// Optional software prefetch of the sweeps (build switch, OFF by default): every chunk asks for the lines it will need
-// JFX_BANDED_PF steps later (prefetch.global.L2: no register, no dependency).  Measured on the B200 (profiles/r2_banded.txt):
-// distances 32 / 64 / 128 and the L1 variant are 10-25 % SLOWER than no prefetch on every shape but 4096 x 4094 (5 % faster).
-// On the host (emulation) it is a no-op.
-#ifndef JFX_BANDED_PF
-#define JFX_BANDED_PF 0
-#endif
-#ifndef JFX_BANDED_PF_INSTR
-#define JFX_BANDED_PF_INSTR "prefetch.global.L2"
-#endif
-#if defined(__CUDA_ARCH__)
-#define JFX_BANDED_PREFETCH(ptr) asm volatile(JFX_BANDED_PF_INSTR " [%0];" ::"l"(ptr))
-#else
-#define JFX_BANDED_PREFETCH(ptr) ((void)(ptr))
-#endif
-
 namespace jfx {
 namespace banded {
 
@@ -146,7 +130,7 @@ JFX_HD bool factor_system(BandElem<R, EC>* lu, int64_t n, int64_t n_sys, int p, 
 // [outer, n, inner] with s = o * inner + i.  W > 0: p, q <= W, window in registers, the loads of U consecutive steps are
 // issued before their dependent arithmetic.  W == 0: any bandwidth, earlier unknowns are read back from `out`.
 // `rhs` may equal `out` (every step reads its right-hand-side entries before it writes them).
-template <typename R, bool EC, bool XC, int W, int U, bool DB = true>
+template <typename R, bool EC, bool XC, int W, int U, bool EXACT = false>
 JFX_HD void solve_system(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>::X* rhs, typename BA<R, EC, XC>::X* out,
                          int64_t n, int64_t n_sys, int64_t inner, int p, int q, int64_t s) {
   using A = BA<R, EC, XC>;
@@ -159,118 +143,113 @@ JFX_HD void solve_system(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>
   auto ld = [&](int row, int64_t j) -> E { return Ls[((int64_t)row * n + j) * n_sys]; };
 
   if constexpr (W > 0) {
-    // The loads of a chunk (U steps: right-hand side and matrix entries) do not depend on the recurrence.  Two register
-    // buffers alternate: the loads of chunk c + 1 are issued before the dependent arithmetic of chunk c, so they are in flight
-    // while it runs.  The reciprocal of the U diagonal is formed in the load phase, off the dependent chain (the sweep
-    // multiplies by it: one rounding more than the reference's division, far inside the 1e-12 bar).
+    // The loads of a chunk (U steps: right-hand side and matrix entries) do not depend on the recurrence: they are all issued
+    // before the chunk's dependent arithmetic.  The reciprocal of the U diagonal is formed in the load phase, after ALL loads
+    // of the chunk (the sweep multiplies by it: one rounding more than the reference's division, far inside the 1e-12 bar).
+    // With few systems there is one warp per scheduler and the sweep is bound by the INSTRUCTIONS per step (measured: 45 / 83
+    // per forward / backward step in the first build = 143 ns per step), so the interior chunks — every index in range — run a
+    // lean variant (FULL): no per-step predicates, addresses by pointer increments; EXACT (p == q == W) drops the band guards.
     X win[W];
 #pragma unroll
     for (int t = 0; t < W; ++t) win[t] = A::xzero();
-    // forward elimination: y_j = b_j - sum_{t=1..p} L[j, j-t] y_{j-t},   L[j, j-t] = band[p - t][j - t]
-    auto load_fwd = [&](int64_t j0, X (&bv)[U], E (&lv)[U][W]) {
-      if constexpr (JFX_BANDED_PF > 0) {
+    // ---- forward elimination: y_j = b_j - sum_{t=1..p} L[j, j-t] y_{j-t},   L[j, j-t] = band[p - t][j - t]
+    auto fwd_chunk = [&](int64_t j0, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      X bv[U];
+      E lv[U][W];
+      if constexpr (FULL) {
+        const X* bp = b + j0 * inner;
+        const E* lp[W];
+#pragma unroll
+        for (int t = 1; t <= W; ++t) lp[t - 1] = Ls + ((int64_t)(p - t) * n + (j0 - t)) * n_sys;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int64_t j = j0 + u + JFX_BANDED_PF;
+          bv[u] = bp[u * inner];
+#pragma unroll
+          for (int t = 1; t <= W; ++t) lv[u][t - 1] = (EXACT || t <= p) ? lp[t - 1][u * n_sys] : A::ezero();
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t j = j0 + u;
+          bv[u] = A::xzero();
+#pragma unroll
+          for (int t = 1; t <= W; ++t) lv[u][t - 1] = A::ezero();
           if (j < n) {
-            JFX_BANDED_PREFETCH(b + j * inner);
+            bv[u] = b[j * inner];
 #pragma unroll
             for (int t = 1; t <= W; ++t)
-              if (t <= p) JFX_BANDED_PREFETCH(Ls + ((int64_t)(p - t) * n + (j - t)) * n_sys);
+              if (t <= p && j - t >= 0) lv[u][t - 1] = ld(p - t, j - t);
           }
         }
       }
+      X* xp = x + j0 * inner;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int64_t j = j0 + u;
-        bv[u] = A::xzero();
-#pragma unroll
-        for (int t = 1; t <= W; ++t) lv[u][t - 1] = A::ezero();
-        if (j < n) {
-          bv[u] = b[j * inner];
-#pragma unroll
-          for (int t = 1; t <= W; ++t)
-            if (t <= p && j - t >= 0) lv[u][t - 1] = ld(p - t, j - t);
-        }
-      }
-    };
-    auto run_fwd = [&](int64_t j0, const X (&bv)[U], const E (&lv)[U][W]) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t j = j0 + u;
-        if (j < n) {
+        if (FULL || j0 + u < n) {
           X y = bv[u];
 #pragma unroll
           for (int t = 1; t <= W; ++t) A::msub(y, lv[u][t - 1], win[t - 1]);
 #pragma unroll
           for (int t = W - 1; t > 0; --t) win[t] = win[t - 1];
           win[0] = y;
-          x[j * inner] = y;
+          xp[u * inner] = y;
         }
       }
     };
-    if constexpr (DB) {
-      X bva[U], bvb[U];
-      E lva[U][W], lvb[U][W];
-      load_fwd(0, bva, lva);
-      for (int64_t j0 = 0; j0 < n; j0 += 2 * U) {
-        load_fwd(j0 + U, bvb, lvb);
-        run_fwd(j0, bva, lva);
-        load_fwd(j0 + 2 * U, bva, lva);
-        run_fwd(j0 + U, bvb, lvb);
-      }
-    } else {
-      X bva[U];
-      E lva[U][W];
-      for (int64_t j0 = 0; j0 < n; j0 += U) {
-        load_fwd(j0, bva, lva);
-        run_fwd(j0, bva, lva);
-      }
+    {
+      int64_t j0 = 0;
+      for (; j0 < W && j0 < n; j0 += U) fwd_chunk(j0, std::false_type{});      // head: rows whose band leaves the matrix
+      for (; j0 + U <= n; j0 += U) fwd_chunk(j0, std::true_type{});            // interior
+      for (; j0 < n; j0 += U) fwd_chunk(j0, std::false_type{});                // ragged tail
     }
-    // back substitution: x_j = (y_j - sum_{t=1..q} U[j, j+t] x_{j+t}) / U[j, j],   U[j, j+t] = band[p + t][j + t];
+    // ---- back substitution: x_j = (y_j - sum_{t=1..q} U[j, j+t] x_{j+t}) / U[j, j],   U[j, j+t] = band[p + t][j + t];
     // a chunk covers j = j1 - 1 down to j1 - U
 #pragma unroll
     for (int t = 0; t < W; ++t) win[t] = A::xzero();
-    auto load_bwd = [&](int64_t j1, X (&yv)[U], E (&uv)[U][W], E (&rd)[U]) {
-      if constexpr (JFX_BANDED_PF > 0) {
+    auto bwd_chunk = [&](int64_t j1, auto full_tag) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      X yv[U];
+      E uv[U][W], rd[U];
+      if constexpr (FULL) {
+        const X* yp = x + (j1 - 1) * inner;
+        const E* dp = Ls + ((int64_t)p * n + (j1 - 1)) * n_sys;
+        const E* up[W];
+#pragma unroll
+        for (int t = 1; t <= W; ++t) up[t - 1] = Ls + ((int64_t)(p + t) * n + (j1 - 1 + t)) * n_sys;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int64_t j = j1 - 1 - u - JFX_BANDED_PF;
+          yv[u] = *(yp - u * inner);
+          rd[u] = *(dp - u * n_sys);
+#pragma unroll
+          for (int t = 1; t <= W; ++t) uv[u][t - 1] = (EXACT || t <= q) ? *(up[t - 1] - u * n_sys) : A::ezero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) rd[u] = A::recip(rd[u]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t j = j1 - 1 - u;
+          yv[u] = A::xzero();
+          rd[u] = A::ezero();
+#pragma unroll
+          for (int t = 1; t <= W; ++t) uv[u][t - 1] = A::ezero();
           if (j >= 0) {
-            JFX_BANDED_PREFETCH(x + j * inner);
-            JFX_BANDED_PREFETCH(Ls + ((int64_t)p * n + j) * n_sys);
+            yv[u] = x[j * inner];
+            rd[u] = ld(p, j);
 #pragma unroll
             for (int t = 1; t <= W; ++t)
-              if (t <= q) JFX_BANDED_PREFETCH(Ls + ((int64_t)(p + t) * n + (j + t)) * n_sys);
+              if (t <= q && j + t < n) uv[u][t - 1] = ld(p + t, j + t);
           }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (j1 - 1 - u >= 0) rd[u] = A::recip(rd[u]);
       }
+      X* xp = x + (j1 - 1) * inner;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int64_t j = j1 - 1 - u;
-        yv[u] = A::xzero();
-        rd[u] = A::ezero();
-#pragma unroll
-        for (int t = 1; t <= W; ++t) uv[u][t - 1] = A::ezero();
-        if (j >= 0) {
-          yv[u] = x[j * inner];
-          rd[u] = ld(p, j);
-#pragma unroll
-          for (int t = 1; t <= W; ++t)
-            if (t <= q && j + t < n) uv[u][t - 1] = ld(p + t, j + t);
-        }
-      }
-      // reciprocals only after EVERY load of the chunk has been issued: the first one waits for its diagonal entry, and the
-      // issue is in order (with the reciprocal inside the loop above each step paid its own DRAM latency)
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (j1 - 1 - u >= 0) rd[u] = A::recip(rd[u]);
-    };
-    auto run_bwd = [&](int64_t j1, const X (&yv)[U], const E (&uv)[U][W], const E (&rd)[U]) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t j = j1 - 1 - u;
-        if (j >= 0) {
+        if (FULL || j1 - 1 - u >= 0) {
           X v = yv[u];
 #pragma unroll
           for (int t = 1; t <= W; ++t) A::msub(v, uv[u][t - 1], win[t - 1]);
@@ -278,27 +257,15 @@ JFX_HD void solve_system(const BandElem<R, EC>* lu, const typename BA<R, EC, XC>
 #pragma unroll
           for (int t = W - 1; t > 0; --t) win[t] = win[t - 1];
           win[0] = v;
-          x[j * inner] = v;
+          *(xp - u * inner) = v;
         }
       }
     };
-    if constexpr (DB) {
-      X yva[U], yvb[U];
-      E uva[U][W], uvb[U][W], rda[U], rdb[U];
-      load_bwd(n, yva, uva, rda);
-      for (int64_t j1 = n; j1 > 0; j1 -= 2 * U) {
-        load_bwd(j1 - U, yvb, uvb, rdb);
-        run_bwd(j1, yva, uva, rda);
-        load_bwd(j1 - 2 * U, yva, uva, rda);
-        run_bwd(j1 - U, yvb, uvb, rdb);
-      }
-    } else {
-      X yva[U];
-      E uva[U][W], rda[U];
-      for (int64_t j1 = n; j1 > 0; j1 -= U) {
-        load_bwd(j1, yva, uva, rda);
-        run_bwd(j1, yva, uva, rda);
-      }
+    {
+      int64_t j1 = n;
+      for (; j1 > 0 && j1 + W > n; j1 -= U) bwd_chunk(j1, std::false_type{});  // head: rows whose band leaves the matrix
+      for (; j1 - U >= 0; j1 -= U) bwd_chunk(j1, std::true_type{});            // interior
+      for (; j1 > 0; j1 -= U) bwd_chunk(j1, std::false_type{});                // ragged tail
     }
   } else {
     for (int64_t j = 0; j < n; ++j) {
@@ -482,15 +449,16 @@ inline bool rows_variant_applies(int64_t inner, int p, int q, int64_t n_sys) {
 #ifndef JFX_BANDED_U8
 #define JFX_BANDED_U8 2
 #endif
-#ifndef JFX_BANDED_DB
-#define JFX_BANDED_DB 0   /* measured: a second register buffer does not hide a DRAM latency (profiles/r2_banded.txt) */
-#endif
 template <typename F> inline void dispatch_window(int p, int q, F&& f) {
   const int w = p > q ? p : q;
-  if (w <= 2) f(std::integral_constant<int, 2>{}, std::integral_constant<int, JFX_BANDED_U2>{});
-  else if (w <= 4) f(std::integral_constant<int, 4>{}, std::integral_constant<int, JFX_BANDED_U4>{});
-  else if (w <= 8) f(std::integral_constant<int, 8>{}, std::integral_constant<int, JFX_BANDED_U8>{});
-  else f(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});
+  auto pick = [&](auto wt, auto ut) {
+    if (p == decltype(wt)::value && q == decltype(wt)::value) f(wt, ut, std::true_type{});   // EXACT: full band, no guards
+    else f(wt, ut, std::false_type{});
+  };
+  if (w <= 2) pick(std::integral_constant<int, 2>{}, std::integral_constant<int, JFX_BANDED_U2>{});
+  else if (w <= 4) pick(std::integral_constant<int, 4>{}, std::integral_constant<int, JFX_BANDED_U4>{});
+  else if (w <= 8) pick(std::integral_constant<int, 8>{}, std::integral_constant<int, JFX_BANDED_U8>{});
+  else f(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{}, std::false_type{});
 }
 
 }  // namespace banded

@@ -57,14 +57,14 @@ __global__ void __launch_bounds__(128) banded_factor_kernel(BandElem<R, EC>* lu,
   if (banded::factor_system<R, EC>(lu, n, n_sys, p, q, s)) atomicOr(flag, 1);
 }
 
-template <typename R, bool EC, bool XC, int W, int U>
+template <typename R, bool EC, bool XC, int W, int U, bool EXACT>
 __global__ void __launch_bounds__(128) banded_solve_kernel(const BandElem<R, EC>* __restrict__ lu,
                                                            const typename BA<R, EC, XC>::X* rhs,
                                                            typename BA<R, EC, XC>::X* out, int64_t n, int64_t n_sys,
                                                            int64_t inner, int p, int q) {
   const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (s >= n_sys) return;
-  banded::solve_system<R, EC, XC, W, U, (JFX_BANDED_DB != 0)>(lu, rhs, out, n, n_sys, inner, p, q, s);
+  banded::solve_system<R, EC, XC, W, U, EXACT>(lu, rhs, out, n, n_sys, inner, p, q, s);
 }
 
 // polynomial axis last: one warp per 32 consecutive rows, tiles staged through shared memory (banded.cuh: solve_rows_warp)
@@ -106,8 +106,8 @@ int launch_solve_t(cudaStream_t st, const jfx_banded* b, const void* rhs, void* 
   const E* lu = static_cast<const E*>(b->lu);
   const X* r = static_cast<const X*>(rhs);
   X* o = static_cast<X*>(out);
-  banded::dispatch_window(b->p, b->q, [&](auto w, auto u) {
-    banded_solve_kernel<R, EC, XC, decltype(w)::value, decltype(u)::value>
+  banded::dispatch_window(b->p, b->q, [&](auto w, auto u, auto exact) {
+    banded_solve_kernel<R, EC, XC, decltype(w)::value, decltype(u)::value, decltype(exact)::value>
         <<<blocks, threads, 0, st>>>(lu, r, o, b->n, b->n_sys, inner, b->p, b->q);
   });
   JFX_CUDA_OK(cudaGetLastError());

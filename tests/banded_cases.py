@@ -24,6 +24,12 @@ CASES = {
     "rows_kernel_w4":     ((593, 33, 13), 2, (-4, -1, 0, 3), 2, True, "complex128"),
     "rows_kernel_f64":    ((19010, 19), 1, (-1, 0, 1), 1, False, "float64"),
     "rows_kernel_c64":    ((19010, 18), 1, (-2, 0, 2), 2, False, "complex64"),
+    "chunk_kernel_many":  ((33, 21, 576), 1, (-2, 0, 2), 2, False, "complex128"),    # >= 18 944 systems, axis not last: register chunks
+    "edge_n3":            ((5, 3), 1, (-2, 0, 2), 2, False, "complex128"),           # shorter than the window reach and the chunk
+    "edge_n12":           ((3, 12), 1, (-2, 0, 2), 2, False, "complex128"),          # exactly one chunk
+    "edge_n13":           ((13, 3), 0, (-2, 0, 2), 2, False, "float64"),
+    "edge_n24":           ((2, 24, 2), 1, (-2, 0, 2), 2, False, "complex128"),       # whole chunks only
+    "edge_n9_w4":         ((4, 9), 1, (-4, 0, 4), 2, False, "complex128"),
     "many_systems":       ((300, 20), 1, (-2, 0, 2), 2, False, "complex128"),      # several CTAs, ragged last one
 }
 

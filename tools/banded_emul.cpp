@@ -33,7 +33,7 @@ static int run(int n_terms, int64_t n, int64_t n_sys, int n_diags, const int* of
     if (factor_system<R, EC>(lu.data(), n, n_sys, p, q, s)) flag = 1;
   if (lu_out) std::memcpy(lu_out, lu.data(), lu.size() * sizeof(E));
   if (flag) return 1;
-  if (inner == 1 && (p > q ? p : q) <= 4 && use_rows) {      // the launch logic of kernels_banded.cu: warps of 32 consecutive rows
+  if (inner == 1 && (p > q ? p : q) <= 4 && use_rows == 1) {      // the launch logic of kernels_banded.cu: warps of 32 consecutive rows
     std::vector<X> tile((size_t)32 * rows_pitch<R, EC, XC>());
     for (int64_t s0 = 0; s0 < n_sys; s0 += 32) {
       if (p <= 2 && q <= 2) solve_rows_warp<R, EC, XC, 2>(lu.data(), static_cast<const X*>(rhs), static_cast<X*>(out), n, n_sys, p, q, s0, tile.data());
@@ -41,16 +41,16 @@ static int run(int n_terms, int64_t n, int64_t n_sys, int n_diags, const int* of
     }
     return 0;
   }
-  dispatch_window(p, q, [&](auto w, auto u) {
+  dispatch_window(p, q, [&](auto w, auto u, auto exact) {
     for (int64_t s = 0; s < n_sys; ++s)
-      solve_system<R, EC, XC, decltype(w)::value, decltype(u)::value, (JFX_BANDED_DB != 0)>(lu.data(), static_cast<const X*>(rhs), static_cast<X*>(out),
+      solve_system<R, EC, XC, decltype(w)::value, decltype(u)::value, decltype(exact)::value>(lu.data(), static_cast<const X*>(rhs), static_cast<X*>(out),
                                                                       n, n_sys, inner, p, q, s);
   });
   return 0;
 }
 
-// dtype: 0 f32, 1 f64, 2 c64, 3 c128 (jfx_dtype).  use_rows != 0: the row-tile variant where it can run (polynomial axis last,
-// bandwidth <= 4; the device additionally asks for enough systems), else one thread per system.  Returns 1 for a zero / non-finite pivot, -1 for a bad combination.
+// dtype: 0 f32, 1 f64, 2 c64, 3 c128 (jfx_dtype).  use_rows = 1: the row-tile variant where it can run (polynomial axis last,
+// bandwidth <= 4; the device additionally asks for enough systems); else one thread per system with register chunks.  Returns 1 for a zero / non-finite pivot, -1 for a bad combination.
 extern "C" int banded_emul(int dtype, int band_complex, int n_terms, int64_t n, int64_t n_sys, int n_diags, const int* offsets,
                            const double* W, const double* P, const void* rhs, void* out, int64_t inner, void* lu_out, int use_rows) {
   switch (dtype) {
