@@ -63,6 +63,34 @@ def current_stream_ptr() -> int:
     return int(torch.cuda.current_stream().cuda_stream)
 
 
+class device_scope:
+    """Make the device of a CUDA array current for the duration of a block (plans, tables and workspaces live on ONE device:
+    the one that is current when they are created; launches go to the current device's current stream).  A no-op for host
+    arrays and when the device is current already."""
+
+    def __init__(self, x):
+        self._ctx = None
+        dev = getattr(x, "device", None)
+        if torch is not None and getattr(x, "is_cuda", False) and dev.index is not None \
+                and dev.index != torch.cuda.current_device():
+            self._ctx = torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            return self._ctx.__exit__(*exc)
+        return False
+
+
+def device_key(x):
+    """Cache-key component: the CUDA device index of a device array, "host" for numpy arrays."""
+    return x.device.index if getattr(x, "is_cuda", False) else "host"
+
+
 class PinnedArray:
     """numpy array living in CUDA pinned host memory (jfx_host_alloc)."""
 
@@ -121,6 +149,8 @@ class Plan:
     def __init__(self, op: int, dtype: int, shape_in: Sequence[int], axes: Sequence[AxisSpec | None]):
         self._lib = L.load()
         require_device()
+        # the plan's tables are uploaded to the device that is current now; execute() refuses arrays of another device
+        self.device_index = int(torch.cuda.current_device()) if torch is not None and torch.cuda.is_available() else 0
         self.op, self.dtype = int(op), int(dtype)
         self.shape_in = tuple(int(s) for s in shape_in)
         desc, keep = _fill_plan_desc(op, dtype, shape_in, axes)
@@ -166,6 +196,13 @@ class Plan:
             raise TypeError(f"plan dtype {_JFX2NP[self.dtype]} != array dtype {x.dtype}")
         if not x.is_cuda:
             raise L.JfxError(-3, "device path needs a CUDA tensor; jaxfun_b200 has no CPU fallback")
+        if x.device.index != self.device_index:
+            raise ValueError(f"this plan lives on cuda:{self.device_index}, the array on {x.device}: plans are per device "
+                             "(create them under engine.device_scope(array))")
+        with device_scope(x):
+            return self._execute_on_device(x, out)
+
+    def _execute_on_device(self, x, out):
         x = x.contiguous()
         if out is None:
             out = torch.empty(self.shape_out, dtype=x.dtype, device=x.device)
@@ -192,6 +229,8 @@ class Plan:
             raise ValueError(f"plan expects shape {self.shape_in}, got {tuple(x.shape)}")
         if not x.is_cuda:
             raise L.JfxError(-3, "device path needs a CUDA tensor; jaxfun_b200 has no CPU fallback")
+        if x.device.index != self.device_index:
+            raise ValueError(f"this plan lives on cuda:{self.device_index}, the array on {x.device}")
         x = x.contiguous()
         ws = self.workspace(x.device)
         ptrs = (C.c_void_p * len(peer_ptrs))(*[C.c_void_p(int(p)) for p in peer_ptrs])

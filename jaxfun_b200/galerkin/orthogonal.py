@@ -22,7 +22,7 @@ from typing import NamedTuple
 import numpy as np
 
 from .. import _lib as L
-from ..engine import AxisSpec, Plan, as_jfx_array, fast_path_available, jfx_dtype
+from ..engine import AxisSpec, Plan, as_jfx_array, device_key, device_scope, fast_path_available, jfx_dtype
 
 
 class Domain(NamedTuple):
@@ -258,20 +258,21 @@ class OrthogonalSpace:
         dtype = jfx_dtype(x.dtype)
         if table is not None and name is None:
             cache = False
-        key = (op, dtype, tuple(x.shape), axis, N, k, name)
+        key = (op, dtype, tuple(x.shape), axis, N, k, name, device_key(x))      # one plan per device
         plan = self._plans.get(key) if cache else None
-        if plan is None:
-            if table is not None:
-                spec = AxisSpec(L.BASIS_CTABLE if np.iscomplexobj(table) else L.BASIS_TABLE, table=table)
-            else:
-                spec = self.axis_spec(op, x.shape[axis], dtype, N, k,
-                                      inner=int(np.prod(x.shape[axis + 1:], dtype=np.int64)))
-            axes = [None] * x.ndim
-            axes[axis] = spec
-            plan = Plan(op, dtype, tuple(x.shape), axes)
-            if cache:
-                self._plans[key] = plan
-        return plan(x)
+        with device_scope(x):
+            if plan is None:
+                if table is not None:
+                    spec = AxisSpec(L.BASIS_CTABLE if np.iscomplexobj(table) else L.BASIS_TABLE, table=table)
+                else:
+                    spec = self.axis_spec(op, x.shape[axis], dtype, N, k,
+                                          inner=int(np.prod(x.shape[axis + 1:], dtype=np.int64)))
+                axes = [None] * x.ndim
+                axes[axis] = spec
+                plan = Plan(op, dtype, tuple(x.shape), axes)
+                if cache:
+                    self._plans[key] = plan
+            return plan(x)
 
     def forward(self, u, axis: int = -1):
         """Samples at quadrature points -> expansion coefficients (orthogonal.py:256-262)."""

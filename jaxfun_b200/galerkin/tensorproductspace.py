@@ -16,7 +16,7 @@ from collections.abc import Sequence
 import numpy as np
 
 from .. import _lib as L
-from ..engine import Plan, as_jfx_array, jfx_dtype
+from ..engine import Plan, as_jfx_array, device_key, device_scope, jfx_dtype
 from .orthogonal import OrthogonalSpace
 
 tensor_product_symbol = "⊗"
@@ -100,10 +100,11 @@ class TensorProductSpace:
 
     def _plan(self, op: int, x, N=None, k=None) -> Plan:
         dtype = jfx_dtype(x.dtype)
-        key = (op, dtype, tuple(x.shape), N, k)
+        key = (op, dtype, tuple(x.shape), N, k, device_key(x))                  # one plan per device
         plan = self._plans.get(key)
         if plan is None:
-            plan = Plan(op, dtype, tuple(x.shape), self._axis_specs(op, tuple(x.shape), dtype, N, k))
+            with device_scope(x):
+                plan = Plan(op, dtype, tuple(x.shape), self._axis_specs(op, tuple(x.shape), dtype, N, k))
             self._plans[key] = plan
         return plan
 

@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import _lib as L
-from ..engine import AxisSpec, Plan, jfx_dtype
+from ..engine import AxisSpec, Plan, device_key, device_scope, jfx_dtype
 
 
 def stiffness_matrix(space, k: int = 2, nq: int | None = None) -> np.ndarray:
@@ -67,11 +67,12 @@ class KroneckerSumSolver:
         import torch
         from ..integrators.base import axpby_diag
         dt = jfx_dtype(f.dtype)
-        key = (tuple(f.shape), dt)
+        key = (tuple(f.shape), dt, device_key(f))
         if key not in self._plans:
             lead = f.ndim - len(self.V)
-            pw = Plan(L.OP_APPLY, dt, tuple(f.shape), [None] * lead + [AxisSpec(L.BASIS_TABLE, table=W) for W in self.W])
-            pv = Plan(L.OP_APPLY, dt, pw.shape_out, [None] * lead + [AxisSpec(L.BASIS_TABLE, table=V) for V in self.V])
+            with device_scope(f):
+                pw = Plan(L.OP_APPLY, dt, tuple(f.shape), [None] * lead + [AxisSpec(L.BASIS_TABLE, table=W) for W in self.W])
+                pv = Plan(L.OP_APPLY, dt, pw.shape_out, [None] * lead + [AxisSpec(L.BASIS_TABLE, table=V) for V in self.V])
             self._plans[key] = (pw, pv)
             dinv = torch.from_numpy(np.broadcast_to(self.Dinv, pw.shape_out).copy()).to(f.device)
             self._dinv_dev[key] = dinv
@@ -150,8 +151,13 @@ class WavenumberBandedSolver:
         return WavenumberBandedSolver(self.poly_axis, local_shape, self.weights[:, rank * per:(rank + 1) * per], self.diags,
                                       self.offsets)
 
-    def _handle(self, dtype: int):
-        h = self._handles.get(dtype)
+    def _handle(self, dtype: int, device=None):
+        """Factors of the systems in the precision of `dtype` on CUDA device `device` (created on first use: the object
+        is assembled and factored on the device that is current, so the device of the right-hand side is made current)."""
+        if device is None:
+            import torch
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        h = self._handles.get((dtype, device))
         if h is None:
             import ctypes as C
             d = L.BandedDesc()
@@ -165,7 +171,7 @@ class WavenumberBandedSolver:
             if rc == -2:      # zero / non-finite pivot: the reference raises ValueError (la/diamatrix.py:461-471)
                 raise ValueError(self._lib.jfx_last_error().decode())
             L.check(rc)
-            self._handles[dtype] = h
+            self._handles[(dtype, device)] = h
         return h
 
     def __del__(self):
@@ -210,8 +216,10 @@ class WavenumberBandedSolver:
             raise ValueError("out must be a contiguous array of the right-hand side's shape, dtype and device")
         outer = int(np.prod(self.shape[:self.poly_axis], dtype=np.int64))
         inner = int(np.prod(self.shape[self.poly_axis + 1:], dtype=np.int64))
-        L.check(self._lib.jfx_banded_solve(self._handle(dt), C.c_void_p(current_stream_ptr()), C.c_void_p(rhs.data_ptr()),
-                                           C.c_void_p(out.data_ptr()), outer, inner))
+        with device_scope(rhs):
+            h = self._handle(dt, device_key(rhs))
+            L.check(self._lib.jfx_banded_solve(h, C.c_void_p(current_stream_ptr()), C.c_void_p(rhs.data_ptr()),
+                                               C.c_void_p(out.data_ptr()), outer, inner))
         return out
 
 

@@ -75,3 +75,14 @@ def test_dense_tables_match_oracle_transforms(name, OC, PC, kw, dom):
             up = o.backward_primitive(c, k=k, N=nn, axis=0)
             T = p._dense_table(L.OP_BACKWARD_PRIMITIVE, N, nn, k)
             assert np.abs(T @ c - up).max() <= 1e-12 * np.abs(up).max()
+
+
+def test_device_scope_and_key_are_neutral_for_host_arrays():
+    """Plans are per device: caches key on the array's device and creation runs under `device_scope` (a no-op for host
+    arrays and for the device that is current already)."""
+    import numpy as np
+    from jaxfun_b200.engine import device_key, device_scope
+    x = np.zeros(3)
+    assert device_key(x) == "host"
+    with device_scope(x) as sc:
+        assert sc._ctx is None

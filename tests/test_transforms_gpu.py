@@ -53,12 +53,15 @@ def test_1d_all_ops(cuda, name, N, n, dom):
     assert relerr(u, u_ref) < TOL64
     assert relerr(p.forward(dev(u_ref, cuda)), o.forward(u_ref, axis=-1)) < TOL64
     assert relerr(p.scalar_product(dev(u_ref, cuda)), o.scalar_product(u_ref, axis=-1)) < TOL64
-    # round trip, as tests/galerkin/test_forward_backward.py:31-46 of the reference
-    assert relerr(p.forward(p.backward(dev(c, cuda), N=n)), c) < 1e-11
+    # round trip, as tests/galerkin/test_forward_backward.py:31-46 of the reference.  The north-star bar (1e-12 of the
+    # max-norm) holds up to n = 64; above it the k-th derivative amplifies the rounding of the coefficients by ~ n^(2k) and
+    # the two evaluation orders (table x derivative matrix here, coefficient recurrence + series in the oracle) differ by it
+    tol = TOL64 if max(N, n) <= 64 else 1e-11
+    assert relerr(p.forward(p.backward(dev(c, cuda), N=n)), c) < tol
     if name != "ChebyshevU":
         for k in (1, 2):
             ref = o.backward_primitive(c, k=k, N=n, axis=-1)
-            assert relerr(p.backward_primitive(dev(c, cuda), k=k, N=n), ref) < 1e-11
+            assert relerr(p.backward_primitive(dev(c, cuda), k=k, N=n), ref) < tol
 
 
 @pytest.mark.parametrize("name", ["Legendre", "Chebyshev", "Fourier"])
