@@ -94,3 +94,43 @@ def test_device_code_flags_zero_and_nonfinite_pivots(emul):
     W0 = W.copy()
     W0[0, 1] = 0.0                                   # one singular system among healthy ones
     assert run_emul(emul, (3, 6), 1, (-1, 0, 1), W0, P, rhs)[0] == 1
+
+
+def test_device_code_on_host_fuzz(emul):
+    """Seeded random systems: shapes, position of the polynomial axis, one- and two-sided bands up to the generic variant,
+    real / complex bands and all four dtypes, both kernel variants where they apply."""
+    rng = np.random.default_rng(20261018)
+    for trial in range(60):
+        nd = int(rng.integers(2, 4))
+        shape = tuple(int(v) for v in rng.integers(1, 9, size=nd))
+        pa = int(rng.integers(0, nd))
+        n = int(rng.integers(1, 40))
+        shape = shape[:pa] + (n,) + shape[pa + 1:]
+        n_sys = int(np.prod(shape)) // n
+        wmax = int(rng.choice([1, 2, 4, 8, 12]))
+        lo = int(rng.integers(0, min(wmax, n - 1) + 1)) if n > 1 else 0
+        hi = int(rng.integers(0, min(wmax, n - 1) + 1)) if n > 1 else 0
+        offs = sorted({0} | {int(o) for o in rng.integers(-lo, hi + 1, size=4)} | ({-lo} if lo else set()) | ({hi} if hi else set()))
+        cband = bool(rng.integers(0, 2))
+        dt = str(rng.choice(["complex128", "complex64"] if cband else ["float64", "float32", "complex128", "complex64"]))
+        nt = int(rng.integers(1, 4))
+        P = rng.standard_normal((nt, len(offs), n))
+        W = rng.standard_normal((nt, n_sys))
+        if cband:
+            P = P + 1j * rng.standard_normal(P.shape)
+            W = W + 1j * rng.standard_normal(W.shape)
+        B = np.einsum("tf,tdp->fdp", W, P)
+        P[0, offs.index(0), :] += np.abs(B).sum(axis=1).max() + 1.0
+        W[0, :] = np.abs(W[0, :]) + 1.0
+        rhs = rng.standard_normal(shape)
+        if dt.startswith("complex"):
+            rhs = rhs + 1j * rng.standard_normal(shape)
+        rhs = rhs.astype(dt)
+        want = O.WavenumberSolver(pa, shape, W, P, tuple(offs)).solve(rhs.astype(np.complex128 if np.iscomplexobj(rhs) else np.float64))
+        tol = tolerance(dt)
+        for rows in (0, 1):
+            if rows and (pa != nd - 1 or max(abs(o) for o in offs) > 4):
+                continue
+            rc, x, _ = run_emul(emul, shape, pa, tuple(offs), W, P, rhs, rows=rows)
+            assert rc == 0, (trial, shape, pa, offs, dt)
+            assert np.abs(x - want).max() <= tol * max(np.abs(want).max(), 1e-300), (trial, shape, pa, offs, dt, rows)
