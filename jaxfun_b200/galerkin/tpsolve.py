@@ -258,6 +258,55 @@ def tpmats_wavenumber_factor(terms) -> WavenumberBandedSolver:
     return WavenumberBandedSolver(pa, shape, np.array(W), P, offsets)
 
 
+def tpmats_lu_factor(terms) -> KroneckerSumSolver:
+    """`tpmats_lu_factor` (la/tpmatrix.py:1089-1233): the diagonalisation solver.  Here it takes a Kronecker SUM
+    sum_i (B_0 x .. x A_i x .. x B_{d-1}): one term per axis, and on every axis all terms but one carry the same matrix B
+    (what `inner(v * Div(Grad(u)))` and `laplace_terms` produce).  Anything else raises `SolverNotApplicable`."""
+    import itertools
+    terms = [(float(sc), [np.diag(np.asarray(m)) if np.ndim(m) == 1 else np.asarray(m) for m in mats]) for sc, mats in terms]
+    d = len(terms[0][1])
+    if len(terms) != d:
+        raise SolverNotApplicable(f"a Kronecker sum has one term per axis; got {len(terms)} terms for {d} axes")
+
+    def same(a, b):
+        return a.shape == b.shape and np.allclose(a, b, rtol=1e-12, atol=1e-14 * max(1.0, float(np.abs(a).max())))
+
+    for perm in itertools.permutations(range(d)):          # perm[ax] = the term whose matrix on axis ax is the odd one out
+        pairs = []
+        for ax in range(d):
+            t = perm[ax]
+            others = [terms[u][1][ax] for u in range(d) if u != t]
+            if any(not same(others[0], o) for o in others[1:]):
+                break
+            B = others[0] if others else np.eye(terms[t][1][ax].shape[0])
+            pairs.append((terms[t][0] * terms[t][1][ax], B))                   # the term's scale goes with its A_i
+        else:
+            return KroneckerSumSolver(pairs)
+    raise SolverNotApplicable("the terms are not a Kronecker sum with one common mass matrix per axis")
+
+
+class TPMatrices:
+    """Sum of tensor-product operators  sum_t scale_t (M_0 x .. x M_{d-1})  with the solve interface of the reference's
+    `TPMatrices` (la/tpmatrix.py:386-545): `lu_factor()` picks and caches a factored solver — the per-wavenumber banded LU
+    for Fourier x polynomial structure, the per-axis diagonalisation for a Kronecker sum — and `solve(rhs)` uses it.
+    `terms` = [(scale, [M_0, .., M_{d-1}]), ...]; a 1-D array stands for a diagonal matrix."""
+
+    def __init__(self, terms):
+        self.tpmats = [(sc, list(mats)) for sc, mats in terms]
+        self._lu_cache = None
+
+    def lu_factor(self):
+        if self._lu_cache is None:
+            try:
+                self._lu_cache = tpmats_wavenumber_factor(self.tpmats)       # dispatch order of la/tpmatrix.py:421-426
+            except SolverNotApplicable:
+                self._lu_cache = tpmats_lu_factor(self.tpmats)
+        return self._lu_cache
+
+    def solve(self, rhs):
+        return self.lu_factor().solve(rhs)
+
+
 def _axis_matrices(space):
     """(stiffness, mass) of one axis; Fourier axes give their diagonals (orthogonal exponentials: (e_l, e_k) = 2 pi / df,
     second derivative -(k df)^2)."""

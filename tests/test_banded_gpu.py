@@ -159,6 +159,31 @@ def test_poisson_fourier_fourier_legendre_3d(cuda):
     assert np.linalg.norm(uj - uej) / M**1.5 < np.sqrt(10 * np.finfo(float).eps)
 
 
+def test_tpmatrices_solve_dispatch(cuda):
+    """`TPMatrices.solve` (la/tpmatrix.py:429-545) through both factored solvers, against the dense Kronecker solve; Helmholtz
+    (alpha != 0) keeps the Fourier x polynomial structure and goes to the wavenumber solver as well."""
+    D = jf.FunctionSpace(12, jf.Legendre, BCS, scaling=n_ + 1)
+    Cb = jf.FunctionSpace(10, jf.Chebyshev, BCS, scaling=n_ + 1)
+    rng = np.random.default_rng(8)
+    for spaces, alpha in (([D, Cb], 0.0), ([jf.Fourier(8), D], 0.0), ([jf.Fourier(8), D], -3.0), ([D, jf.Fourier(6), jf.Fourier(4)], -1.5)):
+        T = jf.TensorProduct(*spaces)
+        terms = S.laplace_terms(T, alpha)
+        A = S.TPMatrices(terms)
+        shape = tuple(s.dim for s in T.basespaces)
+        cplx = any(s.complex_data for s in T.basespaces)
+        b = rng.standard_normal(shape) + (1j * rng.standard_normal(shape) if cplx else 0)
+        K = 0
+        for sc, mats in terms:
+            k = np.array([[sc]])
+            for m in mats:
+                k = np.kron(k, np.diag(m) if np.ndim(m) == 1 else m)
+            K = K + k
+        ref = np.linalg.solve(K, b.ravel()).reshape(shape)
+        got = A.solve(dev(b, cuda)).cpu().numpy()
+        assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max(), (spaces, alpha)
+        assert isinstance(A.lu_factor(), S.WavenumberBandedSolver if cplx else S.KroneckerSumSolver)
+
+
 def test_banded_at_size(cuda):
     """Fourier 1024 x Legendre-Dirichlet 1022 Helmholtz-type systems (offsets -2, 0, 2): residual of the solve and the time of
     one launch, printed for the record (-s)."""

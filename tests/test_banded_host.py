@@ -115,6 +115,37 @@ def test_wavenumber_factor_assembly_matches_kron():
     assert isinstance(S.poisson_solver(jf.TensorProduct(jf.Fourier(6), D)), S.WavenumberBandedSolver)
 
 
+def test_tpmatrices_dispatch_and_caching():
+    """`TPMatrices.lu_factor` (la/tpmatrix.py:386-427; tests/la/test_tpmatrices_solvers.py:245-270): wavenumber solver for
+    Fourier x polynomial operators, diagonalisation for all-polynomial Kronecker sums, cached; other structures are refused."""
+    import jaxfun_b200 as jf
+    from jaxfun_b200.galerkin import tpsolve as S
+    n = sp.Symbol("n", integer=True)
+    bcs = {"left": {"D": 0}, "right": {"D": 0}}
+    D = jf.FunctionSpace(10, jf.Legendre, bcs, scaling=n + 1)
+    Cb = jf.FunctionSpace(12, jf.Chebyshev, bcs, scaling=n + 1)
+    A = S.TPMatrices(S.laplace_terms(jf.TensorProduct(jf.Fourier(8), D)))
+    assert isinstance(A.lu_factor(), S.WavenumberBandedSolver) and A.lu_factor() is A.lu_factor()
+    B = S.TPMatrices(S.laplace_terms(jf.TensorProduct(D, Cb)))
+    lu = B.lu_factor()
+    assert isinstance(lu, S.KroneckerSumSolver) and lu is B.lu_factor()
+    assert isinstance(S.TPMatrices(S.laplace_terms(jf.TensorProduct(D, Cb, D))).lu_factor(), S.KroneckerSumSolver)
+    # the factors solve the Kronecker system (host arithmetic with the solver's own tables)
+    K = 0
+    for sc, mats in S.laplace_terms(jf.TensorProduct(D, Cb)):
+        K = K + sc * np.kron(mats[0], mats[1])
+    f = np.random.default_rng(0).standard_normal((8, 10))
+    u = np.einsum("ia,jb,ab->ij", lu.V[0], lu.V[1], np.einsum("ia,jb,ab->ij", lu.W[0], lu.W[1], f) * lu.Dinv)
+    assert np.abs(K @ u.ravel() - f.ravel()).max() < 1e-11 * np.abs(f).max()
+    # the order of the terms does not matter; a sum that is not a Kronecker sum is refused
+    assert isinstance(S.tpmats_lu_factor(list(reversed(S.laplace_terms(jf.TensorProduct(D, Cb))))), S.KroneckerSumSolver)
+    with pytest.raises(S.SolverNotApplicable):
+        S.TPMatrices(S.laplace_terms(jf.TensorProduct(D, Cb), alpha=2.0)).lu_factor()           # three terms on two axes
+    with pytest.raises(S.SolverNotApplicable):
+        e3, e4, e2 = np.eye(3), np.eye(4), np.eye(2)                           # three different matrices on axis 0
+        S.tpmats_lu_factor([(1.0, [e3 + 1, e4, e2]), (1.0, [e3 * 2 + 1, e4 + 3, e2]), (1.0, [e3 * 3 + 1, e4, e2 + 1])])
+
+
 def test_sharded_solver_blocks():
     """`shard(rank, size)`: the blocks of the reference's multi-device mode (la/tpmatrix.py:786-812) — contiguous wavenumber
     ranges of axis 0; together they reproduce the global solve (checked with the oracle); poly_axis = 0 is refused."""
