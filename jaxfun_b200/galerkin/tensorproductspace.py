@@ -243,7 +243,7 @@ def _sample_boundary_value(v, symbols, grids, shape):
 
 
 class DirectSumTPS:
-    """Tensor product with ONE DirectSum factor (2-D / 3-D) or TWO (2-D, `_init_two_directions`) whose boundary values may depend on the other coordinates
+    """Tensor product with ONE or TWO DirectSum factors (2-D / 3-D; two: `_init_two_directions`) whose boundary values may depend on the other coordinates
     (`DirectSumTPS`, tensorproductspace.py:575-851; the case of `examples/poisson2D_periodic.py`).
 
     The lift is a fixed element of the orthogonal tensor-product space: every boundary datum g_b(other coordinates) is
@@ -256,11 +256,13 @@ class DirectSumTPS:
     def __init__(self, basespaces, system=None, name: str = "DSTPS") -> None:
         from .composite import DirectSum
         idx = [i for i, s in enumerate(basespaces) if isinstance(s, DirectSum)]
-        if len(idx) == 2 and len(basespaces) == 2:
+        if len(idx) == 2 and (len(basespaces) == 2 or (len(basespaces) == 3 and idx == [1, 2])):
             self._init_two_directions(list(basespaces), system, name)
             return
+        if len(idx) == 2 and len(basespaces) == 3:
+            raise ValueError("DirectSum cannot be the first space in a 3D tensor product.")   # tensorproductspace.py:612-615
         if len(idx) != 1:
-            raise NotImplementedError("DirectSumTPS: one inhomogeneous direction (2-D / 3-D) or two (2-D) are built")
+            raise NotImplementedError("DirectSumTPS: one or two inhomogeneous directions are built")
         b, d = idx[0], len(basespaces)
         if d == 3 and b == 0:
             raise ValueError("DirectSum cannot be the first space in a 3D tensor product.")   # tensorproductspace.py:612-615
@@ -294,56 +296,80 @@ class DirectSumTPS:
         self._cache: dict = {}
 
     def _init_two_directions(self, basespaces, system, name) -> None:
-        """Both factors of a 2-D product carry inhomogeneous boundary values (tensorproductspace.py:620-668, 689-747): the
-        lift is the transfinite interpolant of the boundary data,
+        """Two factors carry inhomogeneous boundary values (tensorproductspace.py:620-668, 689-747): a 2-D product of two
+        DirectSums, or a 3-D product whose LAST two factors are DirectSums behind a plain first factor (the reference refuses a
+        DirectSum in front, :612-615).  Writing (y, z) for the two inhomogeneous directions and x for the optional first one,
+        the lift is the transfinite interpolant of the boundary data, point by point in x,
 
-            sum_b B^x_b(x) [hom. part of g_b](y) + sum_c [hom. part of h_c](x) B^y_c(y) + sum_bc C_bc B^x_b(x) B^y_c(y),
+            sum_b B^y_b(y) [hom. part of g_b](x, z) + sum_c [hom. part of h_c](x, y) B^z_c(z) + sum_bc C_bc(x) B^y_b(y) B^z_c(z),
 
         where "hom. part" is the projection onto the OTHER direction's composite space after removing that direction's own
-        lift of the corner values C_bc = (boundary functional c of y)(g_b) — the `projected_bcs` of the reference (Dirichlet:
-        the value at the corner, Neumann: the derivative / df^nd).  Boundary data must be numbers or SymPy expressions in the
-        coordinate of the other axis (x, y), as in the reference."""
+        lift of the corner values C_bc = (boundary functional c of z)(g_b) — the `projected_bcs` of the reference (Dirichlet:
+        the value at the corner, Neumann: the derivative / df^nd) — and, in 3-D, everything is finally projected onto the first
+        factor (`project` onto the product of the other spaces, :704-737, 739-747).  Boundary data must be numbers or SymPy
+        expressions in the coordinates of the other axes (named x, y[, z] by position), as in the reference."""
         import sympy as sp
-        Dx, Dy = basespaces
-        self.bc_axis, self.name, self.system = (0, 1), name, system
+        d = len(basespaces)
+        lead = d - 2                                           # 0: (D, D);  1: (plain, D, D)
+        S0 = basespaces[0] if lead else None
+        Dx, Dy = basespaces[lead], basespaces[lead + 1]
+        self.bc_axis, self.name, self.system = (lead, lead + 1), name, system
         self.basespaces = list(basespaces)
-        self.hom = TensorProduct(Dx.a, Dy.a, system=system, name=name + "0")
-        self.orthogonal = TensorProduct(Dx.orthogonal, Dy.orthogonal, system=system, name=name + "o")
-        sym = {0: sp.Symbol("x", real=True), 1: sp.Symbol("y", real=True)}
+        self.hom = TensorProduct(*([S0] if lead else []), Dx.a, Dy.a, system=system, name=name + "0")
+        self.orthogonal = TensorProduct(*([S0.get_orthogonal()] if lead else []), Dx.orthogonal, Dy.orthogonal, system=system,
+                                        name=name + "o")
+        names_xyz = ["x", "y", "z"][:d]
+        sym = {0: sp.Symbol(names_xyz[lead], real=True), 1: sp.Symbol(names_xyz[lead + 1], real=True)}
+        sym_lead = sp.Symbol(names_xyz[0], real=True) if lead else None
         from .composite import _BC_ORDER, ordered_bc_names
+        # samples of the first factor's coordinate: everything below carries a leading axis of that length (1 in 2-D)
+        S0h = self.hom.basespaces[0] if lead else None
+        xq = np.asarray(S0h.mesh(), dtype=float) if lead else np.zeros(1)
+        nq0 = xq.shape[0]
 
         def as_expr(v, other):
             e = sp.sympify(v)
-            extra = {str(f) for f in e.free_symbols} - {str(sym[other])}
+            allowed = {str(sym[other])} | ({str(sym_lead)} if lead else set())
+            if lead:
+                extra = {str(f) for f in e.free_symbols} - allowed
+                assert not extra, f"boundary value {e} may only depend on {sorted(allowed)}"
+                return e.xreplace({f: (sym_lead if str(f) == str(sym_lead) else sym[other]) for f in e.free_symbols})
+            extra = {str(f) for f in e.free_symbols} - allowed
             assert not extra, f"boundary value {e} may only depend on {sym[other]}"
             return e.xreplace({f: sym[other] for f in e.free_symbols})
 
+        def on_lead(e):
+            """Samples over the first factor's mesh of an expression in its coordinate (a constant in 2-D)."""
+            e = sp.sympify(e)
+            if not e.free_symbols:
+                return np.full(nq0, complex(e) if e.has(sp.I) else float(e))
+            return np.broadcast_to(np.asarray(sp.lambdify(sym_lead, e, modules="numpy")(xq)), (nq0,)).copy()
+
         def functional(D, side, kind, expr, var):
-            """Boundary functional (side, kind) of direction D applied to expr(var): value, or derivative / df^nd."""
+            """Boundary functional (side, kind) of direction D applied to expr(var): value, or derivative / df^nd — sampled
+            over the first factor's mesh."""
             a, b_ = (float(v) for v in D.a.domain)
             z = a if side == "left" else b_
             nd = _BC_ORDER[kind]
             if kind not in ("D",) and kind[0] != "N":
                 raise NotImplementedError("two inhomogeneous directions: Dirichlet / Neumann conditions")
             df = 2.0 / (b_ - a)
-            f = (expr.diff(var, nd) / df**nd if nd else expr).subs(var, z)
-            return complex(f) if sp.sympify(f).has(sp.I) else float(f)
+            return on_lead((expr.diff(var, nd) / df**nd if nd else expr).subs(var, z))
 
         Ds, names = {0: Dx, 1: Dy}, {ax: ordered_bc_names(Ds_.bcs) for ax, Ds_ in ((0, Dx), (1, Dy))}
         data = {ax: [as_expr(v, 1 - ax) for v in Ds[ax].raw_vals] for ax in (0, 1)}
-        # corner values from the x-side data, as the reference (projected_bcs[0]): C[b][c] = functional_c^y (g_b)
-        C = np.array([[functional(Dy, sc, kc, g, sym[1]) for (sc, kc) in names[1]] for g in data[0]])
-        # consistency of the data at the corners: the y-side data must give the same numbers
+        # corner values from the first direction's data, as the reference (projected_bcs[0]): C[b][c] = functional_c (g_b)
+        C = np.array([[functional(Dy, sc, kc, g, sym[1]) for (sc, kc) in names[1]] for g in data[0]])      # [nb, nc, nq0]
+        # consistency of the data at the corners: the second direction's data must give the same numbers
         C2 = np.array([[functional(Dx, sb, kb, h, sym[0]) for h in data[1]] for (sb, kb) in names[0]])
         if not np.allclose(C, C2, rtol=1e-9, atol=1e-11):
             raise ValueError(f"boundary data of the two directions disagree at the corners:\n{C}\nvs\n{C2}")
-        N0, N1 = Dx.N, Dy.N
         rows = {}
         for ax, D in Ds.items():
             R = np.zeros((D.S_bc.shape[0], D.N))
             R[:, :D.S_bc.shape[1]] = D.S_bc
             rows[ax] = R                                          # lifting functions of direction ax in orthogonal coefficients
-        lift = np.einsum("bc,bi,cj->ij", C, rows[0], rows[1])      # corner block
+        lift = np.einsum("bcq,bi,cj->qij", C, rows[0], rows[1])    # corner block, per sample of the first coordinate
         for ax in (0, 1):
             o = 1 - ax
             Do = Ds[o]
@@ -353,17 +379,30 @@ class DirectSumTPS:
             Tf = np.asarray(comp_o._dense_table(L.OP_FORWARD, comp_o.dim, comp_o.num_quad_points, 0))
             St = np.asarray(comp_o.S).T
             for b, g in enumerate(data[ax]):
-                f = sp.lambdify(sym[o], g, modules="numpy")
-                samples = np.broadcast_to(np.asarray(f(xo), dtype=complex if g.has(sp.I) else float), xo.shape).copy()
-                corner = C[b] if ax == 0 else C[:, b]
-                samples = samples - Vo @ (corner @ rows[o])      # minus the other direction's lift of the corner values
-                orth_coeffs = St @ (Tf @ samples)                  # homogeneous part, in orthogonal coefficients
-                lift = lift + (np.outer(rows[0][b], orth_coeffs) if ax == 0 else np.outer(orth_coeffs, rows[1][b]))
+                if lead:
+                    f = sp.lambdify((sym_lead, sym[o]), g, modules="numpy")
+                    vals = f(xq[:, None], xo[None, :])
+                else:
+                    vals = sp.lambdify(sym[o], g, modules="numpy")(xo)[None, :] if g.free_symbols else complex(g) if g.has(sp.I) else float(g)
+                samples = np.broadcast_to(np.asarray(vals, dtype=complex if g.has(sp.I) else float), (nq0, xo.shape[0])).copy()
+                corner = C[b] if ax == 0 else C[:, b]              # [n_other_bcs, nq0]
+                samples = samples - np.einsum("cq,cj,pj->qp", corner, rows[o], Vo)   # minus the other direction's lift of the corners
+                orth_coeffs = np.einsum("jm,mp,qp->qj", St, Tf, samples)             # homogeneous part, orthogonal coefficients
+                lift = lift + (np.einsum("i,qj->qij", rows[0][b], orth_coeffs) if ax == 0
+                               else np.einsum("qi,j->qij", orth_coeffs, rows[1][b]))
+        if lead:
+            # project1D along the first factor (forward transform of the samples), then to its orthogonal coefficients
+            T0 = np.asarray(S0h._dense_table(L.OP_FORWARD, S0h.dim, S0h.num_quad_points, 0))
+            lift = np.tensordot(T0, lift, axes=(1, 0))
+            if not S0h.is_orthogonal:
+                lift = np.tensordot(np.asarray(S0h.S).T, lift, axes=(1, 0))
+        else:
+            lift = lift[0]
         if not self.orthogonal.complex_data and np.iscomplexobj(lift):
             assert np.abs(lift.imag).max() < 1e-14 * max(1.0, np.abs(lift).max())
             lift = lift.real
         self.lift = np.ascontiguousarray(lift)
-        self.corner_values = C
+        self.corner_values = C if lead else C[:, :, 0]
         self._cache = {}
 
     # ---- bookkeeping forwarded to the homogeneous product --------------------------------------------------------

@@ -109,3 +109,28 @@ def test_two_inhomogeneous_directions_on_the_gpu(cuda):
     assert rel(T.backward(dev(cr, cuda)), To.backward(a)) < 1e-12
     assert rel(T.backward_primitive(dev(cr, cuda), (1, 0)), To.backward_primitive(a, (1, 0))) < 1e-11
     assert rel(T.forward(dev(To.backward(a), cuda)), cr) < 1e-10
+
+
+def test_two_inhomogeneous_directions_in_3d_on_the_gpu(cuda):
+    """(Fourier, DirectSum, DirectSum): the 3-D layout of tensorproductspace.py:704-747.  The transforms are the homogeneous
+    3-D product's engine plans plus the host-built lift (tests/test_directsum_tps_host.py checks the lift itself)."""
+    import sympy as sp
+    x, y, z = sp.symbols("x y z", real=True)
+    ue = (sp.cos(x) + 2) * ((y**2 + y) * (z**3 - z) + 3 - 2 * z + sp.Rational(1, 2) * y * z + y)
+    domy, domz = (0.0, 2.0), (-1.0, 1.0)
+    bcy = {"left": {"D": ue.subs(y, domy[0])}, "right": {"N": ue.diff(y).subs(y, domy[1])}}
+    bcz = {"left": {"D": ue.subs(z, domz[0])}, "right": {"D": ue.subs(z, domz[1])}}
+    N = 16
+    T = jf.TensorProduct(jf.Fourier(8), jf.FunctionSpace(N, jf.Legendre, bcy, domain=domy),
+                         jf.FunctionSpace(N, jf.Chebyshev, bcz, domain=domz))
+    To = O.TensorProductSpace(O.Fourier(8), O.Legendre(N, domain=domy), O.Chebyshev(N, domain=domz))
+    X, Y, Z = T.mesh()
+    u = sp.lambdify((x, y, z), ue, "numpy")(X, Y, Z) + 0j
+    c = T.forward(dev(u, cuda))
+    assert tuple(c.shape) == (8, N - 2, N - 2)
+    assert rel(T.backward(c), u) < 1e-12
+    rng = np.random.default_rng(7)
+    cr = rng.standard_normal((8, N - 2, N - 2)) + 1j * rng.standard_normal((8, N - 2, N - 2))
+    a = T.to_orthogonal(dev(cr, cuda)).cpu().numpy()
+    assert rel(T.backward(dev(cr, cuda)), To.backward(a)) < 1e-12
+    assert rel(T.forward(dev(To.backward(a), cuda)), cr) < 1e-10

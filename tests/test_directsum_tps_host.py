@@ -102,9 +102,11 @@ def test_unsupported_layouts_are_refused():
     D = jf.FunctionSpace(8, jf.Legendre, {"left": {"D": sp.sin(x)}, "right": {"D": 0}})
     with pytest.raises(ValueError):
         D.backward(np.zeros(6))                                   # function-valued data need the tensor product
-    Dc = jf.FunctionSpace(8, jf.Legendre, {"left": {"D": 1.0}, "right": {"D": 0}})
+    Dc = jf.FunctionSpace(8, jf.Legendre, {"left": {"D": 1.0}, "right": {"D": 1.0}})
+    with pytest.raises(ValueError):                               # tensorproductspace.py:612-615, with two DirectSums as well
+        jf.TensorProduct(Dc, jf.Fourier(8), Dc)
     with pytest.raises(NotImplementedError):
-        jf.TensorProduct(jf.Fourier(8), Dc, Dc)                   # two inhomogeneous directions in 3-D
+        jf.TensorProduct(Dc, Dc, Dc)
     with pytest.raises(ValueError):                               # tensorproductspace.py:612-615
         jf.TensorProduct(jf.FunctionSpace(8, jf.Legendre, {"left": {"D": 1.0}, "right": {"D": 0}}), jf.Fourier(8), jf.Fourier(8))
 
@@ -155,3 +157,58 @@ def test_two_inhomogeneous_directions(numpy_engine, space):
     bad = {"left": {"D": ue.subs(y, domy[0]) + 1}, "right": {"D": ue.subs(y, domy[1])}}
     with pytest.raises(ValueError):
         jf.TensorProduct(jf.FunctionSpace(N, Sp, bcx, domain=domx), jf.FunctionSpace(N, Sp, bad, domain=domy))
+
+
+@pytest.mark.parametrize("first", ["Fourier", "Legendre", "Composite"])
+def test_two_inhomogeneous_directions_in_3d(numpy_engine, first):
+    """(plain, DirectSum, DirectSum) — the 3-D layout the reference builds for two inhomogeneous directions
+    (tensorproductspace.py:704-747): the data of both directions depend on the first coordinate as well.  The lift takes the
+    prescribed values on all four faces for every x, a function of the space is reproduced, free coefficients keep the faces."""
+    import jaxfun_b200 as jf
+    x, y, z = sp.symbols("x y z", real=True)
+    if first == "Fourier":
+        fx, S0 = sp.cos(x) + sp.Rational(1, 2) * sp.sin(2 * x) + 2, jf.Fourier(8)
+    elif first == "Legendre":
+        fx, S0 = 1 + x - x**3, jf.Legendre(8)
+    else:
+        fx, S0 = (1 - x**2) * (2 + x), jf.FunctionSpace(8, jf.Legendre, {"left": {"D": 0}, "right": {"D": 0}})
+    ue = fx * ((y**2 + y) * (z**3 - z) + 3 - 2 * z + sp.Rational(1, 2) * y * z + z**2 * y**3 + y)
+    domy, domz = (0.0, 2.0), (-1.0, 1.0)
+    bcy = {"left": {"D": ue.subs(y, domy[0])}, "right": {"N": ue.diff(y).subs(y, domy[1])}}
+    bcz = {"left": {"D": ue.subs(z, domz[0])}, "right": {"D": ue.subs(z, domz[1])}}
+    N = 10
+    T = jf.TensorProduct(S0, jf.FunctionSpace(N, jf.Legendre, bcy, domain=domy), jf.FunctionSpace(N, jf.Chebyshev, bcz, domain=domz))
+    assert type(T).__name__ == "DirectSumTPS" and T.num_dofs == (S0.dim, N - 2, N - 2) and T.bc_axis == (1, 2)
+    To = T.orthogonal
+    V = [lambda pts, k=0, s=s: np.asarray(s.evaluate_basis_derivative(np.asarray(s.map_reference_domain(pts)), k)) for s in To.basespaces]
+    xs = np.linspace(0.3, 2.9, 5) if first == "Fourier" else np.linspace(-0.9, 0.8, 5)
+    ys, zs = np.linspace(0, 2, 6), np.linspace(-1, 1, 7)
+    f = sp.lambdify((x, y, z), ue, "numpy")
+    fy = sp.lambdify((x, y, z), ue.diff(y), "numpy")
+
+    def expand(a, X, Y, Z, ky=0):
+        return np.einsum("ijk,pi,qj,rk->pqr", a, V[0](X), V[1](Y, ky), V[2](Z))
+
+    def faces_ok(a, tol):
+        X, Z = np.meshgrid(xs, zs, indexing="ij")
+        assert np.abs(expand(a, xs, np.array([0.0]), zs)[:, 0, :] - f(X, 0.0, Z)).max() < tol
+        dfy = float(To.basespaces[1].domain_factor)
+        assert np.abs(dfy * expand(a, xs, np.array([2.0]), zs, ky=1)[:, 0, :] - fy(X, 2.0, Z)).max() < 10 * tol
+        X, Y = np.meshgrid(xs, ys, indexing="ij")
+        for zb in (-1.0, 1.0):
+            assert np.abs(expand(a, xs, ys, np.array([zb]))[:, :, 0] - f(X, Y, zb)).max() < tol
+
+    faces_ok(T.lift, 1e-10)
+    Xm, Ym, Zm = T.mesh()
+    u = f(Xm, Ym, Zm) + 0 * Xm * Ym * Zm
+    c = T.forward(u)
+    assert c.shape == (S0.dim, N - 2, N - 2)
+    assert rel(T.backward(c), u) < 1e-11                           # ue lies in the space: reproduced
+    rng = np.random.default_rng(1)
+    cr = rng.standard_normal(c.shape) + (1j * rng.standard_normal(c.shape) if first == "Fourier" else 0)
+    a = T.to_orthogonal(cr)
+    faces_ok(a, 1e-9)                                              # the homogeneous part vanishes on the four faces
+    assert rel(T.from_orthogonal(a), cr) < 1e-10
+    bad = {"left": {"D": ue.subs(z, domz[0]) + fx}, "right": {"D": ue.subs(z, domz[1])}}
+    with pytest.raises(ValueError):
+        jf.TensorProduct(S0, jf.FunctionSpace(N, jf.Legendre, bcy, domain=domy), jf.FunctionSpace(N, jf.Chebyshev, bad, domain=domz))
