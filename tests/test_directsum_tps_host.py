@@ -212,3 +212,53 @@ def test_two_inhomogeneous_directions_in_3d(numpy_engine, first):
     bad = {"left": {"D": ue.subs(z, domz[0]) + fx}, "right": {"D": ue.subs(z, domz[1])}}
     with pytest.raises(ValueError):
         jf.TensorProduct(S0, jf.FunctionSpace(N, jf.Legendre, bcy, domain=domy), jf.FunctionSpace(N, jf.Chebyshev, bad, domain=domz))
+
+
+def test_directsumtps_3d_complex_data_as_the_reference_test(numpy_engine):
+    """The space of tests/galerkin/test_tensorproductspace_extra.py:48-81 (`test_directsumtps_poisson_3d`): Fourier x Chebyshev x
+    Chebyshev with COMPLEX Dirichlet data ue = sin(2x) exp(2y + i z) on both inhomogeneous directions.  Its transform assertions:
+    the projection of ue evaluates back to ue (< sqrt(ulp(1))) and forward(backward(uh)) returns uh (< ulp(1000))."""
+    import jaxfun_b200 as jf
+    x, y, z = sp.symbols("x y z", real=True)
+    N = 20
+    ue = sp.sin(2 * x) * sp.exp(2 * y + z * sp.I)
+    bcsy = {"left": {"D": ue.subs(y, -1)}, "right": {"D": ue.subs(y, 1)}}
+    bcsz = {"left": {"D": ue.subs(z, -1)}, "right": {"D": ue.subs(z, 1)}}
+    T = jf.TensorProduct(jf.Fourier(N), jf.FunctionSpace(N, jf.Chebyshev, bcsy), jf.FunctionSpace(N + 2, jf.Chebyshev, bcsz))
+    assert type(T).__name__ == "DirectSumTPS" and np.iscomplexobj(T.lift)
+    X, Y, Z = T.mesh()
+    uej = sp.lambdify((x, y, z), ue, "numpy")(X, Y, Z)
+    uh = T.forward(uej)
+    uj = T.backward(uh)
+    eps = np.finfo(float).eps
+    assert np.linalg.norm(uj - uej) < np.sqrt(eps)
+    assert np.linalg.norm(T.forward(uj) - uh) < 1000 * eps
+    # the lift alone already carries the boundary values: on z = +-1 the homogeneous part vanishes
+    a = T.to_orthogonal(np.zeros_like(uh))
+    k = np.arange(N + 2)
+    for zb, vals in ((-1.0, (-1.0) ** k), (1.0, np.ones(N + 2))):
+        face = T.orthogonal.basespaces[0].backward(T.orthogonal.basespaces[1].backward(a @ vals, axis=1), axis=0)
+        want = sp.lambdify((x, y), ue.subs(z, zb), "numpy")(X[:, :, 0], Y[:, :, 0])
+        assert np.abs(face - want).max() < 1e-11
+
+
+def test_directsumtps_3d_clamped_direction_on_a_mapped_domain(numpy_engine):
+    """The space of `test_directsumtps_biharmonic_dirichlet_3d` (test_tensorproductspace_extra.py:84-135): Dirichlet data in y,
+    Dirichlet + Neumann data (physical units) on both ends of z, both on the domain (-1/2, 1/2), complex values."""
+    import jaxfun_b200 as jf
+    x, y, z = sp.symbols("x y z", real=True)
+    N = 20
+    ue = sp.sin(2 * x) * sp.exp(4 * y + z * sp.I)
+    lo, hi = -0.5, 0.5
+    bcsy = {"left": {"D": ue.subs(y, lo)}, "right": {"D": ue.subs(y, hi)}}
+    bcsz = {"left": {"D": ue.subs(z, lo), "N": ue.diff(z, 1).subs(z, lo)}, "right": {"D": ue.subs(z, hi), "N": ue.diff(z, 1).subs(z, hi)}}
+    T = jf.TensorProduct(jf.Fourier(N), jf.FunctionSpace(N, jf.Chebyshev, bcsy, domain=(lo, hi)),
+                         jf.FunctionSpace(N + 2, jf.Chebyshev, bcsz, domain=(lo, hi)))
+    assert T.num_dofs == (N, N - 2, N - 2)
+    X, Y, Z = T.mesh()
+    uej = sp.lambdify((x, y, z), ue, "numpy")(X, Y, Z)
+    uh = T.forward(uej)
+    uj = T.backward(uh)
+    eps = np.finfo(float).eps
+    assert np.linalg.norm(uj - uej) < np.sqrt(eps)
+    assert np.linalg.norm(T.forward(uj) - uh) < 1000 * eps
