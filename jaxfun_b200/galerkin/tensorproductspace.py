@@ -479,6 +479,11 @@ class DirectSumTPS:
     def evaluate_mesh(self, c, kind: str = "quadrature", N=None):
         return self.orthogonal.evaluate_mesh(self.to_orthogonal(c), kind, N)
 
+    def evaluate(self, x, c):
+        """Expansion (homogeneous part + boundary lift) at scattered points x [n_pts, d] — `DirectSumTPS.evaluate`,
+        tests/galerkin/test_tensorproductspace_more.py:83-99: the orthogonal product evaluates the lifted coefficients."""
+        return self.orthogonal.evaluate(x, self.to_orthogonal(c))
+
 
 def TensorProduct(*basespaces: OrthogonalSpace, system=None, name: str = "T") -> TensorProductSpace:
     """Factory (tensorproductspace.py:507-557): deep-copies the factor spaces; a DirectSum factor makes it a DirectSumTPS."""

@@ -262,3 +262,39 @@ def test_directsumtps_3d_clamped_direction_on_a_mapped_domain(numpy_engine):
     eps = np.finfo(float).eps
     assert np.linalg.norm(uj - uej) < np.sqrt(eps)
     assert np.linalg.norm(T.forward(uj) - uh) < 1000 * eps
+
+
+def test_directsumtps_evaluate_has_no_host_route():
+    """`DirectSumTPS.evaluate` = the orthogonal product's scattered evaluation of the lifted coefficients; like every
+    compute entry point it needs the device."""
+    import torch
+    import jaxfun_b200 as jf
+    from jaxfun_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    x, y = sp.symbols("x y", real=True)
+    ue = sp.exp(-(x**2 + y**2))                                   # test_tensorproductspace_more.py:83-99
+    bcsx = {"left": {"D": ue.subs(x, 0)}, "right": {"D": ue.subs(x, 1)}}
+    bcsy = {"left": {"D": ue.subs(y, 0)}, "right": {"D": ue.subs(y, 1)}}
+    T = jf.TensorProduct(jf.FunctionSpace(16, jf.Legendre, bcsx, domain=(0, 1)), jf.FunctionSpace(16, jf.Legendre, bcsy, domain=(0, 1)))
+    with pytest.raises(_lib.JfxError) as e:
+        T.evaluate(np.array([0.5, 0.5]), np.zeros(T.num_dofs))
+    assert e.value.code == -3
+
+
+def test_directsum_two_inhomogeneous_point_value(numpy_engine):
+    """tests/galerkin/test_tensorproductspace_more.py:83-99: the projection of exp(-(x^2 + y^2)) onto a space with Dirichlet data on
+    all four sides of (0, 1)^2, evaluated at (1/2, 1/2) through the orthogonal expansion of the lifted coefficients, < ulp(100)."""
+    import jaxfun_b200 as jf
+    x, y = sp.symbols("x y", real=True)
+    ue = sp.exp(-(x**2 + y**2))
+    N = 16
+    bcsx = {"left": {"D": ue.subs(x, 0)}, "right": {"D": ue.subs(x, 1)}}
+    bcsy = {"left": {"D": ue.subs(y, 0)}, "right": {"D": ue.subs(y, 1)}}
+    T = jf.TensorProduct(jf.FunctionSpace(N, jf.Legendre, bcsx, domain=(0, 1)), jf.FunctionSpace(N, jf.Legendre, bcsy, domain=(0, 1)))
+    X, Y = T.mesh()
+    uf = T.forward(sp.lambdify((x, y), ue, "numpy")(X, Y))
+    a = T.to_orthogonal(uf)
+    V = [np.asarray(s.eval_basis_functions(np.asarray(s.map_reference_domain(np.array([0.5]))))) for s in T.orthogonal.basespaces]
+    u0 = (V[0] @ a @ V[1].T)[0, 0]
+    assert abs(u0 - float(ue.subs({x: 0.5, y: 0.5}))) < 100 * np.finfo(float).eps
