@@ -15,7 +15,12 @@
 //    there are no transposes, and the solve may be in place;
 //  * one launch does both sweeps; the recurrence window (the last p / q unknowns) lives in registers, and the loads of a
 //    chunk of U steps (right-hand side and matrix entries: independent of the recurrence) are issued together before the
-//    chunk's dependent arithmetic, so a thread has U * (1 + p) loads in flight instead of one.
+//    chunk's dependent arithmetic, so a thread has U * (1 + p) loads in flight instead of one;
+//  * two kernels: `banded_solve_kernel` (one thread per system, any layout, window widths 2 / 4 / 8 or the generic read-back
+//    variant for wider bands) and `banded_solve_rows_kernel` (polynomial axis last, bandwidth <= 4, >= 18 944 systems: one warp
+//    moves [32 rows x 8 steps] tiles through shared memory so that the global accesses are row-contiguous).
+// The per-system bodies live in banded.cuh as __host__ __device__ functions: tools/banded_emul.cpp runs exactly that code on
+// the CPU (tests/test_banded_emul.py).  Measurements and the variants that lost: profiles/r2_banded.txt.
 // HBM-bound: per system and sweep pair, n * (2 * sizeof(rhs element) [read b, write x] + sizeof(rhs element) * 2 [y written
 // and read back, L2-resident for fields <= ~100 MB] + (p + q + 1) * sizeof(band element)) bytes.
 #include <memory>

@@ -1,6 +1,10 @@
-"""Tensor-product Galerkin solves by per-axis diagonalisation — the fast path of
-`jaxfun.la.tpmatrix.TPMatrices.solve(method="lu")` / `tpmats_lu_factor`
-(`src/jaxfun/la/tpmatrix.py:429-587`), SURVEY.md §8(f) rank 3.
+"""Tensor-product Galerkin solves — the factored paths of `jaxfun.la.tpmatrix.TPMatrices.solve(method="lu")`
+(`src/jaxfun/la/tpmatrix.py:386-587`), SURVEY.md §8(f) rank 3:
+
+* `KroneckerSumSolver` / `tpmats_lu_factor`: per-axis diagonalisation (tpmatrix.py:429-587, 1089-1233), described below;
+* `WavenumberBandedSolver` / `tpmats_wavenumber_factor`: one banded LU per Fourier wavenumber combination for Fourier x
+  polynomial operators (tpmatrix.py:590-1014, 1236-1354), assembled, factored and solved in libjfx.so (`jfx_banded_*`);
+* `TPMatrices(terms)`: the reference's dispatch between the two with cached factors (tpmatrix.py:386-427).
 
 A separable operator  sum_i (B_0 x .. x A_i x .. x B_{d-1})  (e.g. the weak Laplacian with stiffness A_i
 and mass B_i per axis) is diagonalised by the generalised eigenvectors A_i V_i = B_i V_i Lambda_i:
