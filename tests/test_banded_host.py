@@ -210,3 +210,29 @@ def test_banded_cabi_argument_checks_and_no_cpu_fallback():
         with pytest.raises(_lib.JfxError) as e:
             S.solve(torch.zeros(4, 8, dtype=torch.complex128))
         assert e.value.code == -3
+
+
+def test_axis_matrices_known_answers():
+    """The per-axis operators `laplace_terms` hands to the solvers, against closed forms: Shen's Legendre-Dirichlet basis
+    phi_k = P_k - P_{k+2} has (phi_j, phi_k'') = -(4k + 6) delta_jk and the pentadiagonal mass 2/(2k+1) + 2/(2k+5), -2/(2k+5);
+    a Fourier axis on (0, 2 pi) has mass 2 pi and second-derivative symbol -k^2 2 pi; on (0, 1) the factors df = 2 pi enter as
+    (1 / df) and df^2 / df."""
+    import jaxfun_b200 as jf
+    from jaxfun_b200.galerkin import tpsolve as S
+    N = 14
+    D = jf.FunctionSpace(N, jf.Legendre, {"left": {"D": 0}, "right": {"D": 0}})
+    A, M = S.stiffness_matrix(D, 2), S.mass_matrix(D)
+    k = np.arange(N - 2)
+    assert np.abs(A - np.diag(-(4.0 * k + 6))).max() < 1e-12
+    Mx = np.diag(2 / (2 * k + 1) + 2 / (2 * k + 5)) + np.diag(-2 / (2 * k[:-2] + 5), 2) + np.diag(-2 / (2 * k[:-2] + 5), -2)
+    assert np.abs(M - Mx).max() < 1e-14
+    offs, data = S.dia_from_dense(M)
+    assert offs == (-2, 0, 2) and np.allclose(data[1], np.diagonal(M)) and np.allclose(data[2][2:], np.diagonal(M, 2))
+    assert np.allclose(data[0][:-2], np.diagonal(M, -2)) and data[0][-2:].tolist() == [0.0, 0.0] and data[2][:2].tolist() == [0.0, 0.0]
+    F = jf.Fourier(8)
+    a, m = S._axis_matrices(F)
+    kk = np.asarray(F.wavenumbers(), dtype=float)
+    assert np.allclose(m, 2 * np.pi) and np.allclose(a, -(kk**2) * 2 * np.pi)
+    F1 = jf.Fourier(8, domain=(0.0, 1.0))
+    a1, m1 = S._axis_matrices(F1)
+    assert np.allclose(m1, 1.0) and np.allclose(a1, -((2 * np.pi * kk) ** 2))
