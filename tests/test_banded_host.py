@@ -236,3 +236,23 @@ def test_axis_matrices_known_answers():
     F1 = jf.Fourier(8, domain=(0.0, 1.0))
     a1, m1 = S._axis_matrices(F1)
     assert np.allclose(m1, 1.0) and np.allclose(a1, -((2 * np.pi * kk) ** 2))
+
+
+def test_plain_c_client_builds_and_refuses_without_a_device(tmp_path):
+    """tools/banded_client.c is a C99 program against include/jfx.h alone (no Python, no torch): it compiles with gcc, links
+    libjfx.so, and on a host without a GPU stops with the library's JFX_ERR_CUDA (exit code 3) instead of computing anything."""
+    import subprocess
+    import torch
+    cuda_home = "/usr/local/cuda"
+    if not os.path.exists(os.path.join(cuda_home, "include", "cuda_runtime_api.h")):
+        pytest.skip("CUDA toolkit headers not found")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "banded_client")
+    subprocess.check_call(["gcc", "-O2", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda_home, "include"),
+                           os.path.join(root, "tools", "banded_client.c"), "-L", os.path.join(root, "jaxfun_b200"), "-ljfx",
+                           "-L", os.path.join(cuda_home, "lib64"), "-lcudart", "-lm",
+                           "-Wl,-rpath," + os.path.join(root, "jaxfun_b200"), "-o", exe])
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the device run of the client is not part of the CPU suite")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stdout
