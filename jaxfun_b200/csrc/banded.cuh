@@ -1,5 +1,5 @@
 // Per-system bodies of the wavenumber-batched banded solver (see kernels_banded.cu for the design).  They are
-// __host__ __device__ so that tools/banded_emul.cu can run exactly this code on the CPU (tests/test_banded_emul.py): the
+// __host__ __device__ so that tools/banded_emul.cpp can run exactly this code on the CPU (tests/test_banded_emul.py): the
 // kernels in kernels_banded.cu are thin wrappers that map one thread to one system (or one band entry).
 #pragma once
 #include <cmath>
